@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the COSKAD anomaly-scoring hot path on B200.
+
+Metric (BASELINE.json): pose windows/sec scored.  Workload at N=1 (configs[1]): hyperbolic STS-GCN
+encoder forward + Poincare distance scoring over 16 Mi synthetic UBnormal-shape windows resident in
+HBM (27.4 GB), processed as `--steps` chunks of `--windows-per-step` windows (one step = one pass of
+the fused kernel over one chunk; consecutive steps walk distinct chunks, each 1.7 GB >> L2).
+Multi-GPU (torchrun, one rank per GPU): windows are sharded, every rank scores its own chunk per
+step (weak scaling) and the scores are all-gathered over NCCL inside the timed region.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU path (the oracle
+port: same ATen ops as models/sts/ae.py + the restated geoopt scoring) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_WINDOW = 3.947e6      # 1 973 496 MAC, reference operation order, D=16
+BYTES_PER_WINDOW = 1636.0      # compulsory HBM bytes: x 1632 + score 4
+TOTAL_WINDOWS = 16 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=16)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--windows-per-step', type=int, default=1024 * 1024)
+    ap.add_argument('--resident-windows', type=int, default=TOTAL_WINDOWS,
+                    help='windows kept resident in HBM per GPU (steps cycle through them)')
+    ap.add_argument('--cpu-sample', type=int, default=4096, help='windows per CPU-baseline pass')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [v.strip() for v in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_path(sample: int, passes: int, warm: int = 1):
+    """The reference's CPU implementation of the path (oracle port), all host threads:
+    STSE forward (models/sts/ae.py:108-121) + project(expmap0) + dist (eval_COSKAD.py:194-196)."""
+    import torch
+    from oracle import geoopt_math as ogm
+    from oracle import stsgcn as onet
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    sd = onet.init_state_dict('stse', latent_dim=16, seed=0)
+    x = onet.synth_windows(sample, seed=999)
+    k = torch.tensor(-1.)
+    c = torch.full((16,), 0.01)
+    times = []
+    with torch.no_grad():
+        for i in range(warm + passes):
+            t0 = time.perf_counter()
+            for lo in range(0, sample, 2048):                       # dataset_batch_size 2048
+                z = onet.stse_forward(x[lo:lo + 2048], sd)
+                s = ogm.dist(ogm.project(ogm.expmap0(z, k=k), k=k), c, k=k)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    return times, ncpu, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    times, ncpu, nthr = cpu_path(args.cpu_sample, args.steps, max(args.warmup, 1))
+    total = sum(times)
+    v = args.cpu_sample * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': 'pose windows/sec scored', 'value': v, 'unit': 'windows/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'hyperbolic STS-GCN encoder fwd + Poincare distance scoring, UBnormal-shape windows '
+                               '(BASELINE configs[1]); CPU reference arm: each step = a bounded sample of '
+                               f'{args.cpu_sample} windows in batches of 2048'},
+        'cpu_baseline': {'value': v, 'unit': 'windows/s', 'cores': nthr, 'kind': 'port',
+                         'sample': f'{args.cpu_sample} windows x {len(times)} passes, host cpu_count {ncpu}'},
+        'e2e': {'value': v, 'unit': 'windows/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from coskad_b200 import _lib
+    from coskad_b200.pipeline import HostScorer
+    from coskad_b200.synth import make_model, synth_windows_
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a B200: no CUDA device visible (there is no CPU fallback for the product path)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    model = make_model('stse', 16, seed=0, device=dev)     # random init, randomised BN statistics
+    W = args.windows_per_step
+    resident = max(W, min(args.resident_windows, TOTAL_WINDOWS))
+    nchunks = resident // W
+    # synthetic UBnormal-shape windows generated on the device, seed 999 + rank
+    g = torch.Generator(device=dev).manual_seed(999 + rank)
+    x = torch.empty((nchunks * W, 2, 12, 17), device=dev, dtype=torch.float32)
+    synth_windows_(x, g, 'ubnormal')
+    # center: gyro-midpoint of the first 65 536 projected embeddings
+    from coskad_b200 import gmath
+    z0, _ = model.encode_score(x[:65536])
+    center = gmath.weighted_midpoint(gmath.expmap0_project(z0))
+    scores = torch.empty(W, device=dev, dtype=torch.float32)
+    gathered = torch.empty(W * world, device=dev, dtype=torch.float32) if world > 1 else None
+    ctx = model._ctx
+
+    def step(i):
+        xi = x[(i % nchunks) * W:((i % nchunks) + 1) * W]
+        model.encode_score(xi, _lib.SCORE_POINCARE, center=center, want_latent=False, score_out=scores)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, scores)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = ctx.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.time()
+    ev[0].record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+        ev[i + 1].record()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = W * world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e through the public host API: pinned host windows -> scores on the host ----------------
+    e2e = None
+    if not args.no_e2e:
+        hs = HostScorer(model, _lib.SCORE_POINCARE, chunk=131072, device=local)
+        xh = torch.empty((W, 2, 12, 17), dtype=torch.float32).pin_memory()
+        xh.copy_(x[:W])
+        oh = torch.empty(W, dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            hs.score(xh, oh, center=center)
+        barrier()
+        n_e2e = max(3, min(args.steps, 8))
+        hs.h2d_bytes = hs.d2h_bytes = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            hs.score(xh, oh, center=center)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {'value': W * world * n_e2e / (float(t.item()) * 1e-3), 'unit': 'windows/s',
+               'h2d_bytes_per_step': hs.h2d_bytes // n_e2e, 'd2h_bytes_per_step': hs.d2h_bytes // n_e2e,
+               'steps': n_e2e, 'note': 'HostScorer: pinned host chunk -> H2D (copy stream) -> fused kernel -> D2H scores'}
+        if rank == 0 and not bool(torch.isfinite(oh).all()):
+            raise SystemExit('non-finite scores in the e2e pass')
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the fused kernel is the only kernel of a step) ------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    import ctypes
+    tf = ctypes.c_double(0.0)
+    ctx.check(ctx.lib.coskad_measure_fp32_peak(ctx.h, ctypes.byref(tf), _lib.stream_ptr(dev)), 'coskad_measure_fp32_peak')
+    fp32_peak_measured = float(tf.value)
+    fp32_peak_derived = 148 * 128 * 2 * float(peaks.get('sm_max_mhz', 1965.0)) * 1e6 / 1e12
+    k_ms = statistics.mean(kern_ms) if world == 1 else total_ms / args.steps
+    ach_tf = FLOP_PER_WINDOW * W / (k_ms * 1e-3) / 1e12
+    ach_gb = BYTES_PER_WINDOW * W / (k_ms * 1e-3) / 1e9
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    roofline = {'bound': 'fp32_fma', 'achieved': ach_tf, 'peak': fp32_peak_measured, 'unit': 'TFLOP/s',
+                'frac': ach_tf / fp32_peak_measured if fp32_peak_measured else None, 'traffic': None,
+                'kernel': 'fused_eval_kernel<false>', 'launch_ms': k_ms,
+                'peak_source': 'measured on this GPU by coskad_measure_fp32_peak (register-resident FFMA loop)',
+                'peak_derived': fp32_peak_derived, 'frac_of_derived': ach_tf / fp32_peak_derived,
+                'flop_per_window': FLOP_PER_WINDOW,
+                'note': 'the fused path is compute bound on the FP32 pipe (2 400 FLOP/B, SURVEY.md 8-d); '
+                        'roofline_hbm gives the HBM view of the same launch'}
+    roofline_hbm = {'bound': 'hbm', 'achieved': ach_gb, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gb / hbm_peak,
+                    'traffic': None, 'bytes_per_window': BYTES_PER_WINDOW,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        times, ncpu, nthr = cpu_path(args.cpu_sample, 3, 1)
+        cpu_baseline = {'value': args.cpu_sample * len(times) / sum(times), 'unit': 'windows/s', 'cores': nthr,
+                        'kind': 'port', 'sample': f'{args.cpu_sample} windows x {len(times)} passes (batches of 2048), '
+                                                   f'host cpu_count {ncpu}'}
+
+    line = {
+        'metric': 'pose windows/sec scored', 'value': value, 'unit': 'windows/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'hyperbolic STS-GCN encoder fwd + Poincare distance scoring, UBnormal-shape windows '
+                               '[2,12,17], channels 2-32-16-32-64, latent 16 (BASELINE configs[1])',
+                   'windows_per_step_per_gpu': W, 'resident_windows_per_gpu': nchunks * W,
+                   'l2_policy': 'inputs larger than L2: each step reads a distinct 1.7 GB chunk',
+                   'parallelism': f'window-sharded x{world}' + (', NCCL all-gather of scores per step' if world > 1 else '')},
+        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'roofline_hbm': roofline_hbm,
+        'cpu_baseline': cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == 'reference' else run_ours(a))

@@ -1,0 +1,211 @@
+"""Frame-level score aggregation: the batched replacement of the Python triple loop in
+eval_COSKAD.py:140-220 (transformation x clip x person, one ``.cpu()`` sync per window upstream)
+and of utils/eval_utils.py:57-106.
+
+``score_and_aggregate`` groups the windows by (transformation, clip, person) once on the host
+(index arithmetic only), then one CUDA launch builds every person's per-frame curve (float64,
+window order = dataset order, bit-exact with numpy's nanmean) and a second one takes the max over
+each clip's persons.  ``pad_scores`` / ``score_process`` / AUC stay on the host with the very same
+scipy / sklearn calls the reference makes (negligible cost, parity "AUC to 4
+decimals").  The reference-named helpers at the bottom keep ``utils.eval_utils``' signatures.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def ranges(nums):                                      # utils/eval_utils.py:210-214
+    nums = sorted(set(nums))
+    gaps = [[s, e] for s, e in zip(nums, nums[1:]) if s + 1 < e]
+    edges = iter(nums[:1] + sum(gaps, []) + nums[-1:])
+    return list(zip(edges, edges))
+
+
+def pad_scores(fig_reconstruction_loss, gt, pad_size):
+    """utils/eval_utils.py:232-248 (host side, in place like upstream)."""
+    zero_interval = set(list(range(len(gt) - 1))) - set(np.nonzero(fig_reconstruction_loss)[0])
+    non_presence_intervals = ranges(zero_interval)
+    nope = []
+    for _, interval in enumerate(non_presence_intervals):
+        start, end = interval
+        if start == 0 and end == len(gt) - 2:
+            continue
+        elif start == 0 and end != len(gt) - 2:
+            nope.append((start, min(end + pad_size, len(gt))))
+        elif start != 0 and end == len(gt) - 2:
+            nope.append((max(start - pad_size, 0), end))
+        elif start != 0 and end != len(gt) - 2:
+            nope.append((max(start - pad_size, 0), min(end + pad_size, len(gt))))
+    for interval in nope:
+        fig_reconstruction_loss[range(interval[0], interval[1])] = 0
+    return fig_reconstruction_loss
+
+
+def score_process(score, win_size=50, dataname='STC', use_scaler=False):
+    """utils/eval_utils.py:200-207: shift by 11 frames, gaussian_filter1d(sigma=30)."""
+    from scipy.ndimage import gaussian_filter1d
+    scores_shifted = np.zeros_like(score)
+    shift = 8 + (8 // 2) - 1
+    scores_shifted[shift:] = score[:-shift]
+    return gaussian_filter1d(scores_shifted, 30)
+
+
+def filter_by_cond(vec, cond):                         # utils/eval_utils.py:171-172
+    return vec[cond]
+
+
+def filter_vectors_by_cond(vecs, cond):                # utils/eval_utils.py:168-169
+    return [filter_by_cond(vec, cond) for vec in vecs]
+
+
+class GroupIndex:
+    """CSR grouping of windows by (transformation, clip, person) -- host index arithmetic only."""
+
+    def __init__(self, trans: np.ndarray, meta: np.ndarray, clips: Sequence[Tuple[int, int, int]], num_transform: int):
+        trans = np.asarray(trans).astype(np.int64).reshape(-1)
+        meta = np.asarray(meta).astype(np.int64)
+        n_clip = len(clips)
+        nfr = np.asarray([int(f) for _, _, f in clips], dtype=np.int64)
+        mult = int(meta[:, 1].max(initial=0)) + 1 + max((c for _, c, _ in clips), default=0)
+        sc = meta[:, 0] * mult + meta[:, 1]
+        if n_clip:
+            keys = np.asarray([s * mult + c for s, c, _ in clips], dtype=np.int64)
+            order = np.argsort(keys)
+            pos = np.clip(np.searchsorted(keys[order], sc), 0, n_clip - 1)
+            cidx = np.where(keys[order][pos] == sc, order[pos], -1)     # (scene, clip) -> clip index, -1 if unknown
+        else:
+            cidx = np.full(len(sc), -1, dtype=np.int64)
+        sel = np.nonzero((cidx >= 0) & (trans >= 0) & (trans < num_transform))[0]
+        gclip = trans[sel] * n_clip + cidx[sel]                       # global clip id: transformation major
+        person = meta[sel, 2]
+        srt = np.lexsort((sel, person, gclip))                        # stable in dataset order inside a person
+        self.win_idx = sel[srt]
+        g, p = gclip[srt], person[srt]
+        new = np.ones(len(srt), dtype=bool)
+        new[1:] = (g[1:] != g[:-1]) | (p[1:] != p[:-1])
+        starts = np.nonzero(new)[0]
+        self.n_persons = len(starts)
+        self.person_off = np.concatenate([starts, [len(srt)]]).astype(np.int64)
+        self.person_clip = g[starts].astype(np.int32)
+        self.person_id = p[starts]
+        self.n_clips = num_transform * n_clip
+        self.clip_frames = np.tile(nfr, num_transform)
+        self.clip_off = np.concatenate([[0], np.cumsum(self.clip_frames)]).astype(np.int64)
+        self.clip_person_off = np.searchsorted(self.person_clip, np.arange(self.n_clips + 1)).astype(np.int64)
+        pf = self.clip_frames[self.person_clip] if self.n_persons else np.zeros(0, dtype=np.int64)
+        self.person_out_off = np.concatenate([[0], np.cumsum(pf)]).astype(np.int64)
+        self.n_clip_per_transform = n_clip
+
+
+def aggregate_curves(score: torch.Tensor, frames, gi: GroupIndex) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(per-person curves, per-clip max curves) as float64 device tensors"""
+    if not score.is_cuda:
+        raise _lib.CoskadError('scores must be a CUDA tensor: the aggregation runs on the B200 (no CPU fallback)')
+    dev = score.device
+    score = score.detach().to(torch.float32).contiguous().view(-1)
+    frames_d = torch.as_tensor(np.ascontiguousarray(frames), dtype=torch.int64).to(dev) if not torch.is_tensor(frames) \
+        else frames.to(device=dev, dtype=torch.int64).contiguous()
+    T = int(frames_d.shape[1])
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+    win_idx, person_off = t(gi.win_idx, torch.int64), t(gi.person_off, torch.int64)
+    person_clip, person_out_off = t(gi.person_clip, torch.int32), t(gi.person_out_off, torch.int64)
+    clip_person_off, clip_off = t(gi.clip_person_off, torch.int64), t(gi.clip_off, torch.int64)
+    total_pf = int(gi.person_out_off[-1])
+    person_out = torch.empty(max(total_pf, 1), dtype=torch.float64, device=dev)
+    out = torch.zeros(max(int(gi.clip_off[-1]), 1), dtype=torch.float64, device=dev)
+    ctx = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    rc = ctx.lib.coskad_frame_aggregate(ctx.h, score.data_ptr(), frames_d.data_ptr(), T, win_idx.data_ptr(),
+                                        person_off.data_ptr(), person_clip.data_ptr(), person_out_off.data_ptr(),
+                                        gi.n_persons, clip_person_off.data_ptr(), clip_off.data_ptr(), gi.n_clips,
+                                        total_pf, int(gi.clip_frames.max(initial=0)), person_out.data_ptr(),
+                                        out.data_ptr(), _lib.stream_ptr(dev))
+    ctx.check(rc, 'coskad_frame_aggregate')
+    return person_out, out
+
+
+def score_and_aggregate(score: torch.Tensor, trans, meta, frames, clips: Sequence[Tuple[int, int, int]],
+                        num_transform: int, pad_size: int = -1, gts: Optional[Dict[Tuple[int, int], np.ndarray]] = None,
+                        smooth: bool = True, masks: Optional[Dict[Tuple[int, int], np.ndarray]] = None
+                        ) -> Dict[int, List[np.ndarray]]:
+    """Per transformation, the list of per-clip frame-score curves (float64), identical to what the
+    loops of eval_COSKAD.py:140-220 produce from the same per-window scores.
+
+    clips: (scene, clip, n_frames) in the sorted gt-file order.  masks: optional boolean frame masks
+    (HR subsets, eval_COSKAD.py:213-215) applied before score_process."""
+    gi = GroupIndex(trans, meta, clips, num_transform)
+    person_out, out = aggregate_curves(score, frames, gi)
+    ncl = gi.n_clip_per_transform
+    res: Dict[int, List[np.ndarray]] = {}
+    if pad_size != -1:
+        pc = person_out.cpu().numpy()
+    oc = out.cpu().numpy()
+    for tr in range(num_transform):
+        curves = []
+        for ci, (scene, clip, F) in enumerate(clips):
+            gc = tr * ncl + ci
+            if pad_size != -1:
+                p0, p1 = int(gi.clip_person_off[gc]), int(gi.clip_person_off[gc + 1])
+                gt = gts[(scene, clip)] if gts is not None else np.zeros(F)
+                per = [pad_scores(pc[gi.person_out_off[p]: gi.person_out_off[p + 1]].copy(), gt, pad_size)
+                       for p in range(p0, p1)]
+                cs = np.amax(np.stack(per, axis=0), axis=0)            # eval_COSKAD.py:211
+            else:
+                cs = oc[gi.clip_off[gc]: gi.clip_off[gc + 1]].copy()
+            if masks is not None and (scene, clip) in masks:
+                cs = cs[masks[(scene, clip)]]
+            if smooth:
+                cs = score_process(cs)
+            curves.append(cs)
+        res[tr] = curves
+    return res
+
+
+# ---- reference-named compat surface (utils/eval_utils.py:41-106) ------------------------------------
+def _scatter(loss: torch.Tensor, frames_fig, n_frames: int) -> np.ndarray:
+    """pose[n, frames_fig[n]-1] = loss[n] as a float64 [w, n_frames] matrix, one D2H copy instead of w."""
+    l = loss.detach().to(torch.float32).cpu().numpy()
+    w = l.shape[0]
+    pose = np.zeros(shape=(w, n_frames))
+    fr = np.asarray(frames_fig)
+    rows = np.repeat(np.arange(w), fr.shape[1])
+    pose[rows, (fr - 1).reshape(-1)] = np.repeat(l, fr.shape[1])
+    return pose
+
+
+def windows_based_loss_hy(hidden_c, hidden_out_fig, frames_fig, n_frames, loss_fn=None, hyperbolic=False):
+    """utils/eval_utils.py:57-74.  hyperbolic: gmath.dist(latents, c); else mean_d loss_fn(c, z) with the
+    reference's MSE (any other loss_fn is rejected: the kernels implement MSE / cosine)."""
+    from . import gmath
+    z = torch.as_tensor(hidden_out_fig).cuda() if not torch.is_tensor(hidden_out_fig) else hidden_out_fig.cuda()
+    c = torch.as_tensor(hidden_c).cuda().view(-1)
+    if hyperbolic:
+        loss = gmath.dist(z, c, k=-1.0)
+    elif loss_fn is None or isinstance(loss_fn, torch.nn.MSELoss):
+        loss = gmath.euclid_score(z, c)
+    else:
+        loss = gmath.cosine_score(z, c)      # eval_COSKAD.py:81 passes the cosine lambda for use_vae
+    return _scatter(loss, frames_fig, n_frames)
+
+
+def windows_based_loss_rec_and_hy(gt_fig, out_fig, hidden_c, hidden_out_fig, frames_fig, n_frames, loss_fn=None,
+                                  rec_loss_weight=0.2, loss_type='rec'):
+    """utils/eval_utils.py:77-106."""
+    from . import gmath
+    assert len(gt_fig.shape) == 4
+    z = torch.as_tensor(hidden_out_fig).cuda()
+    c = torch.as_tensor(hidden_c).cuda().view(-1)
+    w = gt_fig.shape[0]
+    g = torch.as_tensor(gt_fig).cuda().reshape(w, -1)
+    o = torch.as_tensor(out_fig).cuda().reshape(w, -1)
+    loss = gmath.euclid_score(o, g)               # mean over (c,t,v) of (gt - out)^2 -- order independent
+    loss_h = gmath.euclid_score(z, c)
+    if loss_type == 'rec+hyp':
+        loss = loss / rec_loss_weight + loss_h
+    elif loss_type == 'hyp':
+        loss = loss_h
+    return _scatter(loss, frames_fig, n_frames)

@@ -1,0 +1,456 @@
+// abi.cu -- the C ABI of libcoskad_b200.so (see include/coskad_b200.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/coskad_b200.h"
+#include "aggregate.cuh"
+#include "common.cuh"
+#include "fold.cuh"
+#include "fused_eval.cuh"
+#include "latent_ops.cuh"
+#include "train_ops.cuh"
+
+using namespace coskad;
+
+struct coskad_ctx {
+  int device = 0;
+  int sm_count = 0;
+  std::string err;
+  int64_t launches = 0;
+  // packed weights (one allocation each)
+  float* enc_pack = nullptr;
+  float* dec_pack = nullptr;
+  bool enc_set = false, dec_set = false;
+  int head_rows = 0;
+  FusedParams fp{};
+  // scratch
+  int32_t* cnt_scratch = nullptr;
+  size_t cnt_scratch_elems = 0;
+  bool smem_attr_set = false;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(coskad_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_err = buf;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, COSKAD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CK_LAUNCH()                                                                           \
+  do {                                                                                        \
+    ctx->launches++;                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, COSKAD_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static inline size_t align4(size_t n) { return (n + 3) & ~static_cast<size_t>(3); }
+
+extern "C" int coskad_abi_version(void) { return COSKAD_ABI_VERSION; }
+
+extern "C" const char* coskad_last_error(const coskad_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int64_t coskad_launch_count(const coskad_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int coskad_create(coskad_ctx** out, int device, int n_frames, int n_joints) {
+  coskad_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, COSKAD_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n_frames != kT || n_joints != kV)
+    return fail(nullptr, COSKAD_ERR_ARG,
+                "libcoskad_b200 is built for %d frames x %d joints (every reference config); got %d x %d",
+                kT, kV, n_frames, n_joints);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, COSKAD_ERR_NO_DEVICE, "no CUDA device visible: libcoskad_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, COSKAD_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return fail(nullptr, COSKAD_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, COSKAD_ERR_NO_DEVICE, "device %d is sm_%d%d; libcoskad_b200 carries sm_100a code only", device,
+                prop.major, prop.minor);
+  ctx = new coskad_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_destroy(coskad_ctx* ctx) {
+  if (!ctx) return COSKAD_OK;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->enc_pack);
+  cudaFree(ctx->dec_pack);
+  cudaFree(ctx->cnt_scratch);
+  delete ctx;
+  return COSKAD_OK;
+}
+
+// expected channel plan of the fused kernel
+static const int kEncC[5] = {kC0, kC1, kC2, kC3, kC4};
+static const int kDecC[5] = {kC4, kC3, kC2, kC1, kC0};
+
+static int check_layer(coskad_ctx* ctx, const coskad_layer_params& L, int ci, int co, int idx, const char* what) {
+  if (L.c_in != ci || L.c_out != co)
+    return fail(ctx, COSKAD_ERR_ARG, "%s layer %d is %d->%d; the fused sm_100a kernel is built for %d->%d", what, idx,
+                L.c_in, L.c_out, ci, co);
+  if (!L.A || !L.T || !L.w1 || !L.bn1_w || !L.bn1_b || !L.bn1_rm || !L.bn1_rv || !L.prelu)
+    return fail(ctx, COSKAD_ERR_ARG, "%s layer %d has NULL parameters", what, idx);
+  if (L.w2 && (!L.bn2_w || !L.bn2_b || !L.bn2_rm || !L.bn2_rv))
+    return fail(ctx, COSKAD_ERR_ARG, "%s layer %d residual BatchNorm parameters are NULL", what, idx);
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_set_encoder(coskad_ctx* ctx, int n_layers, const coskad_layer_params* L, const float* head_w,
+                                  const float* head_b, int head_rows, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (n_layers != 4) return fail(ctx, COSKAD_ERR_ARG, "encoder must have 4 ST_GCNN layers, got %d", n_layers);
+  if (head_rows < 1 || head_rows > kDP) return fail(ctx, COSKAD_ERR_ARG, "head_rows must be in [1,%d], got %d", kDP, head_rows);
+  if (!L || !head_w) return fail(ctx, COSKAD_ERR_ARG, "NULL weights");
+  for (int i = 0; i < 4; ++i) {
+    int rc = check_layer(ctx, L[i], kEncC[i], kEncC[i + 1], i, "encoder");
+    if (rc) return rc;
+  }
+  CK(cudaSetDevice(ctx->device));
+  // layout: per layer Tw, Aw, Wm ; then head_w[16][F], head_b[16]
+  size_t off = 0, oT[4], oA[4], oW[4];
+  for (int i = 0; i < 4; ++i) {
+    const bool mf = kEncC[i + 1] < kEncC[i];
+    const int K = mf ? kEncC[i] : 2 * kEncC[i], CO = mf ? 2 * kEncC[i + 1] : kEncC[i + 1];
+    oT[i] = off; off += kTwFloats;
+    oA[i] = off; off += kAwFloats;
+    oW[i] = off; off += align4(mix_blob_floats(K, CO));
+  }
+  const size_t oHW = off; off += static_cast<size_t>(kDP) * kF;
+  const size_t oHB = off; off += kDP;
+  if (!ctx->enc_pack) CK(cudaMalloc(&ctx->enc_pack, off * sizeof(float)));
+  for (int i = 0; i < 4; ++i) {
+    const bool mf = kEncC[i + 1] < kEncC[i];
+    fold_layer_kernel<<<8, 256, 0, st>>>(L[i], mf ? 1 : 0, ctx->enc_pack + oT[i], ctx->enc_pack + oA[i], ctx->enc_pack + oW[i]);
+    CK_LAUNCH();
+    ctx->fp.eTw[i] = ctx->enc_pack + oT[i];
+    ctx->fp.eAw[i] = ctx->enc_pack + oA[i];
+    ctx->fp.eWm[i] = ctx->enc_pack + oW[i];
+  }
+  pack_head_kernel<<<64, 256, 0, st>>>(head_w, head_b, head_rows, ctx->enc_pack + oHW, ctx->enc_pack + oHB);
+  CK_LAUNCH();
+  ctx->fp.head_w = ctx->enc_pack + oHW;
+  ctx->fp.head_b = ctx->enc_pack + oHB;
+  ctx->head_rows = head_rows;
+  ctx->enc_set = true;
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_set_decoder(coskad_ctx* ctx, const float* rev_w, const float* rev_b, int latent_dim, int n_layers,
+                                  const coskad_layer_params* L, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (n_layers != 4) return fail(ctx, COSKAD_ERR_ARG, "decoder must have 4 ST_GCNN layers, got %d", n_layers);
+  if (latent_dim != 8 && latent_dim != 16) return fail(ctx, COSKAD_ERR_ARG, "decoder latent_dim must be 8 or 16, got %d", latent_dim);
+  if (!L || !rev_w || !rev_b) return fail(ctx, COSKAD_ERR_ARG, "NULL weights");
+  for (int i = 0; i < 4; ++i) {
+    int rc = check_layer(ctx, L[i], kDecC[i], kDecC[i + 1], i, "decoder");
+    if (rc) return rc;
+  }
+  CK(cudaSetDevice(ctx->device));
+  const int DL = latent_dim;
+  size_t off = 0, oT[3], oA[3], oW[3];
+  const size_t oM = off; off += static_cast<size_t>(kC3) * kP * DL;
+  const size_t om0 = off; off += static_cast<size_t>(kC3) * kP;
+  for (int i = 0; i < 3; ++i) {       // decoder layers 1..3
+    const int ci = kDecC[i + 1], co = kDecC[i + 2];
+    const bool mf = co < ci;
+    const int K = mf ? ci : 2 * ci, CO = mf ? 2 * co : co;
+    oT[i] = off; off += kTwFloats;
+    oA[i] = off; off += kAwFloats;
+    oW[i] = off; off += align4(mix_blob_floats(K, CO));
+  }
+  if (!ctx->dec_pack) CK(cudaMalloc(&ctx->dec_pack, off * sizeof(float)));
+  // layer 0 collapse in float64
+  const int rows = (DL + 1) * kC4;
+  double *In = nullptr, *G1 = nullptr, *G = nullptr;
+  CK(cudaMalloc(&In, sizeof(double) * rows * kP));
+  CK(cudaMalloc(&G1, sizeof(double) * rows * kP));
+  CK(cudaMalloc(&G, sizeof(double) * rows * kP));
+  dec_basis_kernel<<<128, 256, 0, st>>>(rev_w, rev_b, DL, kC4, In);
+  CK_LAUNCH();
+  dec_temporal_kernel<<<128, 256, 0, st>>>(In, L[0].T, rows, G1);
+  CK_LAUNCH();
+  dec_spatial_kernel<<<128, 256, 0, st>>>(G1, L[0].A, rows, G);
+  CK_LAUNCH();
+  dec_mix_kernel<<<128, 256, 0, st>>>(L[0], In, G, DL, ctx->dec_pack + oM, ctx->dec_pack + om0);
+  CK_LAUNCH();
+  float slope0 = 0.f;
+  CK(cudaMemcpyAsync(&slope0, L[0].prelu, sizeof(float), cudaMemcpyDeviceToHost, st));
+  for (int i = 0; i < 3; ++i) {
+    const int ci = kDecC[i + 1], co = kDecC[i + 2];
+    fold_layer_kernel<<<8, 256, 0, st>>>(L[i + 1], co < ci ? 1 : 0, ctx->dec_pack + oT[i], ctx->dec_pack + oA[i], ctx->dec_pack + oW[i]);
+    CK_LAUNCH();
+    ctx->fp.dTw[i] = ctx->dec_pack + oT[i];
+    ctx->fp.dAw[i] = ctx->dec_pack + oA[i];
+    ctx->fp.dWm[i] = ctx->dec_pack + oW[i];
+  }
+  CK(cudaStreamSynchronize(st));
+  cudaFree(In); cudaFree(G1); cudaFree(G);
+  ctx->fp.dM = ctx->dec_pack + oM;
+  ctx->fp.dm0 = ctx->dec_pack + om0;
+  ctx->fp.d_slope0 = slope0;
+  ctx->fp.DL = DL;
+  ctx->dec_set = true;
+  return COSKAD_OK;
+}
+
+static int ensure_smem_attr(coskad_ctx* ctx) {
+  if (ctx->smem_attr_set) return COSKAD_OK;
+  CK(cudaFuncSetAttribute(fused_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  ctx->smem_attr_set = true;
+  return COSKAD_OK;
+}
+
+static int fused_grid(const coskad_ctx* ctx, int64_t B) {
+  const int64_t ntiles = (B + kNW - 1) / kNW;
+  return static_cast<int>(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);   // persistent: one CTA per SM
+}
+
+extern "C" int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float* x, const float* center, int64_t B,
+                                       float* z, float* score, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (!ctx->enc_set) return fail(ctx, COSKAD_ERR_STATE, "coskad_set_encoder has not been called");
+  if (B < 0 || (B > 0 && !x)) return fail(ctx, COSKAD_ERR_ARG, "bad x/B");
+  if (flavour < COSKAD_SCORE_NONE || flavour > COSKAD_SCORE_POINCARE_HM) return fail(ctx, COSKAD_ERR_ARG, "unknown flavour %d", flavour);
+  if (flavour != COSKAD_SCORE_NONE && (!score || !center)) return fail(ctx, COSKAD_ERR_ARG, "score/center is NULL for flavour %d", flavour);
+  if (B == 0) return COSKAD_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_smem_attr(ctx);
+  if (rc) return rc;
+  FusedParams p = ctx->fp;
+  p.x = x; p.center = center; p.z = z; p.score = (flavour == COSKAD_SCORE_NONE) ? nullptr : score;
+  p.xhat = nullptr; p.rec_score = nullptr;
+  p.B = B; p.head_rows = ctx->head_rows; p.flavour = flavour;
+  // the VAE head stacks fc_var under fc_mean: the geometry sees only the latent rows
+  p.D = (ctx->head_rows == 9) ? 8 : ctx->head_rows;
+  fused_eval_kernel<false><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_autoencode_score_fwd(coskad_ctx* ctx, const float* x, const float* center, int64_t B, float* z,
+                                           float* xhat, float* rec_score, float* lat_score, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (!ctx->enc_set || !ctx->dec_set) return fail(ctx, COSKAD_ERR_STATE, "encoder/decoder weights not set");
+  if (ctx->head_rows != ctx->fp.DL) return fail(ctx, COSKAD_ERR_STATE, "encoder head rows (%d) != decoder latent (%d)", ctx->head_rows, ctx->fp.DL);
+  if (B < 0 || (B > 0 && !x)) return fail(ctx, COSKAD_ERR_ARG, "bad x/B");
+  if (lat_score && !center) return fail(ctx, COSKAD_ERR_ARG, "center is NULL");
+  if (B == 0) return COSKAD_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_smem_attr(ctx);
+  if (rc) return rc;
+  FusedParams p = ctx->fp;
+  p.x = x; p.center = center; p.z = z; p.score = lat_score; p.xhat = xhat; p.rec_score = rec_score;
+  p.B = B; p.head_rows = ctx->head_rows; p.D = ctx->head_rows; p.flavour = COSKAD_SCORE_EUCLID;
+  fused_eval_kernel<true><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+// Debug aid for the parity tests: run the first tile of the fused kernel up to `stage` and copy the
+// CTA's activation buffers out: [R0 | R1 | GB | GB2 | zfin] = 2*96*205 + 2*6*205 + 48 floats.
+extern "C" int coskad_debug_fused_stage(coskad_ctx* ctx, int with_decoder, const float* x, int64_t B, int stage,
+                                        float* dbg_out, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (!ctx->enc_set || (with_decoder && !ctx->dec_set)) return fail(ctx, COSKAD_ERR_STATE, "weights not set");
+  if (B < 1 || !x || !dbg_out) return fail(ctx, COSKAD_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_smem_attr(ctx);
+  if (rc) return rc;
+  FusedParams p = ctx->fp;
+  p.x = x; p.center = nullptr; p.z = nullptr; p.score = nullptr; p.xhat = nullptr; p.rec_score = nullptr;
+  p.B = B; p.head_rows = ctx->head_rows; p.D = ctx->head_rows; p.flavour = COSKAD_SCORE_NONE;
+  p.dbg = dbg_out; p.dbg_stage = stage;
+  if (with_decoder) fused_eval_kernel<true><<<1, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  else fused_eval_kernel<false><<<1, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+extern "C" int coskad_debug_fused_floats(void) { return 2 * kRBig + 2 * kRSmall + kNW * kDP; }
+extern "C" int coskad_fused_tile_windows(void) { return kNW; }
+
+// ---- latent ops -----------------------------------------------------------------------------------
+static inline int row_grid(const coskad_ctx* ctx, int64_t B) {
+  int64_t g = (B + kRowWarps - 1) / kRowWarps;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+#define CHECK_BD()                                                                                          \
+  if (!ctx) return COSKAD_ERR_ARG;                                                                          \
+  if (B < 0 || D < 1 || D > 512) return fail(ctx, COSKAD_ERR_ARG, "bad B/D (D must be in [1,512]), got B=%lld D=%d", (long long)B, D); \
+  if (B == 0) return COSKAD_OK;                                                                             \
+  CK(cudaSetDevice(ctx->device));
+
+extern "C" int coskad_geom_map(coskad_ctx* ctx, int op, const float* in, int64_t B, int D, float* out, void* stream_) {
+  CHECK_BD();
+  if (op < 0 || op > COSKAD_MAP_L2NORMALIZE) return fail(ctx, COSKAD_ERR_ARG, "unknown map op %d", op);
+  if (!in || !out) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (D <= 32) geom_map_kernel<1><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(op, in, B, D, out);
+  else if (D <= 128) geom_map_kernel<4><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(op, in, B, D, out);
+  else geom_map_kernel<16><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(op, in, B, D, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_dist(coskad_ctx* ctx, int flavour, const float* a, const float* b, int b_bcast, int64_t B, int D,
+                           float* out, void* stream_) {
+  CHECK_BD();
+  if (flavour < COSKAD_SCORE_POINCARE || flavour > COSKAD_SCORE_POINCARE_HM) return fail(ctx, COSKAD_ERR_ARG, "unknown flavour %d", flavour);
+  if (!a || !b || !out) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (D <= 32) dist_kernel<1><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(flavour, a, b, b_bcast, B, D, out);
+  else if (D <= 128) dist_kernel<4><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(flavour, a, b, b_bcast, B, D, out);
+  else dist_kernel<16><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(flavour, a, b, b_bcast, B, D, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_dist0(coskad_ctx* ctx, const float* x, int64_t B, int D, float* out, void* stream_) {
+  CHECK_BD();
+  if (!x || !out) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (D <= 32) dist0_kernel<1><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(x, B, D, out);
+  else if (D <= 128) dist0_kernel<4><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(x, B, D, out);
+  else dist0_kernel<16><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(x, B, D, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_poincare_score_bwd(coskad_ctx* ctx, const float* z, const float* center, const float* dscore,
+                                         int64_t B, int D, int with_project, float* dz, void* stream_) {
+  CHECK_BD();
+  if (D > 32) return fail(ctx, COSKAD_ERR_ARG, "poincare_score_bwd supports D <= 32");
+  if (!z || !center || !dscore || !dz) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  poincare_score_bwd_kernel<<<row_grid(ctx, B), kRowWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
+      z, center, dscore, B, D, with_project, dz);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_center_partial(coskad_ctx* ctx, int flavour, const float* zproj, int64_t B, int D, double* acc,
+                                     void* stream_) {
+  CHECK_BD();
+  if (D > 128) return fail(ctx, COSKAD_ERR_ARG, "center ops support D <= 128");
+  if (!zproj || !acc) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  int g = row_grid(ctx, B);
+  if (g > ctx->sm_count * 2) g = ctx->sm_count * 2;
+  if (D <= 32) center_partial_kernel<1><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, acc);
+  else center_partial_kernel<4><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, acc);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_center_finalize(coskad_ctx* ctx, int flavour, const double* acc, int D, float eps, float* center,
+                                      void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (D < 1 || D > 128 || !acc || !center) return fail(ctx, COSKAD_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (D <= 32) center_finalize_kernel<1><<<1, 32, 0, st>>>(flavour, acc, D, eps, center);
+  else center_finalize_kernel<4><<<1, 32, 0, st>>>(flavour, acc, D, eps, center);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_frame_aggregate(coskad_ctx* ctx, const float* score, const int64_t* frames, int T,
+                                      const int64_t* win_idx, const int64_t* person_off, const int32_t* person_clip,
+                                      const int64_t* person_out_off, int64_t n_persons, const int64_t* clip_person_off,
+                                      const int64_t* clip_off, int64_t n_clips, int64_t total_person_frames,
+                                      int64_t max_clip_frames, double* person_out, double* out, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (T < 1 || T > 32) return fail(ctx, COSKAD_ERR_ARG, "T must be in [1,32], got %d", T);
+  if (n_persons < 0 || n_clips < 0) return fail(ctx, COSKAD_ERR_ARG, "negative counts");
+  if (n_persons == 0 || n_clips == 0) return COSKAD_OK;
+  if (!score || !frames || !win_idx || !person_off || !person_clip || !person_out_off || !clip_person_off || !clip_off ||
+      !person_out || !out)
+    return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (static_cast<size_t>(total_person_frames) > ctx->cnt_scratch_elems) {
+    CK(cudaStreamSynchronize(st));
+    cudaFree(ctx->cnt_scratch);
+    ctx->cnt_scratch = nullptr;
+    CK(cudaMalloc(&ctx->cnt_scratch, sizeof(int32_t) * static_cast<size_t>(total_person_frames)));
+    ctx->cnt_scratch_elems = static_cast<size_t>(total_person_frames);
+  }
+  const int g1 = static_cast<int>((n_persons + kAggWarps - 1) / kAggWarps);
+  person_curves_kernel<<<g1, kAggWarps * 32, 0, st>>>(score, frames, T, win_idx, person_off, person_clip, n_persons,
+                                                       clip_off, person_out, ctx->cnt_scratch, person_out_off);
+  CK_LAUNCH();
+  if (n_clips > 65535) return fail(ctx, COSKAD_ERR_ARG, "more than 65535 clips per call");
+  int gx = static_cast<int>((max_clip_frames + 255) / 256);
+  if (gx < 1) gx = 1;
+  clip_max_kernel<<<dim3(gx, static_cast<unsigned>(n_clips)), 256, 0, st>>>(person_out, person_out_off, clip_person_off,
+                                                                          clip_off, n_clips, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+// ---- diagnostics -----------------------------------------------------------------------------------
+__global__ void ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = a * static_cast<float>(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += r[i];
+  if (s == 12345.678f) out[0] = s;     // never true; keeps the loop alive
+}
+
+extern "C" int coskad_measure_fp32_peak(coskad_ctx* ctx, double* tflops, void* stream_) {
+  if (!ctx || !tflops) return COSKAD_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  float* d = nullptr;
+  CK(cudaMalloc(&d, 16));
+  const int blocks = ctx->sm_count * 2, threads = 1024, iters = 1 << 15;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  ffma_peak_kernel<<<blocks, threads, 0, st>>>(d, iters, 0.999f, 0.001f);   // warm-up
+  CK_LAUNCH();
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0, st));
+    ffma_peak_kernel<<<blocks, threads, 0, st>>>(d, iters, 0.999f, 0.001f);
+    CK_LAUNCH();
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 16.0 * iters * static_cast<double>(blocks) * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return COSKAD_OK;
+}

@@ -1,0 +1,153 @@
+// latent_ops.cuh -- standalone kernels on latents [B, D]: the gmath namespace, the scores, and the
+// center update.  One warp per latent row, D <= 32*E with E elements per lane.
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+#include "../../include/coskad_b200.h"
+
+namespace coskad {
+
+constexpr int kRowWarps = 8;   // warps (rows) per CTA in the row kernels
+
+template <int E>
+__device__ __forceinline__ void load_row(const float* p, int D, int lane, float (&x)[E]) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) { const int i = lane + 32 * e; x[e] = (i < D) ? p[i] : 0.f; }
+}
+template <int E>
+__device__ __forceinline__ void store_row(float* p, int D, int lane, const float (&x)[E]) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) { const int i = lane + 32 * e; if (i < D) p[i] = x[e]; }
+}
+
+// gmath.expmap0 / project / expmap0+project, hyper_math flavours, L2 normalise
+template <int E>
+__global__ void geom_map_kernel(int op, const float* __restrict__ in, int64_t B, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    float x[E];
+    load_row<E>(in + r * D, D, lane, x);
+    switch (op) {
+      case COSKAD_MAP_EXPMAP0: expmap0(x, geo_geoopt(), false); break;
+      case COSKAD_MAP_PROJECT: project(x, geo_geoopt()); break;
+      case COSKAD_MAP_EXPMAP0_PROJECT: expmap0(x, geo_geoopt(), false); project(x, geo_geoopt()); break;
+      case COSKAD_MAP_EXPMAP0_HM: expmap0(x, geo_hm(), true); break;
+      case COSKAD_MAP_PROJECT_HM: project(x, geo_hm()); break;
+      case COSKAD_MAP_L2NORMALIZE: {     // z / ||z||  (models/sts/vae.py:81, no eps)
+        const float n = sqrtf(vec_sumsq(x));
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = x[e] / n;
+      } break;
+      default: break;
+    }
+    store_row<E>(out + r * D, D, lane, x);
+  }
+}
+
+template <int E>
+__global__ void dist_kernel(int flavour, const float* __restrict__ a, const float* __restrict__ b, int b_bcast,
+                            int64_t B, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    float x[E], y[E];
+    load_row<E>(a + r * D, D, lane, x);
+    load_row<E>(b_bcast ? b : b + r * D, D, lane, y);
+    float s;
+    switch (flavour) {
+      case COSKAD_SCORE_POINCARE:
+      case COSKAD_SCORE_POINCARE_NOPROJ: s = poincare_dist(x, y, geo_geoopt()); break;
+      case COSKAD_SCORE_POINCARE_HM: s = poincare_dist(x, y, geo_hm()); break;
+      case COSKAD_SCORE_EUCLID: s = euclid_score(x, y, D); break;
+      case COSKAD_SCORE_COSINE: s = cosine_score(x, y); break;
+      default: s = 0.f; break;
+    }
+    if (lane == 0) out[r] = s;
+  }
+}
+
+template <int E>
+__global__ void dist0_kernel(const float* __restrict__ x, int64_t B, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    float v[E];
+    load_row<E>(x + r * D, D, lane, v);
+    const float s = 2.f * clamped_artanh(sqrtf(vec_sumsq(v)), 1e-7f);
+    if (lane == 0) out[r] = s;
+  }
+}
+
+// ---- center partial sums ----------------------------------------------------------------------
+// POINCARE (gmath.weighted_midpoint, weights=None): gamma_i = lambda_x(x_i) = 2 / max(1 - |x_i|^2, 1e-15)
+// evaluated in float32 like the reference; the sums over windows run in float64.
+template <int E>
+__global__ void center_partial_kernel(int flavour, const float* __restrict__ z, int64_t B, int D, double* acc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double sx[E], sg = 0.0, sn = 0.0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) sx[e] = 0.0;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + warp; r < B; r += wpg) {
+    float x[E];
+    load_row<E>(z + r * D, D, lane, x);
+    if (flavour == COSKAD_SCORE_POINCARE || flavour == COSKAD_SCORE_POINCARE_NOPROJ) {
+      const float ss = vec_sumsq(x);
+      const float gamma = 2.f / fmaxf(1.f - ss, 1e-15f);
+#pragma unroll
+      for (int e = 0; e < E; ++e) sx[e] += static_cast<double>(gamma * x[e]);
+      sg += static_cast<double>(gamma - 1.f);
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) sx[e] += static_cast<double>(x[e]);
+    }
+    sn += 1.0;
+  }
+  // CTA reduce (per lane slot) then one atomic per element per CTA
+  __shared__ double red[kRowWarps][32 * E + 2];
+#pragma unroll
+  for (int e = 0; e < E; ++e) red[warp][lane + 32 * e] = sx[e];
+  if (lane == 0) { red[warp][32 * E] = sg; red[warp][32 * E + 1] = sn; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * E + 2; i += blockDim.x) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kRowWarps; ++w) s += red[w][i];
+    if (i < 32 * E) { if (i < D) atomicAdd(acc + i, s); }
+    else atomicAdd(acc + D + (i - 32 * E), s);
+  }
+}
+
+// single warp
+template <int E>
+__global__ void center_finalize_kernel(int flavour, const double* __restrict__ acc, int D, float eps, float* center) {
+  const int lane = threadIdx.x & 31;
+  const double cnt = acc[D + 1];
+  float m[E];
+  if (flavour == COSKAD_SCORE_POINCARE || flavour == COSKAD_SCORE_POINCARE_NOPROJ) {
+    // two_mean = num / clamp_abs(den, 1e-10); mobius_scalar_mul(0.5, two_mean)
+    const float den = static_cast<float>(acc[D]);
+    const float dena = (den >= 0.f ? 1.f : -1.f) * (fabsf(den) + 1e-10f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const int i = lane + 32 * e; m[e] = (i < D) ? static_cast<float>(acc[i]) / dena : 0.f; }
+    const float n = fmaxf(sqrtf(vec_sumsq(m)), 1e-15f);
+    const float th = clamped_tanh(0.5f * clamped_artanh(n, 1e-7f));
+#pragma unroll
+    for (int e = 0; e < E; ++e) m[e] = th * (m[e] / n);
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = lane + 32 * e;
+      float c = (i < D && cnt > 0.0) ? static_cast<float>(acc[i] / cnt) : 0.f;
+      if (flavour == COSKAD_SCORE_EUCLID && eps > 0.f) {   // euclidean_encoder_staticCenter.py:121-122
+        if (fabsf(c) < eps && c < 0.f) c = -eps;
+        if (fabsf(c) < eps && c > 0.f) c = eps;
+      }
+      m[e] = c;
+    }
+  }
+  store_row<E>(center, D, lane, m);
+}
+
+}  // namespace coskad

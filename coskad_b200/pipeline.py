@@ -1,0 +1,73 @@
+"""Public end-to-end scoring API: host pose windows in, anomaly scores out.
+
+``score_windows_host`` is the call a user of the drop-in makes with data that lives on the host
+(what eval_COSKAD.py:115-120 does with a DataLoader + ``predict`` + ``light_processing_data``):
+pinned host windows are streamed to the B200 in chunks on a copy stream while the fused kernel
+scores the previous chunk on the compute stream, and the scores come back to pinned host memory.
+``shard_range`` is the window partition used by every multi-GPU entry point (contiguous blocks in
+dataset order).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous block of ceil(n/world) windows per rank, dataset order (last ranks may be short/empty)"""
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+class HostScorer:
+    """Double-buffered H2D -> fused kernel -> D2H pipeline around ``STSE.encode_score``."""
+
+    def __init__(self, model, flavour: int = _lib.SCORE_POINCARE, chunk: int = 131072, device: Optional[int] = None):
+        self.model, self.flavour, self.chunk = model, flavour, int(chunk)
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        shape = (self.chunk, model.input_dim, model.n_frames, model.n_joints)
+        self.dbuf = [torch.empty(shape, device=self.device, dtype=torch.float32) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.ready = [torch.cuda.Event() for _ in range(2)]     # H2D of buffer i done
+        self.free = [torch.cuda.Event() for _ in range(2)]      # kernel reading buffer i done
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    @torch.no_grad()
+    def score(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+              center: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x_host [N,C,T,V] float32 (pinned for full overlap) -> scores [N] float32 on the host"""
+        assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        N = x_host.shape[0]
+        if out_host is None:
+            out_host = torch.empty(N, dtype=torch.float32).pin_memory()
+        comp = torch.cuda.current_stream(self.device)
+        dscore = torch.empty(N, device=self.device, dtype=torch.float32)
+        nchunks = (N + self.chunk - 1) // self.chunk
+        for b in range(2):
+            self.free[b].record(comp)
+        for i in range(nchunks):
+            b = i & 1
+            lo, hi = i * self.chunk, min((i + 1) * self.chunk, N)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.free[b])
+                self.dbuf[b][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                self.ready[b].record(self.copy_stream)
+            comp.wait_event(self.ready[b])
+            self.model.encode_score(self.dbuf[b][: hi - lo], self.flavour, center=center, want_latent=False,
+                                    score_out=dscore[lo:hi])
+            self.free[b].record(comp)
+            self.h2d_bytes += (hi - lo) * x_host[0].numel() * 4
+        out_host.copy_(dscore, non_blocking=True)
+        self.d2h_bytes += N * 4
+        comp.synchronize()
+        return out_host
+
+
+def score_windows_host(model, x_host: torch.Tensor, flavour: int = _lib.SCORE_POINCARE, chunk: int = 131072,
+                       center: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return HostScorer(model, flavour, chunk).score(x_host, center=center)

@@ -1,0 +1,187 @@
+/* coskad_b200.h -- C ABI of libcoskad_b200.so (hand-written sm_100a CUDA kernels for the
+ * COSKAD anomaly-scoring hot path).
+ *
+ * The reference (aleflabo/COSKAD) is pure Python: it has no FFI layer.  Each entry point below
+ * therefore replaces a *Python call site* of the reference; the citation after "replaces:" is
+ * the reference file:line whose arithmetic the entry point reproduces.  The Python binding a
+ * maintainer would add is a ctypes stub -- see INTEGRATION.md and coskad_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 (COSKAD_OK) or a negative coskad_status; it never throws/exits;
+ *     coskad_last_error(ctx) gives a human readable message for the last failure on that ctx.
+ *   - all data pointers are DEVICE pointers on the ctx's device unless the name ends in _host;
+ *     the caller owns every buffer; the library owns only the ctx (packed weights, scratch).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *     asynchronous with respect to the host and ordered on that stream.
+ *   - a ctx is not thread-safe: one ctx per (device, host thread).
+ *   - layouts are the reference's: windows x[B, C, T, V] float32 contiguous (NCHW with
+ *     C = coordinates, T = frames, V = joints), latents z[B, D] float32, scores [B] float32.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef COSKAD_B200_H_
+#define COSKAD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COSKAD_ABI_VERSION 1
+
+typedef struct coskad_ctx coskad_ctx;
+
+typedef enum {
+  COSKAD_OK = 0,
+  COSKAD_ERR_ARG = -1,        /* bad argument / unsupported shape */
+  COSKAD_ERR_CUDA = -2,       /* CUDA runtime error (message in coskad_last_error) */
+  COSKAD_ERR_STATE = -3,      /* weights not set, wrong call order */
+  COSKAD_ERR_NO_DEVICE = -4   /* no usable sm_100 device */
+} coskad_status;
+
+/* Latent geometry / score flavour. */
+typedef enum {
+  COSKAD_SCORE_NONE = 0,        /* no score, latent only                                        */
+  COSKAD_SCORE_POINCARE = 1,    /* project(expmap0(z)) then dist(x, c), geoopt 0.5.0 constants,
+                                   k=-1.  replaces: eval_COSKAD.py:194-196 + utils/eval_utils.py:66-67 */
+  COSKAD_SCORE_POINCARE_NOPROJ = 2, /* expmap0 only (validation path) replaces: models/hyperbolic_encoder.py:266 */
+  COSKAD_SCORE_EUCLID = 3,      /* mean_d (c_d - z_d)^2        replaces: utils/eval_utils.py:61-64   */
+  COSKAD_SCORE_COSINE = 4,      /* 1 - cos(c, z)               replaces: eval_COSKAD.py:81           */
+  COSKAD_SCORE_POINCARE_HM = 5  /* utils/hyper_math.py constants (c=+1): expmap0 :302-306,
+                                   project :100-105, dist :207-210 (dead code upstream; pinned oracle) */
+} coskad_flavour;
+
+/* One ST_GCNN_layer's parameters (device pointers, float32), reference names in comments.
+ * replaces: models/graph_layers/stsgcn.py:47-91 (module state) */
+typedef struct {
+  int32_t c_in, c_out;
+  const float* A;        /* gcn.A            [T, V, V]                 stsgcn.py:134 */
+  const float* T;        /* gcn.T            [V, T, T]                 stsgcn.py:138 */
+  const float* w1;       /* tcn.0.weight     [c_out, c_in] (1x1 conv)  stsgcn.py:57  */
+  const float* b1;       /* tcn.0.bias       [c_out] or NULL                         */
+  const float* bn1_w;    /* tcn.1.weight / bias / running_mean / running_var [c_out] */
+  const float* bn1_b;
+  const float* bn1_rm;
+  const float* bn1_rv;
+  const float* w2;       /* residual.0.weight [c_out, c_in]; NULL => nn.Identity (stsgcn.py:80) */
+  const float* b2;       /* residual.0.bias or NULL                                  */
+  const float* bn2_w;    /* residual.1.*                                             */
+  const float* bn2_b;
+  const float* bn2_rm;
+  const float* bn2_rv;
+  const float* prelu;    /* prelu.weight [1]                            stsgcn.py:82 */
+} coskad_layer_params;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int coskad_abi_version(void);
+/* n_frames / n_joints: the fused sm_100a kernels are built for the shapes every reference
+ * config uses (12 frames, 17 joints); other shapes are rejected with COSKAD_ERR_ARG. */
+int coskad_create(coskad_ctx** out, int device, int n_frames, int n_joints);
+int coskad_destroy(coskad_ctx* ctx);
+const char* coskad_last_error(const coskad_ctx* ctx);   /* ctx may be NULL: last create() error */
+
+/* ---- weights ------------------------------------------------------------------------------
+ * Encoder = n_layers ST_GCNN layers + a linear head of `head_rows` rows over the flattened
+ * (c,t,v) features.  For STSE/STSAE the head is btlnk (head_rows = latent_dim); for STSVAE it is
+ * fc_mean stacked on fc_var (head_rows = latent_dim + 1).  Eval-mode BatchNorm is folded into
+ * the 1x1 convolutions on the device, in float64, at this call.
+ * replaces: models/sts/ae.py:60-72,147-157 (module construction) + nn.Module.eval() semantics */
+int coskad_set_encoder(coskad_ctx* ctx, int n_layers, const coskad_layer_params* layers_host,
+                       const float* head_w /*[head_rows, F]*/, const float* head_b /*[head_rows] or NULL*/,
+                       int head_rows, void* stream);
+/* Decoder = rev_btlnk Linear(latent -> F) + n_layers ST_GCNN layers.
+ * replaces: models/sts/ae.py:200-230 */
+int coskad_set_decoder(coskad_ctx* ctx, const float* rev_w /*[F, latent]*/, const float* rev_b /*[F]*/,
+                       int latent_dim, int n_layers, const coskad_layer_params* layers_host, void* stream);
+
+/* ---- fused eval hot path ------------------------------------------------------------------
+ * x[B,2,12,17] -> 4 fused ST_GCNN layers -> head -> geometry -> score, one persistent kernel;
+ * activations never leave the SM.  z (nullable) receives the raw head output [B, head_rows];
+ * score (nullable iff flavour NONE) receives [B].  center: [latent] device pointer.
+ * replaces: STSE.forward models/sts/ae.py:108-121 (+ the per-person scoring in eval_COSKAD.py:186-199) */
+int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float* x, const float* center,
+                            int64_t B, float* z, float* score, void* stream);
+/* Euclidean auto-encoder: also runs the decoder and the reconstruction score.
+ * xhat (nullable) [B,2,12,17]; rec_score (nullable) [B] = mean_{c,t,v}(x - xhat)^2;
+ * lat_score (nullable) [B] = mean_d (c_d - z_d)^2.
+ * replaces: STSAE.forward models/sts/ae.py:233-250 + utils/eval_utils.py:77-90 */
+int coskad_autoencode_score_fwd(coskad_ctx* ctx, const float* x, const float* center, int64_t B,
+                                float* z, float* xhat, float* rec_score, float* lat_score, void* stream);
+
+/* ---- geometry on latents (the gmath namespace) -------------------------------------------
+ * op codes for coskad_geom_map: z[B,D] -> out[B,D] */
+typedef enum {
+  COSKAD_MAP_EXPMAP0 = 0,          /* gmath.expmap0(u, k=-1)                  */
+  COSKAD_MAP_PROJECT = 1,          /* gmath.project(x, k=-1)                  */
+  COSKAD_MAP_EXPMAP0_PROJECT = 2,  /* project(expmap0(u))                     */
+  COSKAD_MAP_EXPMAP0_HM = 3,       /* utils/hyper_math.py expmap0 (c=1)       */
+  COSKAD_MAP_PROJECT_HM = 4,       /* utils/hyper_math.py project (c=1)       */
+  COSKAD_MAP_L2NORMALIZE = 5       /* z / ||z||   (models/sts/vae.py:81)      */
+} coskad_map_op;
+int coskad_geom_map(coskad_ctx* ctx, int op, const float* in, int64_t B, int D, float* out, void* stream);
+/* Pairwise-broadcast distance/score between a[B,D] and b (b_is_broadcast: b is [D], else [B,D]).
+ * flavour POINCARE: gmath.dist(a, b, k=-1); POINCARE_HM: hyper_math.dist; EUCLID: mean (b-a)^2;
+ * COSINE: 1 - cos(b, a).  replaces: geoopt stereographic math dist / utils/eval_utils.py:61-67 */
+int coskad_dist(coskad_ctx* ctx, int flavour, const float* a, const float* b, int b_is_broadcast,
+                int64_t B, int D, float* out, void* stream);
+/* dist0(x) = 2 artanh(||x||).   replaces: models/hyperbolic_encoder.py:181 */
+int coskad_dist0(coskad_ctx* ctx, const float* x, int64_t B, int D, float* out, void* stream);
+/* backward of score = dist(project?(expmap0(z)), c) w.r.t. z (training loss, hyperbolic_encoder.py:147-157),
+ * arg order dist(c, x) as in training. dz[B,D] = dscore[B] * d score/d z. */
+int coskad_poincare_score_bwd(coskad_ctx* ctx, const float* z, const float* center, const float* dscore,
+                              int64_t B, int D, int with_project, float* dz, void* stream);
+
+/* ---- center update -------------------------------------------------------------------------
+ * acc is [D+2] float64 on the device and is ACCUMULATED into (zero it first):
+ *   POINCARE: acc[0..D) += sum gamma_i x_i, acc[D] += sum (gamma_i - 1), acc[D+1] += count
+ *   EUCLID / COSINE: acc[0..D) += sum z_i, acc[D+1] += count
+ * Partial sums from several shards/ranks add (all-reduce them), then finalize once.
+ * replaces: gmath.weighted_midpoint models/hyperbolic_encoder.py:122,179; the running sums of
+ * models/euclidean_encoder_staticCenter.py:105-124; models/spherical_vae.py:110-116 */
+int coskad_center_partial(coskad_ctx* ctx, int flavour, const float* zproj, int64_t B, int D, double* acc, void* stream);
+/* eps: center_tolerance clamp of the Euclidean flavour (<=0 disables). */
+int coskad_center_finalize(coskad_ctx* ctx, int flavour, const double* acc, int D, float eps, float* center, void* stream);
+
+/* ---- frame-level aggregation ---------------------------------------------------------------
+ * Bit-exact replacement of the Python triple loop: for each person scatter score -> frames
+ * (index frames-1 with the reference's wrap of frame id 0 -> last frame), treat exact zeros as
+ * absent, float64 mean in window (dataset) order, then max over the clip's persons.
+ *   score[N] f32; frames[N,T] i64 (1-based frame ids);
+ *   win_idx[*] i64  window ids grouped by person, dataset order inside a person;
+ *   person_off[n_persons+1] i64  CSR offsets into win_idx;
+ *   person_clip[n_persons] i32   clip of each person; persons of one clip are contiguous;
+ *   person_out_off[n_persons+1] i64  offsets of each person's curve in person_out
+ *                                (person p owns n_frames(clip(p)) doubles);
+ *   clip_person_off[n_clips+1] i64   CSR offsets: persons of clip c;
+ *   clip_off[n_clips+1] i64      clip c owns out[clip_off[c] .. clip_off[c+1]), n_frames(c) long;
+ *   total_person_frames = person_out_off[n_persons]; max_clip_frames = max_c n_frames(c);
+ *   person_out f64 (per-person curves, always written), out f64 (per-clip per-frame scores).
+ * A clip without persons yields zeros (the reference raises on np.stack of an empty list).
+ * replaces: utils/eval_utils.py:69-74 + eval_COSKAD.py:201-211 */
+int coskad_frame_aggregate(coskad_ctx* ctx, const float* score, const int64_t* frames, int T,
+                           const int64_t* win_idx, const int64_t* person_off, const int32_t* person_clip,
+                           const int64_t* person_out_off, int64_t n_persons,
+                           const int64_t* clip_person_off, const int64_t* clip_off, int64_t n_clips,
+                           int64_t total_person_frames, int64_t max_clip_frames,
+                           double* person_out, double* out, void* stream);
+
+/* ---- training path (per-layer kernels, train-mode BatchNorm) -----------------------------------
+ * declared in the second half of this header once implemented: see coskad_train_* below. */
+
+/* ---- diagnostics ---------------------------------------------------------------------------- */
+/* Sustained FP32-FMA rate of the device (TFLOP/s) from a register-resident FFMA loop; used by
+ * bench.py as the measured denominator of the FP32 roofline. */
+int coskad_measure_fp32_peak(coskad_ctx* ctx, double* tflops, void* stream);
+/* test aid: run tile 0 of the fused kernel up to `stage` (S0..S23 of fused_eval.cuh) and dump the
+ * CTA's shared-memory activations; coskad_debug_fused_floats() floats are written to dbg_out. */
+int coskad_debug_fused_stage(coskad_ctx* ctx, int with_decoder, const float* x, int64_t B, int stage,
+                             float* dbg_out, void* stream);
+int coskad_debug_fused_floats(void);
+int coskad_fused_tile_windows(void);
+/* number of kernel launches issued through this ctx since creation */
+int64_t coskad_launch_count(const coskad_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSKAD_B200_H_ */

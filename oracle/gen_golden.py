@@ -1,0 +1,186 @@
+"""Pin the oracle against the REAL reference and write the golden fixtures under tests/golden/.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+    python oracle/gen_golden.py
+What it does
+  1. imports the reference's own modules (models.sts.ae.STSE / STSAE, utils.hyper_math,
+     utils.model_utils, utils.eval_utils) from /root/reference -- third-party imports that are
+     missing here (matplotlib, geoopt) are stubbed with empty modules, and ``Tensor.cuda`` is made
+     a no-op, ONLY so that the reference's own aggregation / scoring functions can run on CPU;
+  2. checks every oracle restatement against them (asserts);
+  3. stores small input/output vectors of the REFERENCE (not of the oracle) as .npz fixtures.
+The reference ships no tests or golden vectors of its own, so these
+reference-generated vectors are the pin.  geoopt and power_spherical are not importable and not
+vendored: oracle.geoopt_math / oracle.power_spherical stay "parity unpinned".
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _stub(name: str) -> types.ModuleType:
+    mod = types.ModuleType(name)
+    sys.modules[name] = mod
+    return mod
+
+
+def main() -> None:
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(4)
+    from oracle import aggregate as oagg
+    from oracle import geoopt_math as ogm
+    from oracle import hyper_math as ohm
+    from oracle import stsgcn as onet
+
+    # ---- the real reference modules -------------------------------------------------------------
+    import models.sts.ae as ref_ae            # noqa: E402  (reference)
+    import utils.hyper_math as ref_hm         # noqa: E402
+    import utils.model_utils as ref_mu        # noqa: E402
+
+    # -- STSE (hyperbolic / euclidean encoder configs: latent 16)
+    sd = onet.init_state_dict('stse', latent_dim=16, seed=0)
+    ref = ref_ae.STSE(input_dim=2, layer_channels=[32, 16, 32], hidden_dimension=64, latent_dim=16, n_frames=12,
+                      n_joints=17, encoder_type='sts_gcn', projector='linear', distance='euclidean', dropout=0.0)
+    missing = ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    x = onet.synth_windows(10, seed=999)
+    with torch.no_grad():
+        z_ref = ref(x)
+        h1_ref = ref.encoder.model[0](x)
+        z_or = onet.stse_forward(x, sd)
+        h1_or = onet.st_gcnn_layer(x, sd, 'encoder.model.0')
+    assert torch.equal(z_ref, z_or) or (z_ref - z_or).abs().max() < 1e-6, (z_ref - z_or).abs().max()
+    assert (h1_ref - h1_or).abs().max() < 1e-6
+    # eval-mode fold used by the CUDA path
+    w1, w2, b = onet.fold_layer_eval(sd, 'encoder.model.0')
+    g = onet.graph_contract(x, sd['encoder.model.0.gcn.A'], sd['encoder.model.0.gcn.T'])
+    pre = torch.einsum('oc,nctv->notv', w1, g) + torch.einsum('oc,nctv->notv', w2, x) + b[None, :, None, None]
+    h1_fold = torch.nn.functional.prelu(pre, sd['encoder.model.0.prelu.weight'])
+    assert (h1_fold - h1_ref).abs().max() < 2e-5
+    np.savez(os.path.join(GOLD, 'stse_ref.npz'), x=x.numpy(), z=z_ref.numpy(), h1=h1_ref.numpy(),
+             sd_checksum=np.float64(sum(float(v.double().sum()) for k, v in sd.items() if v.is_floating_point())))
+
+    # training-mode forward + backward of the reference (loss = mean of z^2 as a stand-in upstream grad)
+    ref.train()
+    xt = onet.synth_windows(64, seed=7)
+    zt = ref(xt)
+    loss = (zt ** 2).mean()
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    new_stats = {}
+    zt_or = onet.stse_forward(xt, sd, training=True, new_stats=new_stats)
+    assert (zt - zt_or).abs().max() < 1e-5
+    ref_sd_after = ref.state_dict()
+    for k, v in new_stats.items():
+        assert (ref_sd_after[k] - v).abs().max() < 1e-6, k
+    np.savez(os.path.join(GOLD, 'stse_train_ref.npz'), x=xt.numpy(), z=zt.detach().numpy(),
+             **{'grad.' + k: v.numpy() for k, v in grads.items() if k in (
+                 'encoder.model.0.gcn.A', 'encoder.model.0.gcn.T', 'encoder.model.3.tcn.0.weight',
+                 'encoder.model.1.tcn.1.weight', 'encoder.model.2.prelu.weight', 'btlnk.bias',
+                 'encoder.model.1.residual.0.bias')},
+             **{'stat.' + k: ref_sd_after[k].numpy() for k in ('encoder.model.0.tcn.1.running_mean',
+                                                               'encoder.model.3.residual.1.running_var')})
+    # calc_reg_loss
+    reg_ref = ref_mu.calc_reg_loss(ref)
+    reg_or = onet.calc_reg_loss(list(ref.named_parameters()))
+    assert abs(float(reg_ref) - float(reg_or)) < 1e-6 * abs(float(reg_ref))
+
+    # -- STSAE (euclidean auto-encoder config: latent 8)
+    sd_ae = onet.init_state_dict('stsae', latent_dim=8, seed=1)
+    ref_aem = ref_ae.STSAE(input_dim=2, layer_channels=[32, 16, 32], hidden_dimension=64, latent_dim=8, n_frames=12,
+                           n_joints=17, encoder_type='sts_gcn', projector='linear', distance='euclidean', dropout=0.0)
+    ref_aem.load_state_dict(sd_ae, strict=True)
+    ref_aem.eval()
+    with torch.no_grad():
+        z_ae, xh_ae = ref_aem(x)
+        z_ae_or, xh_ae_or = onet.stsae_forward(x, sd_ae)
+    assert (z_ae - z_ae_or).abs().max() < 1e-6 and (xh_ae - xh_ae_or).abs().max() < 1e-6
+    np.savez(os.path.join(GOLD, 'stsae_ref.npz'), x=x.numpy(), z=z_ae.numpy(), xhat=xh_ae.numpy())
+
+    # ---- utils/hyper_math.py (the pinned geometry flavour) ----------------------------------------
+    g_ = torch.Generator().manual_seed(5)
+    u = torch.randn(64, 16, generator=g_) * torch.logspace(-3, 0.7, 64)[:, None]
+    cen = torch.randn(16, generator=g_) * 0.1
+    e_ref = ref_hm.expmap0(u, c=1.0)
+    p_ref = ref_hm.project(e_ref, c=1.0)
+    d_ref = ref_hm.dist(p_ref, cen.expand_as(p_ref), c=1.0)
+    m_ref = ref_hm.poincare_mean(p_ref[:40] * 0.5, dim=0, c=1.0)
+    assert torch.allclose(e_ref, ohm.expmap0(u)) and torch.allclose(p_ref, ohm.project(e_ref))
+    assert torch.allclose(d_ref, ohm.dist(p_ref, cen.expand_as(p_ref)), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(m_ref, ohm.poincare_mean(p_ref[:40] * 0.5), rtol=1e-6, atol=1e-7)
+    np.savez(os.path.join(GOLD, 'geometry_hyper_math.npz'), u=u.numpy(), center=cen.numpy(), expmap0=e_ref.numpy(),
+             project=p_ref.numpy(), dist=d_ref.numpy(), mean=m_ref.numpy())
+    # restated geoopt (UNPINNED) -- stored so the CUDA tests have fixed vectors; these are oracle outputs
+    k = torch.tensor(-1.)
+    e_g = ogm.expmap0(u, k=k)
+    p_g = ogm.project(e_g, k=k)
+    np.savez(os.path.join(GOLD, 'geometry_geoopt_restated.npz'), u=u.numpy(), center=cen.numpy(), expmap0=e_g.numpy(),
+             project=p_g.numpy(), dist=ogm.dist(p_g, cen, k=k).numpy(), dist_cx=ogm.dist(cen, p_g, k=k).numpy(),
+             dist0=ogm.dist0(p_g, k=k).numpy(), midpoint=ogm.weighted_midpoint(p_g, k=k).numpy())
+
+    # ---- utils/eval_utils.py: the real aggregation functions --------------------------------------
+    plt = _stub('matplotlib.pyplot')
+    _stub('matplotlib').pyplot = plt
+    geo = _stub('geoopt'); man = _stub('geoopt.manifolds'); ste = _stub('geoopt.manifolds.stereographic')
+    gm = _stub('geoopt.manifolds.stereographic.math')
+    geo.manifolds = man; man.stereographic = ste; ste.math = gm
+    for name in ('expmap0', 'project', 'dist', 'dist0', 'weighted_midpoint'):
+        setattr(gm, name, getattr(ogm, name))          # restated geoopt stands in for the missing package
+    torch.Tensor.cuda = lambda self, *a, **kw: self    # CPU container: make .cuda() a no-op for the reference
+    import utils.eval_utils as ref_eu                  # noqa: E402
+
+    trans, meta, frames, clips, gts = oagg.synth_dataset(n_clips=4, seed=3, num_transform=2)
+    rng = np.random.default_rng(11)
+    hidden = (rng.standard_normal((len(trans), 16)) * 0.3).astype(np.float32)
+    hidden[rng.random(len(trans)) < 0.02] = 0.0          # exact-zero scores ("absent" windows)
+    c_t = torch.zeros(16)
+    loss_fn = torch.nn.MSELoss(reduction='none')
+    # per-person matrices from the real windows_based_loss_hy (euclidean branch), then the eval loop
+    ref_curves, or_curves = [], []
+    for t in range(2):
+        ct = trans == t
+        for scene, clip, F in clips:
+            cc = ct & (meta[:, 0] == scene) & (meta[:, 1] == clip)
+            per_person = []
+            for fig in sorted(set(meta[cc][:, 2])):
+                cf = cc & (meta[:, 2] == fig)
+                lm = ref_eu.windows_based_loss_hy(c_t, hidden[cf], frames[cf], F, loss_fn, False)
+                lm = np.where(lm == 0.0, np.nan, lm)
+                with np.errstate(all='ignore'):
+                    import warnings
+                    with warnings.catch_warnings():
+                        warnings.simplefilter('ignore')
+                        fl = np.nanmean(lm, 0)
+                per_person.append(np.where(np.isnan(fl), 0, fl))
+            clip_score = np.amax(np.stack(per_person, 0), 0)
+            ref_curves.append(ref_eu.score_process(clip_score.copy()))
+    scores = ((hidden.astype(np.float32) - 0.0) ** 2)
+    scores = torch.mean(loss_fn(c_t, torch.from_numpy(hidden)), dim=-1).numpy()
+    agg = oagg.aggregate_dataset(scores, trans, meta, frames, clips, 2)
+    or_curves = [c for t in range(2) for c in agg[t]]
+    for a, b_ in zip(ref_curves, or_curves):
+        assert np.array_equal(a, b_), 'oracle.aggregate differs from the reference functions'
+    # pad_scores
+    fr = np.array([0, 0, 0, .5, .4, 0, 0, 0, 0, 0, .2, .1, 0, 0, 0, 0, 0, 0, 0, 0.])
+    assert np.array_equal(ref_eu.pad_scores(fr.copy(), np.zeros(20), 2), oagg.pad_scores(fr.copy(), np.zeros(20), 2))
+    np.savez(os.path.join(GOLD, 'aggregate_ref.npz'), scores=scores, trans=trans, meta=meta, frames=frames,
+             clips=np.asarray(clips, dtype=np.int64), curves=np.concatenate(ref_curves),
+             pad_in=fr, pad_out=ref_eu.pad_scores(fr.copy(), np.zeros(20), 2))
+    print('golden fixtures written to', GOLD)
+    for fn in sorted(os.listdir(GOLD)):
+        print('  ', fn, os.path.getsize(os.path.join(GOLD, fn)), 'bytes')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,140 @@
+"""GPU parity of the geometry / center / aggregation kernels against the oracle and the fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aggregate as oagg
+from oracle import geoopt_math as ogm
+from oracle import hyper_math as ohm
+
+pytestmark = pytest.mark.gpu
+K = torch.tensor(-1.)
+
+
+def _close(got, ref, rtol=1e-4, atol=1e-6):
+    got, ref = got.detach().cpu().double(), torch.as_tensor(ref).double()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = (got - ref).abs()
+    assert bool((err <= rtol * ref.abs() + atol).all()), f'max abs err {float(err.max()):.3e}'
+
+
+def test_gmath_fixture_geoopt(golden_dir):
+    from coskad_b200 import gmath
+    g = np.load(os.path.join(golden_dir, 'geometry_geoopt_restated.npz'))
+    u, c = torch.from_numpy(g['u']).cuda(), torch.from_numpy(g['center']).cuda()
+    e = gmath.expmap0(u, k=K)
+    p = gmath.project(e, k=K)
+    _close(e, g['expmap0'], 1e-5, 1e-8)
+    _close(p, g['project'], 1e-5, 1e-8)
+    pf = torch.from_numpy(g['project']).cuda()
+    _close(gmath.dist(pf, c, k=K), g['dist'], 1e-4, 1e-6)
+    _close(gmath.dist(c, pf, k=K), g['dist_cx'], 1e-4, 1e-6)
+    _close(gmath.dist0(pf, k=K), g['dist0'], 1e-4, 1e-6)
+    _close(gmath.weighted_midpoint(pf, k=K), g['midpoint'], 1e-4, 1e-6)
+
+
+def test_hyper_math_fixture_pinned(golden_dir):
+    from coskad_b200 import gmath
+    g = np.load(os.path.join(golden_dir, 'geometry_hyper_math.npz'))
+    u, c = torch.from_numpy(g['u']).cuda(), torch.from_numpy(g['center']).cuda()
+    e = gmath.hm_expmap0(u)
+    _close(e, g['expmap0'], 1e-5, 1e-8)
+    _close(gmath.hm_project(e), g['project'], 1e-5, 1e-8)
+    _close(gmath.hm_dist(torch.from_numpy(g['project']).cuda(), c), g['dist'], 1e-4, 1e-6)
+
+
+@pytest.mark.parametrize('D', [8, 16, 24, 64])
+def test_geometry_random(D):
+    from coskad_b200 import gmath
+    gen = torch.Generator().manual_seed(D)
+    u = torch.randn(1000, D, generator=gen) * torch.logspace(-3, 0.5, 1000)[:, None]
+    y = torch.randn(1000, D, generator=gen) * 0.1
+    x = ogm.project(ogm.expmap0(u, k=K), k=K)
+    _close(gmath.project(gmath.expmap0(u.cuda(), k=K), k=K), x, 1e-5, 1e-8)
+    xs = x * 0.8
+    _close(gmath.dist(xs.cuda(), y.cuda(), k=K), ogm.dist(xs, y, k=K))
+    _close(gmath.dist(xs.cuda(), y[0].cuda(), k=K), ogm.dist(xs, y[0], k=K))
+    _close(gmath.weighted_midpoint(xs.cuda(), k=K), ogm.weighted_midpoint(xs, k=K), 1e-4, 1e-6)
+    # edge cases: zero vector, tiny and huge norms
+    e = torch.zeros(4, D)
+    e[1, 0] = 1e-20
+    e[2] = 1e4
+    e[3, 1] = 16.0
+    _close(gmath.expmap0(e.cuda(), k=K), ogm.expmap0(e, k=K), 1e-5, 1e-12)
+    _close(gmath.project(gmath.expmap0(e.cuda(), k=K), k=K), ogm.project(ogm.expmap0(e, k=K), k=K), 1e-5, 1e-12)
+
+
+def test_center_partials_add_like_shards():
+    """the midpoint of the union equals finalize(sum of per-shard partials) -- what the all-reduce relies on"""
+    from coskad_b200 import gmath
+    gen = torch.Generator().manual_seed(3)
+    x = ogm.project(ogm.expmap0(torch.randn(5000, 16, generator=gen) * 0.5, k=K), k=K)
+    ref = ogm.weighted_midpoint(x, k=K)
+    acc = gmath.center_accumulator(16, 'cuda')
+    for part in x.split(777):
+        gmath.center_partial(part.cuda(), acc, flavour=1)
+    _close(gmath.center_finalize(acc, 16, flavour=1), ref, 1e-5, 1e-7)
+    assert float(acc[17]) == 5000.0
+    # euclidean mean + tolerance clamp (euclidean_encoder_staticCenter.py:118-123)
+    z = torch.randn(3000, 16, generator=gen) * 0.01
+    z[:, 3] = -1e-5
+    c = z.sum(0) / 3000
+    eps = 1e-3
+    c[(abs(c) < eps) & (c < 0)] = -eps
+    c[(abs(c) < eps) & (c > 0)] = eps
+    acc = gmath.center_accumulator(16, 'cuda')
+    gmath.center_partial(z.cuda(), acc, flavour=3)
+    _close(gmath.center_finalize(acc, 16, flavour=3, eps=eps), c, 1e-5, 1e-8)
+
+
+def test_poincare_score_backward_matches_autograd():
+    from coskad_b200 import gmath
+    gen = torch.Generator().manual_seed(9)
+    z = (torch.randn(512, 16, generator=gen) * torch.logspace(-2, 0.6, 512)[:, None]).requires_grad_(True)
+    c = torch.randn(16, generator=gen) * 0.1
+    w = torch.rand(512, generator=gen)
+    for with_project in (True, False):
+        z.grad = None
+        x = ogm.expmap0(z, k=K)
+        if with_project:
+            x = ogm.project(x, k=K)
+        (ogm.dist(c, x, k=K) * w).sum().backward()
+        got = gmath.poincare_score_bwd(z.detach().cuda(), c.cuda(), w.cuda(), with_project)
+        ref = z.grad
+        err = (got.cpu() - ref).abs()
+        assert bool((err <= 2e-3 * ref.abs() + 1e-5 * float(ref.abs().max())).all()), float(err.max())
+
+
+def test_frame_aggregation_bit_exact(golden_dir):
+    from coskad_b200 import aggregate
+    g = np.load(os.path.join(golden_dir, 'aggregate_ref.npz'))
+    clips = [tuple(int(v) for v in r) for r in g['clips']]
+    out = aggregate.score_and_aggregate(torch.from_numpy(g['scores']).cuda(), g['trans'], g['meta'], g['frames'], clips,
+                                        num_transform=2, smooth=True)
+    got = np.concatenate([c for t in range(2) for c in out[t]])
+    assert got.dtype == np.float64
+    assert np.array_equal(got, g['curves'])     # bit exact vs the reference's own functions
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_frame_aggregation_random_datasets(seed):
+    from coskad_b200 import aggregate
+    trans, meta, frames, clips, gts = oagg.synth_dataset(n_clips=9, seed=seed, num_transform=3, max_persons=6)
+    rng = np.random.default_rng(seed)
+    scores = rng.random(len(trans)).astype(np.float32) * 3
+    scores[rng.random(len(trans)) < 0.05] = 0.0
+    ref = oagg.aggregate_dataset(scores, trans, meta, frames, clips, 3, smooth=False)
+    out = aggregate.score_and_aggregate(torch.from_numpy(scores).cuda(), trans, meta, frames, clips, num_transform=3,
+                                        smooth=False)
+    for t in range(3):
+        for a, b in zip(out[t], ref[t]):
+            assert np.array_equal(a, b)
+    # with pad_scores + smoothing + AUC (host side, same scipy/sklearn calls)
+    ref = oagg.aggregate_dataset(scores, trans, meta, frames, clips, 3, pad_size=5, gts=gts)
+    out = aggregate.score_and_aggregate(torch.from_numpy(scores).cuda(), trans, meta, frames, clips, num_transform=3,
+                                        pad_size=5, gts=gts)
+    for t in range(3):
+        for a, b in zip(out[t], ref[t]):
+            assert np.array_equal(a, b)

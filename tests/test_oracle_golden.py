@@ -1,0 +1,128 @@
+"""CPU: the oracle restatements against the fixtures generated from the REAL reference
+(oracle/gen_golden.py ran the reference's own modules; see its header for what is pinned)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import aggregate as oagg
+from oracle import geoopt_math as ogm
+from oracle import hyper_math as ohm
+from oracle import stsgcn as onet
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_stse_oracle_matches_reference_vectors(golden_dir):
+    g = _load(golden_dir, 'stse_ref.npz')
+    sd = onet.init_state_dict('stse', latent_dim=16, seed=0)
+    chk = sum(float(v.double().sum()) for k, v in sd.items() if v.is_floating_point())
+    assert abs(chk - float(g['sd_checksum'])) < 1e-9, 'seeded state dict differs from the one the fixture was made with'
+    x = torch.from_numpy(g['x'])
+    with torch.no_grad():
+        z = onet.stse_forward(x, sd)
+        h1 = onet.st_gcnn_layer(x, sd, 'encoder.model.0')
+    assert torch.allclose(z, torch.from_numpy(g['z']), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(h1, torch.from_numpy(g['h1']), rtol=1e-5, atol=1e-6)
+
+
+def test_synth_windows_reproducible(golden_dir):
+    g = _load(golden_dir, 'stse_ref.npz')
+    assert np.array_equal(onet.synth_windows(10, seed=999).numpy(), g['x'])
+
+
+def test_stsae_oracle_matches_reference_vectors(golden_dir):
+    g = _load(golden_dir, 'stsae_ref.npz')
+    sd = onet.init_state_dict('stsae', latent_dim=8, seed=1)
+    with torch.no_grad():
+        z, xh = onet.stsae_forward(torch.from_numpy(g['x']), sd)
+    assert torch.allclose(z, torch.from_numpy(g['z']), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(xh, torch.from_numpy(g['xhat']), rtol=1e-5, atol=1e-6)
+
+
+def test_train_mode_oracle_matches_reference(golden_dir):
+    g = _load(golden_dir, 'stse_train_ref.npz')
+    sd = onet.init_state_dict('stse', latent_dim=16, seed=0)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k and k != 'c') for k, v in sd.items()}
+    stats = {}
+    z = onet.stse_forward(torch.from_numpy(g['x']), params, training=True, new_stats=stats)
+    assert torch.allclose(z, torch.from_numpy(g['z']), rtol=1e-4, atol=1e-5)
+    (z ** 2).mean().backward()
+    for k in g.files:
+        if k.startswith('grad.'):
+            ref = torch.from_numpy(g[k])
+            got = params[k[5:]].grad
+            assert torch.allclose(got, ref, rtol=1e-3, atol=1e-6 + 1e-4 * float(ref.abs().max())), k
+        if k.startswith('stat.'):
+            assert torch.allclose(stats[k[5:]], torch.from_numpy(g[k]), rtol=1e-5, atol=1e-6), k
+
+
+def test_fold_is_exact_algebra():
+    sd = onet.init_state_dict('stse', seed=3)
+    x = onet.synth_windows(5, seed=1)
+    for i in range(4):
+        pfx = f'encoder.model.{i}'
+        with torch.no_grad():
+            ref = onet.st_gcnn_layer(x, sd, pfx)
+            w1, w2, b = onet.fold_layer_eval(sd, pfx)
+            g = onet.graph_contract(x, sd[pfx + '.gcn.A'], sd[pfx + '.gcn.T'])
+            pre = torch.einsum('oc,nctv->notv', w1, g) + torch.einsum('oc,nctv->notv', w2, x) + b[None, :, None, None]
+            got = torch.nn.functional.prelu(pre, sd[pfx + '.prelu.weight'])
+        assert float((got - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+        x = ref
+
+
+def test_hyper_math_flavour_pinned(golden_dir):
+    g = _load(golden_dir, 'geometry_hyper_math.npz')
+    u, c = torch.from_numpy(g['u']), torch.from_numpy(g['center'])
+    e = ohm.expmap0(u)
+    p = ohm.project(e)
+    assert torch.allclose(e, torch.from_numpy(g['expmap0']), rtol=1e-6, atol=1e-8)
+    assert torch.allclose(p, torch.from_numpy(g['project']), rtol=1e-6, atol=1e-8)
+    assert torch.allclose(ohm.dist(p, c.expand_as(p)), torch.from_numpy(g['dist']), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(ohm.poincare_mean(p[:40] * 0.5), torch.from_numpy(g['mean']), rtol=1e-5, atol=1e-7)
+
+
+def test_geoopt_restatement_properties():
+    """geoopt is not installable here (parity unpinned): check the restatement's defining properties."""
+    k = torch.tensor(-1.)
+    g = torch.Generator().manual_seed(1)
+    u = torch.randn(256, 16, generator=g) * torch.logspace(-2, 1, 256)[:, None]
+    x = ogm.project(ogm.expmap0(u, k=k), k=k)
+    assert float(x.norm(dim=-1).max()) <= 1 - 4e-3 + 1e-6                     # ball containment
+    y = ogm.project(ogm.expmap0(torch.randn(256, 16, generator=g), k=k), k=k)
+    xs_, ys_ = x * 0.7, y * 0.7      # away from the boundary: artanh' = 1/(1-r^2) amplifies fp32 rounding there
+    assert torch.allclose(ogm.dist(xs_, ys_, k=k), ogm.dist(ys_, xs_, k=k), rtol=1e-4, atol=1e-5)   # symmetry
+    assert torch.allclose(ogm.dist(x, torch.zeros(16), k=k), ogm.dist0(x, k=k), rtol=1e-5, atol=1e-6)
+    # closed form: d(0, x) = 2 artanh |x|
+    xs = x[x.norm(dim=-1) < 0.9]
+    assert torch.allclose(ogm.dist0(xs, k=k), 2 * torch.atanh(xs.norm(dim=-1)), rtol=1e-4, atol=1e-6)
+    # midpoint is permutation invariant and of one point is the point
+    m1 = ogm.weighted_midpoint(x[:64] * 0.5, k=k)
+    m2 = ogm.weighted_midpoint((x[:64] * 0.5)[torch.randperm(64, generator=g)], k=k)
+    assert torch.allclose(m1, m2, rtol=1e-4, atol=1e-6)
+    one = x[3:4] * 0.3
+    assert torch.allclose(ogm.weighted_midpoint(one, k=k), one[0], rtol=1e-4, atol=1e-6)
+    # agrees with the hyper_math flavour away from the boundary, to the size of the constants
+    xi = x[x.norm(dim=-1) < 0.5]
+    assert torch.allclose(ogm.dist(xi, y[:len(xi)] * 0.3, k=k), ohm.dist(xi, y[:len(xi)] * 0.3), rtol=1e-3, atol=1e-4)
+
+
+def test_aggregation_oracle_matches_reference_functions(golden_dir):
+    g = _load(golden_dir, 'aggregate_ref.npz')
+    clips = [tuple(int(v) for v in r) for r in g['clips']]
+    agg = oagg.aggregate_dataset(g['scores'], g['trans'], g['meta'], g['frames'], clips, 2)
+    got = np.concatenate([c for t in range(2) for c in agg[t]])
+    assert np.array_equal(got, g['curves'])           # bit exact float64
+    assert np.array_equal(oagg.pad_scores(g['pad_in'].copy(), np.zeros(20), 2), g['pad_out'])
+
+
+def test_frame_id_zero_wraps_and_zero_scores_are_absent():
+    frames = np.array([[0, 1, 2], [1, 2, 3]])
+    loss = np.array([0.5, 0.0], dtype=np.float32)
+    pose = oagg.scatter_windows(loss, frames, 6)
+    assert pose[0, -1] == 0.5 and pose[0, 0] == 0.5 and pose[0, 1] == 0.5
+    cur = oagg.person_curve(loss, frames, 6)
+    assert np.array_equal(cur, np.array([0.5, 0.5, 0, 0, 0, 0.5]))
