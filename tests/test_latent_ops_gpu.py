@@ -90,21 +90,45 @@ def test_center_partials_add_like_shards():
 
 
 def test_poincare_score_backward_matches_autograd():
+    """fp32 kernel vs float64 autograd through the restated geoopt formulas (the truth); the fp32
+    autograd of the same formulas is measured alongside: the kernel must not be worse than 3x it."""
     from coskad_b200 import gmath
     gen = torch.Generator().manual_seed(9)
-    z = (torch.randn(512, 16, generator=gen) * torch.logspace(-2, 0.6, 512)[:, None]).requires_grad_(True)
+    z = torch.randn(512, 16, generator=gen) * torch.logspace(-2, 0.6, 512)[:, None]
     c = torch.randn(16, generator=gen) * 0.1
     w = torch.rand(512, generator=gen)
     for with_project in (True, False):
-        z.grad = None
-        x = ogm.expmap0(z, k=K)
-        if with_project:
-            x = ogm.project(x, k=K)
-        (ogm.dist(c, x, k=K) * w).sum().backward()
-        got = gmath.poincare_score_bwd(z.detach().cuda(), c.cuda(), w.cuda(), with_project)
-        ref = z.grad
-        err = (got.cpu() - ref).abs()
-        assert bool((err <= 2e-3 * ref.abs() + 1e-5 * float(ref.abs().max())).all()), float(err.max())
+        ref = {}
+        for dt in (torch.float32, torch.float64):
+            zz = z.to(dt).clone().requires_grad_(True)
+            x = ogm.expmap0(zz, k=K.to(dt))
+            if with_project:
+                x = ogm.project(x, k=K.to(dt), eps=4e-3)
+            (ogm.dist(c.to(dt), x, k=K.to(dt)) * w.to(dt)).sum().backward()
+            ref[dt] = zz.grad.double()
+        got = gmath.poincare_score_bwd(z.cuda(), c.cuda(), w.cuda(), with_project).cpu().double()
+        # without project() tanh saturates to 1.0f for |z| > ~3 and the reference's own fp32 gradient is garbage
+        rows = torch.ones(512, dtype=torch.bool) if with_project else (z.norm(dim=-1) < 3.0)
+        scale = ref[torch.float64][rows].abs().amax(dim=-1, keepdim=True) + 1e-30
+        e_ours = float(((got[rows] - ref[torch.float64][rows]).abs() / scale).max())
+        e_f32 = float(((ref[torch.float32][rows] - ref[torch.float64][rows]).abs() / scale).max())
+        assert e_ours < 5e-4 and e_ours < 3 * e_f32 + 1e-6, (with_project, e_ours, e_f32)
+
+
+def test_poincare_score_autograd_function():
+    from coskad_b200 import gmath
+    gen = torch.Generator().manual_seed(2)
+    z = (torch.randn(300, 16, generator=gen) * 0.7)
+    c = torch.randn(16, generator=gen) * 0.1
+    zr = z.clone().requires_grad_(True)
+    loss_ref = ogm.dist(c, ogm.project(ogm.expmap0(zr, k=K), k=K), k=K).mean()
+    loss_ref.backward()
+    zc = z.cuda().requires_grad_(True)
+    s, x = gmath.poincare_score(zc, c.cuda(), True)
+    s.mean().backward()
+    _close(s.mean(), loss_ref.detach(), 1e-5, 1e-7)
+    _close(zc.grad, zr.grad, 1e-3, 1e-6 * float(zr.grad.abs().max()) + 1e-8)
+    _close(x, ogm.project(ogm.expmap0(z, k=K), k=K), 1e-5, 1e-8)
 
 
 def test_frame_aggregation_bit_exact(golden_dir):
