@@ -46,6 +46,15 @@ SIGNATURES = {
     'coskad_frame_aggregate': (C.c_int, [c_ctx_p, c_float_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    'coskad_train_contract_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 3 + [C.c_int64] + [c_float_p] * 2 + [C.c_void_p]),
+    'coskad_train_contract_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64] + [c_float_p] * 3 + [C.c_void_p]),
+    'coskad_train_mix_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64, C.c_int, C.c_int] + [c_float_p] * 3 + [C.c_void_p]),
+    'coskad_train_bn_finalize': (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float] + [c_float_p] * 5 + [C.c_void_p]),
+    'coskad_train_bn_prelu_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 8 + [C.c_int64, C.c_int, c_float_p, C.c_void_p]),
+    'coskad_train_bn_prelu_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 9 + [C.c_int64, C.c_int, C.c_void_p, c_float_p, c_float_p, C.c_void_p]),
+    'coskad_train_mix_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64, C.c_int, C.c_int] + [c_float_p] * 6 + [C.c_void_p]),
+    'coskad_train_linear': (C.c_int, [c_ctx_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int64, C.c_int, C.c_int, c_float_p, C.c_void_p]),
+    'coskad_train_col_sum': (C.c_int, [c_ctx_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_measure_fp32_peak': (C.c_int, [c_ctx_p, C.POINTER(C.c_double), C.c_void_p]),
     'coskad_launch_count': (C.c_int64, [c_ctx_p]),
     'coskad_debug_fused_stage': (C.c_int, [c_ctx_p, C.c_int, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),

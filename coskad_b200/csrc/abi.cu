@@ -454,3 +454,134 @@ extern "C" int coskad_measure_fp32_peak(coskad_ctx* ctx, double* tflops, void* s
   *tflops = best;
   return COSKAD_OK;
 }
+
+// ---- training path --------------------------------------------------------------------------------
+#define TRAIN_PRE()                                    \
+  if (!ctx) return COSKAD_ERR_ARG;                     \
+  CK(cudaSetDevice(ctx->device));                      \
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+static inline int ew_grid(const coskad_ctx* ctx, int64_t n, int threads = kTrainThreads) {
+  int64_t g = (n + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static bool chan_ok(int c) { return c == 2 || c == 16 || c == 32 || c == 64; }
+
+extern "C" int coskad_train_contract_fwd(coskad_ctx* ctx, const float* X, const float* A, const float* T, int64_t R,
+                                         float* G1, float* G, void* stream_) {
+  TRAIN_PRE();
+  if (R <= 0) return COSKAD_OK;
+  const int g = static_cast<int>(R < ctx->sm_count * 8 ? R : ctx->sm_count * 8);
+  train_contract_fwd_kernel<<<g, kTrainThreads, 0, st>>>(X, A, T, R, G1, G);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const float* dXres, const float* X,
+                                         const float* G1, const float* A, const float* T, int64_t R, float* dX,
+                                         float* dA, float* dT, void* stream_) {
+  TRAIN_PRE();
+  if (R <= 0) return COSKAD_OK;
+  const int g = static_cast<int>(R < ctx->sm_count * 4 ? R : ctx->sm_count * 4);
+  train_contract_bwd_kernel<<<g, kTrainThreads, 0, st>>>(dG, dXres, X, G1, A, T, R, dX, dA, dT);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1,
+                                    const float* W2, const float* b2, int64_t B, int CI, int CO, float* y1, float* y2,
+                                    double* stats, void* stream_) {
+  TRAIN_PRE();
+  if (!chan_ok(CI) || !chan_ok(CO)) return fail(ctx, COSKAD_ERR_ARG, "training kernels support channels {2,16,32,64}, got %d->%d", CI, CO);
+  if (B <= 0) return COSKAD_OK;
+  const size_t smem = sizeof(float) * (2 * CO * CI + 4 * CO);
+  const int g = ew_grid(ctx, B * kP);
+#define LAUNCH_MIX(CI_) train_mix_fwd_kernel<CI_><<<g, kTrainThreads, smem, st>>>(G, X, W1, b1, W2, b2, B, CO, y1, y2, stats)
+  switch (CI) { case 2: LAUNCH_MIX(2); break; case 16: LAUNCH_MIX(16); break; case 32: LAUNCH_MIX(32); break; default: LAUNCH_MIX(64); break; }
+#undef LAUNCH_MIX
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_bn_finalize(coskad_ctx* ctx, const double* stats, int64_t n_per_channel, int CO, float eps,
+                                        float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi,
+                                        void* stream_) {
+  TRAIN_PRE();
+  train_bn_finalize_kernel<<<(CO + 63) / 64, 64, 0, st>>>(stats, static_cast<double>(n_per_channel), CO, eps, momentum, rm1,
+                                                         rv1, rm2, rv2, mi);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_bn_prelu_fwd(coskad_ctx* ctx, const float* y1, const float* y2, const float* mi,
+                                         const float* g1, const float* be1, const float* g2, const float* be2,
+                                         const float* slope, int64_t B, int CO, float* out, void* stream_) {
+  TRAIN_PRE();
+  if (B <= 0) return COSKAD_OK;
+  train_bn_prelu_fwd_kernel<<<ew_grid(ctx, B * CO * kP), kTrainThreads, 0, st>>>(y1, y2, mi, g1, be1, g2, be2, slope, B, CO, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2,
+                                         const float* mi, const float* g1, const float* be1, const float* g2,
+                                         const float* be2, const float* slope, int64_t B, int CO, double* red,
+                                         float* dy1, float* dy2, void* stream_) {
+  TRAIN_PRE();
+  if (B <= 0) return COSKAD_OK;
+  int nb = static_cast<int>((B + 7) / 8);
+  const int cap = (ctx->sm_count * 8 + CO - 1) / CO;
+  if (nb > cap) nb = cap;
+  train_bn_prelu_bwd_reduce_kernel<<<dim3(CO, nb), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, B, CO, red);
+  CK_LAUNCH();
+  train_bn_prelu_bwd_apply_kernel<<<ew_grid(ctx, B * CO * kP), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2,
+                                                                                    slope, red, B, CO, dy1, dy2);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const float* dy2, const float* G, const float* X,
+                                    const float* W1, const float* W2, int64_t B, int CI, int CO, float* dG, float* dXres,
+                                    float* dW1, float* db1, float* dW2, float* db2, void* stream_) {
+  TRAIN_PRE();
+  if (!chan_ok(CI) || !chan_ok(CO)) return fail(ctx, COSKAD_ERR_ARG, "training kernels support channels {2,16,32,64}, got %d->%d", CI, CO);
+  if (B <= 0) return COSKAD_OK;
+  const size_t smem = sizeof(float) * (2 * CO * CI);
+  const int g = ew_grid(ctx, B * kP);
+#define LAUNCH_BD(CO_) train_mix_bwd_data_kernel<CO_><<<g, kTrainThreads, smem, st>>>(dy1, dy2, W1, W2, B, CI, dG, dXres)
+  switch (CO) { case 2: LAUNCH_BD(2); break; case 16: LAUNCH_BD(16); break; case 32: LAUNCH_BD(32); break; default: LAUNCH_BD(64); break; }
+#undef LAUNCH_BD
+  CK_LAUNCH();
+  const size_t smem2 = sizeof(float) * 2 * (CO + CI) * kWC;
+  int g2 = static_cast<int>((B * kP + kWC - 1) / kWC);
+  if (g2 > ctx->sm_count * 4) g2 = ctx->sm_count * 4;
+  train_mix_bwd_weight_kernel<<<g2, kTrainThreads, smem2, st>>>(dy1, dy2, G, X, B, CI, CO, dW1, db1, dW2, db2);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+// mode 0: out[b,d] = sum_f A[b,f] W(d,f) + bias[d]; mode 1: out[b,f] = sum_d a[b,d] W(d,f) + bias[f];
+// mode 2: dW(d,f) += sum_b a[b,d] A[b,f].  w_is_fd: W stored [F,D] (rev_btlnk) instead of [D,F] (btlnk).
+extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_small, const float* A_wide, const float* W,
+                                   int w_is_fd, const float* bias, int64_t B, int F, int D, float* out, void* stream_) {
+  TRAIN_PRE();
+  if (D < 1 || D > 16) return fail(ctx, COSKAD_ERR_ARG, "linear: D must be in [1,16], got %d", D);
+  if (B <= 0) return COSKAD_OK;
+  const int64_t sd = w_is_fd ? 1 : F, sf = w_is_fd ? D : 1;
+  if (mode == 0) lin_reduce_f_kernel<16><<<static_cast<unsigned>(B), kTrainThreads, 0, st>>>(A_wide, W, sd, sf, bias, B, F, D, out);
+  else if (mode == 1) lin_expand_f_kernel<16><<<ew_grid(ctx, B * F), kTrainThreads, 0, st>>>(a_small, W, sd, sf, bias, B, F, D, out);
+  else if (mode == 2) {
+    int nb = static_cast<int>(B < 32 ? B : 32);
+    lin_wgrad_kernel<16><<<dim3((F + kTrainThreads - 1) / kTrainThreads, nb), kTrainThreads, 0, st>>>(a_small, A_wide, sd, sf, B, F, D, out);
+  } else return fail(ctx, COSKAD_ERR_ARG, "linear: unknown mode %d", mode);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_col_sum(coskad_ctx* ctx, const float* a, int64_t B, int N, float* out, void* stream_) {
+  TRAIN_PRE();
+  if (B <= 0 || N <= 0) return COSKAD_OK;
+  col_sum_kernel<<<(N + 31) / 32, kTrainThreads, 0, st>>>(a, B, N, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}

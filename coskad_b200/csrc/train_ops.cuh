@@ -65,3 +65,399 @@ __global__ void poincare_score_bwd_kernel(const float* __restrict__ z, const flo
 }
 
 }  // namespace coskad
+
+// =================================================================================================
+// Training path: per-layer kernels with train-mode BatchNorm (batch statistics, per GPU -- the
+// reference has no SyncBN).  Activations are [B, C, 204] float32 in HBM between kernels: batch
+// statistics over (B, T, V) sit between the convolution and the activation, so a layer cannot be
+// fused end to end in training.  Reference: models/graph_layers/stsgcn.py:94-156
+// forward; the backward kernels implement the analytic gradients of the same graph (autograd
+// semantics of nn.Conv2d 1x1, nn.BatchNorm2d(train), nn.PReLU, torch.einsum).
+// =================================================================================================
+namespace coskad {
+
+constexpr int kTrainThreads = 256;
+
+// ---- graph contraction forward: G1 = temporal(X), G = spatial(G1); one block iteration per row ----
+__global__ void train_contract_fwd_kernel(const float* __restrict__ X, const float* __restrict__ A,
+                                          const float* __restrict__ T, int64_t R, float* __restrict__ G1,
+                                          float* __restrict__ G) {
+  __shared__ float As[kT * kV * kV], Ts[kV * kT * kT], xs[kP], g1s[kP];
+  for (int i = threadIdx.x; i < kT * kV * kV; i += blockDim.x) As[i] = A[i];
+  for (int i = threadIdx.x; i < kV * kT * kT; i += blockDim.x) Ts[i] = T[i];
+  const int i = threadIdx.x;
+  const int t_ = i / kV, v_ = i % kV;     // (q or t, v or w) of this thread's output
+  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+    __syncthreads();
+    if (i < kP) xs[i] = X[r * kP + i];
+    __syncthreads();
+    if (i < kP) {                          // G1[q=t_, v=v_] = sum_t X[t, v] T[v, t, q]
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) s = fmaf(xs[t * kV + v_], Ts[v_ * (kT * kT) + t * kT + t_], s);
+      g1s[i] = s;
+      G1[r * kP + i] = s;
+    }
+    __syncthreads();
+    if (i < kP) {                          // G[t=t_, w=v_] = sum_v G1[t, v] A[t, v, w]
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < kV; ++v) s = fmaf(g1s[t_ * kV + v], As[t_ * (kV * kV) + v * kV + v_], s);
+      G[r * kP + i] = s;
+    }
+  }
+}
+
+// ---- graph contraction backward -----------------------------------------------------------------
+// dG1[t,v] = sum_w dG[t,w] A[t,v,w];  dX[t,v] = dXres[t,v] + sum_q dG1[q,v] T[v,t,q]
+// dA[t,v,w] += G1[t,v] dG[t,w];       dT[v,t,q] += X[t,v] dG1[q,v]      (summed over rows)
+__global__ void train_contract_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ dXres,
+                                          const float* __restrict__ X, const float* __restrict__ G1,
+                                          const float* __restrict__ A, const float* __restrict__ T, int64_t R,
+                                          float* __restrict__ dX, float* dA, float* dT) {
+  __shared__ float As[kT * kV * kV], Ts[kV * kT * kT], dgs[kP], xs[kP], g1s[kP], dg1s[kP];
+  for (int i = threadIdx.x; i < kT * kV * kV; i += blockDim.x) As[i] = A[i];
+  for (int i = threadIdx.x; i < kV * kT * kT; i += blockDim.x) Ts[i] = T[i];
+  constexpr int NA = (kT * kV * kV + kTrainThreads - 1) / kTrainThreads;   // 14
+  constexpr int NT = (kV * kT * kT + kTrainThreads - 1) / kTrainThreads;   // 10
+  float accA[NA], accT[NT];
+#pragma unroll
+  for (int j = 0; j < NA; ++j) accA[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) accT[j] = 0.f;
+  const int i = threadIdx.x;
+  const int t_ = i / kV, v_ = i % kV;
+  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+    __syncthreads();
+    if (i < kP) { dgs[i] = dG[r * kP + i]; xs[i] = X[r * kP + i]; g1s[i] = G1[r * kP + i]; }
+    __syncthreads();
+    if (i < kP) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kV; ++w) s = fmaf(dgs[t_ * kV + w], As[t_ * (kV * kV) + v_ * kV + w], s);
+      dg1s[i] = s;
+    }
+    __syncthreads();
+    if (i < kP) {
+      float s = (dXres != nullptr) ? dXres[r * kP + i] : 0.f;
+#pragma unroll
+      for (int q = 0; q < kT; ++q) s = fmaf(dg1s[q * kV + v_], Ts[v_ * (kT * kT) + t_ * kT + q], s);
+      dX[r * kP + i] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int e = i + j * kTrainThreads;
+      if (e < kT * kV * kV) { const int t = e / (kV * kV), v = (e / kV) % kV, w = e % kV; accA[j] = fmaf(g1s[t * kV + v], dgs[t * kV + w], accA[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int e = i + j * kTrainThreads;
+      if (e < kV * kT * kT) { const int v = e / (kT * kT), t = (e / kT) % kT, q = e % kT; accT[j] = fmaf(xs[t * kV + v], dg1s[q * kV + v], accT[j]); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NA; ++j) { const int e = i + j * kTrainThreads; if (e < kT * kV * kV) atomicAdd(dA + e, accA[j]); }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { const int e = i + j * kTrainThreads; if (e < kV * kT * kT) atomicAdd(dT + e, accT[j]); }
+}
+
+// ---- 1x1 convolutions forward + BatchNorm partial statistics ----------------------------------------
+// y1[b,co,p] = sum_ci W1[co,ci] G[b,ci,p] + b1[co];  y2 likewise from X.  stats (double) [4*Co]: sum y1, sum y1^2, sum y2, sum y2^2
+template <int CI>
+__global__ void train_mix_fwd_kernel(const float* __restrict__ G, const float* __restrict__ X,
+                                     const float* __restrict__ W1, const float* __restrict__ b1,
+                                     const float* __restrict__ W2, const float* __restrict__ b2, int64_t B, int CO,
+                                     float* __restrict__ y1, float* __restrict__ y2, double* stats) {
+  extern __shared__ float sm[];
+  float* w1s = sm;                 // [CO][CI]
+  float* w2s = sm + CO * CI;       // [CO][CI]
+  float* red = w2s + CO * CI;      // [4][CO]
+  for (int i = threadIdx.x; i < CO * CI; i += blockDim.x) { w1s[i] = W1[i]; w2s[i] = W2[i]; }
+  for (int i = threadIdx.x; i < 4 * CO; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int64_t E = B * kP;
+  const int lane = threadIdx.x & 31;
+  for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * blockDim.x; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = e0 + threadIdx.x;
+    const bool valid = e < E;
+    const int64_t b = valid ? e / kP : 0;
+    const int p = valid ? static_cast<int>(e - b * kP) : 0;
+    float g[CI], x[CI];
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+      g[ci] = valid ? G[(b * CI + ci) * kP + p] : 0.f;
+      x[ci] = valid ? X[(b * CI + ci) * kP + p] : 0.f;
+    }
+    for (int co = 0; co < CO; ++co) {
+      float a1 = b1 ? b1[co] : 0.f, a2 = b2 ? b2[co] : 0.f;
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) { a1 = fmaf(w1s[co * CI + ci], g[ci], a1); a2 = fmaf(w2s[co * CI + ci], x[ci], a2); }
+      if (valid) { y1[(b * CO + co) * kP + p] = a1; y2[(b * CO + co) * kP + p] = a2; }
+      else { a1 = 0.f; a2 = 0.f; }
+      const float s1 = warp_sum(a1), q1 = warp_sum(a1 * a1), s2 = warp_sum(a2), q2 = warp_sum(a2 * a2);
+      if (lane == 0) { atomicAdd(red + co, s1); atomicAdd(red + CO + co, q1); atomicAdd(red + 2 * CO + co, s2); atomicAdd(red + 3 * CO + co, q2); }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * CO; i += blockDim.x) {
+    const int k = i / CO, co = i % CO;
+    atomicAdd(stats + k * CO + co, static_cast<double>(red[i]));
+  }
+}
+
+// mean / invstd from the sums, running-statistics update (momentum 0.1, unbiased variance), nn.BatchNorm2d semantics
+__global__ void train_bn_finalize_kernel(const double* __restrict__ stats, double N, int CO, float eps, float momentum,
+                                         float* rm1, float* rv1, float* rm2, float* rv2, float* __restrict__ mi) {
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= CO) return;
+  for (int br = 0; br < 2; ++br) {
+    const double mean = stats[(2 * br) * CO + co] / N;
+    double var = stats[(2 * br + 1) * CO + co] / N - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mi[(2 * br) * CO + co] = static_cast<float>(mean);
+    mi[(2 * br + 1) * CO + co] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    float* rm = br ? rm2 : rm1;
+    float* rv = br ? rv2 : rv1;
+    if (rm) rm[co] = (1.f - momentum) * rm[co] + momentum * static_cast<float>(mean);
+    if (rv) rv[co] = (1.f - momentum) * rv[co] + momentum * static_cast<float>(var * N / (N - 1.0));
+  }
+}
+
+// out = PReLU(BN1(y1) + BN2(y2))
+__global__ void train_bn_prelu_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ y2,
+                                          const float* __restrict__ mi, const float* __restrict__ g1,
+                                          const float* __restrict__ be1, const float* __restrict__ g2,
+                                          const float* __restrict__ be2, const float* __restrict__ slope, int64_t B,
+                                          int CO, float* __restrict__ out) {
+  const int64_t n = B * CO * kP;
+  const float a = slope[0];
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>((e / kP) % CO);
+    const float h1 = (y1[e] - mi[co]) * mi[CO + co], h2 = (y2[e] - mi[2 * CO + co]) * mi[3 * CO + co];
+    out[e] = prelu(h1 * g1[co] + be1[co] + h2 * g2[co] + be2[co], a);
+  }
+}
+
+// backward reductions: red (double) [3*CO + 1] = sum ds, sum ds*yhat1, sum ds*yhat2 per channel, then d slope
+// grid (CO, NB): block (co, j) walks the rows (b, co) of its batch slice
+__global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y1,
+                                                 const float* __restrict__ y2, const float* __restrict__ mi,
+                                                 const float* __restrict__ g1, const float* __restrict__ be1,
+                                                 const float* __restrict__ g2, const float* __restrict__ be2,
+                                                 const float* __restrict__ slope, int64_t B, int CO, double* red) {
+  const int co = blockIdx.x;
+  const float a = slope[0];
+  const float m1 = mi[co], i1 = mi[CO + co], m2 = mi[2 * CO + co], i2 = mi[3 * CO + co];
+  const float ga1 = g1[co], ga2 = g2[co], bb = be1[co] + be2[co];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int64_t b = static_cast<int64_t>(blockIdx.y) * nwarp + warp; b < B; b += static_cast<int64_t>(gridDim.y) * nwarp) {
+    const int64_t base = (b * CO + co) * kP;
+    for (int p = lane; p < kP; p += 32) {
+      const float h1 = (y1[base + p] - m1) * i1, h2 = (y2[base + p] - m2) * i2;
+      const float pre = h1 * ga1 + h2 * ga2 + bb;
+      const float d = dout[base + p];
+      const float ds = pre >= 0.f ? d : a * d;
+      s0 += ds; s1 = fmaf(ds, h1, s1); s2 = fmaf(ds, h2, s2);
+      if (pre < 0.f) sa = fmaf(d, pre, sa);
+    }
+  }
+  __shared__ float sh[4][8];
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sa = warp_sum(sa);
+  if (lane == 0) { sh[0][warp] = s0; sh[1][warp] = s1; sh[2][warp] = s2; sh[3][warp] = sa; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < nwarp; ++w) t += static_cast<double>(sh[threadIdx.x][w]);
+    if (threadIdx.x < 3) atomicAdd(red + threadIdx.x * CO + co, t);
+    else atomicAdd(red + 3 * CO, t);
+  }
+}
+
+// dy1 = g1*is1*(ds - mean(ds) - yhat1*mean(ds*yhat1)), dy2 likewise (BatchNorm train backward)
+__global__ void train_bn_prelu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y1,
+                                                const float* __restrict__ y2, const float* __restrict__ mi,
+                                                const float* __restrict__ g1, const float* __restrict__ be1,
+                                                const float* __restrict__ g2, const float* __restrict__ be2,
+                                                const float* __restrict__ slope, const double* __restrict__ red,
+                                                int64_t B, int CO, float* __restrict__ dy1, float* __restrict__ dy2) {
+  const int64_t n = B * CO * kP;
+  const float a = slope[0];
+  const double N = static_cast<double>(B) * kP;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>((e / kP) % CO);
+    const float h1 = (y1[e] - mi[co]) * mi[CO + co], h2 = (y2[e] - mi[2 * CO + co]) * mi[3 * CO + co];
+    const float pre = h1 * g1[co] + be1[co] + h2 * g2[co] + be2[co];
+    const float d = dout[e];
+    const float ds = pre >= 0.f ? d : a * d;
+    const float mds = static_cast<float>(red[co] / N);
+    const float m1 = static_cast<float>(red[CO + co] / N), m2 = static_cast<float>(red[2 * CO + co] / N);
+    dy1[e] = g1[co] * mi[CO + co] * (ds - mds - h1 * m1);
+    dy2[e] = g2[co] * mi[3 * CO + co] * (ds - mds - h2 * m2);
+  }
+}
+
+// dG[b,ci,p] = sum_co W1[co,ci] dy1[b,co,p];  dXres[b,ci,p] = sum_co W2[co,ci] dy2[b,co,p]
+template <int CO>
+__global__ void train_mix_bwd_data_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
+                                          const float* __restrict__ W1, const float* __restrict__ W2, int64_t B, int CI,
+                                          float* __restrict__ dG, float* __restrict__ dXres) {
+  extern __shared__ float sm[];
+  float* w1s = sm;                 // [CO][CI]
+  float* w2s = sm + CO * CI;
+  for (int i = threadIdx.x; i < CO * CI; i += blockDim.x) { w1s[i] = W1[i]; w2s[i] = W2[i]; }
+  __syncthreads();
+  const int64_t E = B * kP;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < E; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = e / kP;
+    const int p = static_cast<int>(e - b * kP);
+    float d1[CO], d2[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) { d1[co] = dy1[(b * CO + co) * kP + p]; d2[co] = dy2[(b * CO + co) * kP + p]; }
+    for (int ci = 0; ci < CI; ++ci) {
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int co = 0; co < CO; ++co) { a1 = fmaf(w1s[co * CI + ci], d1[co], a1); a2 = fmaf(w2s[co * CI + ci], d2[co], a2); }
+      dG[(b * CI + ci) * kP + p] = a1;
+      dXres[(b * CI + ci) * kP + p] = a2;
+    }
+  }
+}
+
+// dW1[co,ci] += sum_e dy1[e,co] G[e,ci]; db1[co] += sum_e dy1[e,co]; same for the residual branch.
+// Each block stages a chunk of kWC (b,p) elements of all channels in shared memory; every thread owns
+// (co, ci) pairs in registers across the block's chunks; one atomicAdd per pair per block at the end.
+constexpr int kWC = 32;
+__global__ void train_mix_bwd_weight_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
+                                            const float* __restrict__ G, const float* __restrict__ X, int64_t B,
+                                            int CI, int CO, float* dW1, float* db1, float* dW2, float* db2) {
+  extern __shared__ float sm[];
+  float* d1s = sm;                       // [CO][kWC]
+  float* d2s = d1s + CO * kWC;           // [CO][kWC]
+  float* gs = d2s + CO * kWC;            // [CI][kWC]
+  float* xs = gs + CI * kWC;             // [CI][kWC]
+  constexpr int MAXP = 16;               // pairs per thread: CO*CI <= 4096 with 256 threads
+  float a1[MAXP], a2[MAXP];
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+  float bsum1 = 0.f, bsum2 = 0.f;        // thread co < CO owns the bias sums
+  const int npair = CO * CI;
+  const int64_t E = B * kP;
+  for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * kWC; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * kWC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (CO + CI) * kWC; i += blockDim.x) {
+      const int c = i / kWC, k = i % kWC;
+      const int64_t e = e0 + k;
+      const bool valid = e < E;
+      const int64_t b = valid ? e / kP : 0;
+      const int p = valid ? static_cast<int>(e - b * kP) : 0;
+      if (c < CO) {
+        d1s[c * kWC + k] = valid ? dy1[(b * CO + c) * kP + p] : 0.f;
+        d2s[c * kWC + k] = valid ? dy2[(b * CO + c) * kP + p] : 0.f;
+      } else {
+        gs[(c - CO) * kWC + k] = valid ? G[(b * CI + (c - CO)) * kP + p] : 0.f;
+        xs[(c - CO) * kWC + k] = valid ? X[(b * CI + (c - CO)) * kP + p] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      const int pr = threadIdx.x + j * kTrainThreads;
+      if (pr < npair) {
+        const int co = pr / CI, ci = pr % CI;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < kWC; ++k) { s1 = fmaf(d1s[co * kWC + k], gs[ci * kWC + k], s1); s2 = fmaf(d2s[co * kWC + k], xs[ci * kWC + k], s2); }
+        a1[j] += s1; a2[j] += s2;
+      }
+    }
+    if (threadIdx.x < CO) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < kWC; ++k) { s1 += d1s[threadIdx.x * kWC + k]; s2 += d2s[threadIdx.x * kWC + k]; }
+      bsum1 += s1; bsum2 += s2;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int pr = threadIdx.x + j * kTrainThreads;
+    if (pr < npair) { atomicAdd(dW1 + pr, a1[j]); atomicAdd(dW2 + pr, a2[j]); }
+  }
+  if (threadIdx.x < CO) { if (db1) atomicAdd(db1 + threadIdx.x, bsum1); if (db2) atomicAdd(db2 + threadIdx.x, bsum2); }
+}
+
+// ---- linear layers over the flattened features ------------------------------------------------------
+// W(d, f) = W[d*sd + f*sf]:  btlnk / fc_* weight [D,F]: sd = F, sf = 1;  rev_btlnk weight [F,D]: sd = 1, sf = D
+// out[b,d] = sum_f A[b,f] W(d,f) + bias[d]           (wide-in: head forward, rev_btlnk input gradient)
+template <int DMAX>
+__global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __restrict__ W, int64_t sd, int64_t sf,
+                                    const float* __restrict__ bias, int64_t B, int F, int D, float* __restrict__ out) {
+  const int64_t b = blockIdx.x;
+  if (b >= B) return;
+  float acc[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) acc[d] = 0.f;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const float a = A[b * F + f];
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) if (d < D) acc[d] = fmaf(a, W[d * sd + f * sf], acc[d]);
+  }
+  __shared__ float sh[DMAX][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) { const float s = warp_sum(acc[d]); if (lane == 0) sh[d][warp] = s; }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float s = bias ? bias[threadIdx.x] : 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
+    out[b * D + threadIdx.x] = s;
+  }
+}
+// out[b,f] = sum_d a[b,d] W(d,f) + bias[f]           (wide-out: rev_btlnk forward, head input gradient)
+template <int DMAX>
+__global__ void lin_expand_f_kernel(const float* __restrict__ a, const float* __restrict__ W, int64_t sd, int64_t sf,
+                                    const float* __restrict__ bias, int64_t B, int F, int D, float* __restrict__ out) {
+  const int64_t n = B * F;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = e / F;
+    const int f = static_cast<int>(e - b * F);
+    float s = bias ? bias[f] : 0.f;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) if (d < D) s = fmaf(a[b * D + d], W[d * sd + f * sf], s);
+    out[e] = s;
+  }
+}
+// dW(d,f) += sum_b a[b,d] A[b,f];  grid (ceil(F/256), NB)
+template <int DMAX>
+__global__ void lin_wgrad_kernel(const float* __restrict__ a, const float* __restrict__ A, int64_t sd, int64_t sf,
+                                 int64_t B, int F, int D, float* dW) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) acc[d] = 0.f;
+  if (f < F) {
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+      const float v = A[b * F + f];
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) if (d < D) acc[d] = fmaf(a[b * D + d], v, acc[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) if (d < D) atomicAdd(dW + d * sd + f * sf, acc[d]);
+  }
+}
+// column sums: out[j] += sum_b a[b, j]   (bias gradients), one block per 32 columns
+__global__ void col_sum_kernel(const float* __restrict__ a, int64_t B, int N, float* out) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int row0 = threadIdx.x >> 5, nrow = blockDim.x >> 5;
+  float s = 0.f;
+  if (j < N) for (int64_t b = row0; b < B; b += nrow) s += a[b * N + j];
+  __shared__ float sh[8][33];
+  sh[row0][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (row0 == 0 && j < N) {
+    float t = 0.f;
+    for (int r = 0; r < nrow; ++r) t += sh[r][threadIdx.x & 31];
+    atomicAdd(out + j, t);
+  }
+}
+
+}  // namespace coskad

@@ -1,0 +1,227 @@
+"""Training path: autograd Functions over the per-layer CUDA kernels (csrc/train_ops.cuh).
+
+Reference semantics reproduced (autograd of the module graph):
+    ST_GCNN_layer.forward          models/graph_layers/stsgcn.py:94-116   (train-mode BatchNorm2d, PReLU)
+    Encoder / Decoder              models/common/components.py:94-105,168-179
+    STSE.encode / STSAE.decode     models/sts/ae.py:76-105,210-230
+BatchNorm uses per-GPU batch statistics (the reference has no SyncBN) and updates the running
+statistics in place exactly like nn.BatchNorm2d (momentum 0.1, unbiased variance, num_batches_tracked).
+The eval-mode variant of the same per-layer kernels (running statistics) serves the decode-only path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+P = 12 * 17
+
+
+def _ctx(t: torch.Tensor) -> _lib.Context:
+    return _lib.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _LayerFn(torch.autograd.Function):
+    """one ST_GCNN_layer, train (batch statistics) or eval (running statistics) BatchNorm"""
+
+    @staticmethod
+    def forward(ctx, X, A, T, W1, b1, g1, be1, W2, b2, g2, be2, slope, layer, training):
+        X = _f32c(X)
+        B, CI = X.shape[0], X.shape[1]
+        CO = W1.shape[0]
+        c = _ctx(X)
+        st = _lib.stream_ptr(X.device)
+        lib = c.lib
+        G1 = torch.empty_like(X)
+        G = torch.empty_like(X)
+        c.check(lib.coskad_train_contract_fwd(c.h, X.data_ptr(), A.data_ptr(), T.data_ptr(), B * CI, G1.data_ptr(),
+                                              G.data_ptr(), st), 'coskad_train_contract_fwd')
+        y1 = torch.empty((B, CO, X.shape[2], X.shape[3]), device=X.device, dtype=torch.float32)
+        y2 = torch.empty_like(y1)
+        stats = torch.zeros(4 * CO, device=X.device, dtype=torch.float64)
+        c.check(lib.coskad_train_mix_fwd(c.h, G.data_ptr(), X.data_ptr(), W1.data_ptr(), _lib._ptr(b1), W2.data_ptr(),
+                                         _lib._ptr(b2), B, CI, CO, y1.data_ptr(), y2.data_ptr(), stats.data_ptr(), st),
+                'coskad_train_mix_fwd')
+        bn1, bn2 = layer.tcn[1], layer.residual[1]
+        if training:
+            mi = torch.empty(4 * CO, device=X.device, dtype=torch.float32)
+            c.check(lib.coskad_train_bn_finalize(c.h, stats.data_ptr(), B * P, CO, float(bn1.eps), float(bn1.momentum),
+                                                 bn1.running_mean.data_ptr(), bn1.running_var.data_ptr(),
+                                                 bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), mi.data_ptr(), st),
+                    'coskad_train_bn_finalize')
+            bn1.num_batches_tracked += 1
+            bn2.num_batches_tracked += 1
+        else:   # eval: normalise with the running statistics (parameter prep, 4*CO numbers)
+            mi = torch.cat([bn1.running_mean, torch.rsqrt(bn1.running_var + bn1.eps),
+                            bn2.running_mean, torch.rsqrt(bn2.running_var + bn2.eps)]).to(torch.float32).contiguous()
+        out = torch.empty_like(y1)
+        c.check(lib.coskad_train_bn_prelu_fwd(c.h, y1.data_ptr(), y2.data_ptr(), mi.data_ptr(), g1.data_ptr(),
+                                              be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(), B, CO,
+                                              out.data_ptr(), st), 'coskad_train_bn_prelu_fwd')
+        ctx.save_for_backward(X, G1, G, y1, y2, mi, A, T, W1, W2, g1, be1, g2, be2, slope)
+        ctx.has_b = (b1 is not None, b2 is not None)
+        ctx.training = training
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        X, G1, G, y1, y2, mi, A, T, W1, W2, g1, be1, g2, be2, slope = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError('backward through an eval-mode ST_GCNN layer is not implemented (train() the model)')
+        dout = _f32c(dout)
+        B, CI, CO = X.shape[0], X.shape[1], W1.shape[0]
+        c = _ctx(X)
+        st = _lib.stream_ptr(X.device)
+        lib = c.lib
+        red = torch.zeros(3 * CO + 1, device=X.device, dtype=torch.float64)
+        dy1 = torch.empty_like(y1)
+        dy2 = torch.empty_like(y2)
+        c.check(lib.coskad_train_bn_prelu_bwd(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
+                                              g1.data_ptr(), be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(),
+                                              B, CO, red.data_ptr(), dy1.data_ptr(), dy2.data_ptr(), st),
+                'coskad_train_bn_prelu_bwd')
+        dG = torch.empty_like(X)
+        dXres = torch.empty_like(X)
+        dW1 = torch.zeros_like(W1)
+        dW2 = torch.zeros_like(W2)
+        db1 = torch.zeros(CO, device=X.device, dtype=torch.float32)
+        db2 = torch.zeros(CO, device=X.device, dtype=torch.float32)
+        c.check(lib.coskad_train_mix_bwd(c.h, dy1.data_ptr(), dy2.data_ptr(), G.data_ptr(), X.data_ptr(), W1.data_ptr(),
+                                         W2.data_ptr(), B, CI, CO, dG.data_ptr(), dXres.data_ptr(), dW1.data_ptr(),
+                                         db1.data_ptr(), dW2.data_ptr(), db2.data_ptr(), st), 'coskad_train_mix_bwd')
+        dX = torch.empty_like(X)
+        dA = torch.zeros_like(A)
+        dT = torch.zeros_like(T)
+        c.check(lib.coskad_train_contract_bwd(c.h, dG.data_ptr(), dXres.data_ptr(), X.data_ptr(), G1.data_ptr(),
+                                              A.data_ptr(), T.data_ptr(), B * CI, dX.data_ptr(), dA.data_ptr(),
+                                              dT.data_ptr(), st), 'coskad_train_contract_bwd')
+        redf = red.to(torch.float32)
+        dbeta = redf[:CO]
+        return (dX, dA, dT, dW1, db1 if ctx.has_b[0] else None, redf[CO:2 * CO], dbeta,
+                dW2, db2 if ctx.has_b[1] else None, redf[2 * CO:3 * CO], dbeta.clone(), redf[3 * CO:3 * CO + 1], None, None)
+
+
+def layer_forward(layer, X: torch.Tensor, training: bool) -> torch.Tensor:
+    if isinstance(layer.residual, torch.nn.Identity):
+        raise NotImplementedError('identity residual (c_in == c_out) does not occur in any COSKAD config; not implemented '
+                                  'in the training kernels')
+    conv1, bn1, conv2, bn2 = layer.tcn[0], layer.tcn[1], layer.residual[0], layer.residual[1]
+    return _LayerFn.apply(X, layer.gcn.A, layer.gcn.T, conv1.weight, conv1.bias, bn1.weight, bn1.bias,
+                          conv2.weight, conv2.bias, bn2.weight, bn2.bias, layer.prelu.weight, layer, training)
+
+
+class _LinearReduceFn(torch.autograd.Function):
+    """out[B,D] = H[B,F] W^T + b  with W [D,F]  (btlnk / fc_mean / fc_var, models/sts/ae.py:155-157)"""
+
+    @staticmethod
+    def forward(ctx, H, W, bias):
+        H = _f32c(H)
+        B, F = H.shape
+        D = W.shape[0]
+        c = _ctx(H)
+        out = torch.empty((B, D), device=H.device, dtype=torch.float32)
+        c.check(c.lib.coskad_train_linear(c.h, 0, None, H.data_ptr(), W.data_ptr(), 0, _lib._ptr(bias), B, F, D,
+                                          out.data_ptr(), _lib.stream_ptr(H.device)), 'coskad_train_linear(0)')
+        ctx.save_for_backward(H, W)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        H, W = ctx.saved_tensors
+        dz = _f32c(dz)
+        B, F = H.shape
+        D = W.shape[0]
+        c = _ctx(H)
+        st = _lib.stream_ptr(H.device)
+        dH = torch.empty_like(H)
+        c.check(c.lib.coskad_train_linear(c.h, 1, dz.data_ptr(), None, W.data_ptr(), 0, None, B, F, D, dH.data_ptr(), st),
+                'coskad_train_linear(1)')
+        dW = torch.zeros_like(W)
+        c.check(c.lib.coskad_train_linear(c.h, 2, dz.data_ptr(), H.data_ptr(), None, 0, None, B, F, D, dW.data_ptr(), st),
+                'coskad_train_linear(2)')
+        db = None
+        if ctx.has_bias:
+            db = torch.zeros(D, device=H.device, dtype=torch.float32)
+            c.check(c.lib.coskad_train_col_sum(c.h, dz.data_ptr(), B, D, db.data_ptr(), st), 'coskad_train_col_sum')
+        return dH, dW, db
+
+
+class _LinearExpandFn(torch.autograd.Function):
+    """out[B,F] = z[B,D] W^T + b  with W [F,D]  (rev_btlnk, models/sts/ae.py:206,222)"""
+
+    @staticmethod
+    def forward(ctx, z, W, bias):
+        z = _f32c(z)
+        B, D = z.shape
+        F = W.shape[0]
+        c = _ctx(z)
+        out = torch.empty((B, F), device=z.device, dtype=torch.float32)
+        c.check(c.lib.coskad_train_linear(c.h, 1, z.data_ptr(), None, W.data_ptr(), 1, _lib._ptr(bias), B, F, D,
+                                          out.data_ptr(), _lib.stream_ptr(z.device)), 'coskad_train_linear(1)')
+        ctx.save_for_backward(z, W)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dH):
+        z, W = ctx.saved_tensors
+        dH = _f32c(dH)
+        B, D = z.shape
+        F = W.shape[0]
+        c = _ctx(z)
+        st = _lib.stream_ptr(z.device)
+        dz = torch.empty_like(z)
+        c.check(c.lib.coskad_train_linear(c.h, 0, None, dH.data_ptr(), W.data_ptr(), 1, None, B, F, D, dz.data_ptr(), st),
+                'coskad_train_linear(0)')
+        dW = torch.zeros_like(W)
+        c.check(c.lib.coskad_train_linear(c.h, 2, z.data_ptr(), dH.data_ptr(), None, 1, None, B, F, D, dW.data_ptr(), st),
+                'coskad_train_linear(2)')
+        db = None
+        if ctx.has_bias:
+            db = torch.zeros(F, device=z.device, dtype=torch.float32)
+            c.check(c.lib.coskad_train_col_sum(c.h, dH.data_ptr(), B, F, db.data_ptr(), st), 'coskad_train_col_sum')
+        return dz, dW, db
+
+
+def linear_reduce(H, W, bias):
+    return _LinearReduceFn.apply(H, W, bias)
+
+
+def linear_expand(z, W, bias):
+    return _LinearExpandFn.apply(z, W, bias)
+
+
+def stack_forward(stack, X: torch.Tensor, training: bool) -> torch.Tensor:
+    for layer in stack.model:
+        X = layer_forward(layer, X, training)
+    return X
+
+
+def encoder_features(model, X: torch.Tensor, training: bool = True) -> torch.Tensor:
+    """flattened (c,t,v) encoder output [B, F] (models/sts/ae.py:88-100)"""
+    H = stack_forward(model.encoder, X, training)
+    return H.reshape(H.shape[0], -1)
+
+
+def stse_train_forward(model, X: torch.Tensor) -> torch.Tensor:
+    return linear_reduce(encoder_features(model, X, True), model.btlnk.weight, model.btlnk.bias)
+
+
+def decode_forward(model, Z: torch.Tensor, training: Optional[bool] = None) -> torch.Tensor:
+    """STSAE.decode (models/sts/ae.py:210-230): rev_btlnk, view [B,H,T,V], decoder stack"""
+    training = model.training if training is None else training
+    H = linear_expand(Z, model.rev_btlnk.weight, model.rev_btlnk.bias)
+    H = H.view(Z.shape[0], model.hidden_dimension, model.n_frames, model.n_joints)
+    return stack_forward(model.decoder, H, training)
+
+
+def stsae_train_forward(model, X: torch.Tensor):
+    Z = stse_train_forward(model, X)
+    return Z, decode_forward(model, Z, True)

@@ -165,8 +165,45 @@ int coskad_frame_aggregate(coskad_ctx* ctx, const float* score, const int64_t* f
                            int64_t total_person_frames, int64_t max_clip_frames,
                            double* person_out, double* out, void* stream);
 
-/* ---- training path (per-layer kernels, train-mode BatchNorm) -----------------------------------
- * declared in the second half of this header once implemented: see coskad_train_* below. */
+/* ---- training path (per-layer kernels, train-mode BatchNorm with per-GPU batch statistics) ------
+ * Activations are [B, C, 204] float32 in HBM between kernels (the batch statistics of BatchNorm sit
+ * between the convolution and the activation).  Gradient buffers that are ACCUMULATED into (dA, dT,
+ * dW*, db*, stats, red, linear mode 2 / col_sum outputs) must be zeroed by the caller.
+ * replaces: ST_GCNN_layer.forward under autograd, models/graph_layers/stsgcn.py:94-156 */
+/* G1 = einsum('nctv,vtq->ncqv', X, T); G = einsum('nctv,tvw->nctw', G1, A); R = B*C rows  (stsgcn.py:154-155) */
+int coskad_train_contract_fwd(coskad_ctx* ctx, const float* X, const float* A, const float* T, int64_t R,
+                              float* G1, float* G, void* stream);
+/* dX = dXres (nullable) + T^T A^T dG;  dA += G1 (x) dG;  dT += X (x) dG1 */
+int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const float* dXres, const float* X, const float* G1,
+                              const float* A, const float* T, int64_t R, float* dX, float* dA, float* dT, void* stream);
+/* y1 = conv1x1(G; W1,b1), y2 = conv1x1(X; W2,b2)  (stsgcn.py:57,71); stats (double)[4*CO] += sum y1, sum y1^2, sum y2, sum y2^2 */
+int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1,
+                         const float* W2, const float* b2, int64_t B, int CI, int CO, float* y1, float* y2,
+                         double* stats, void* stream);
+/* mi[4*CO] = mean1, invstd1, mean2, invstd2 (biased variance, eps); running stats updated like nn.BatchNorm2d
+ * (momentum, unbiased variance); n_per_channel = B*204 */
+int coskad_train_bn_finalize(coskad_ctx* ctx, const double* stats, int64_t n_per_channel, int CO, float eps,
+                             float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi, void* stream);
+/* out = PReLU(BN1(y1) + BN2(y2))   (stsgcn.py:106-110) */
+int coskad_train_bn_prelu_fwd(coskad_ctx* ctx, const float* y1, const float* y2, const float* mi, const float* g1,
+                              const float* be1, const float* g2, const float* be2, const float* slope, int64_t B, int CO,
+                              float* out, void* stream);
+/* red (double)[3*CO+1] += sum ds, sum ds*yhat1, sum ds*yhat2 per channel (= d beta, d gamma1, d gamma2) and d slope;
+ * dy1, dy2 = gradients w.r.t. the conv outputs */
+int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2, const float* mi,
+                              const float* g1, const float* be1, const float* g2, const float* be2, const float* slope,
+                              int64_t B, int CO, double* red, float* dy1, float* dy2, void* stream);
+/* dG = W1^T dy1, dXres = W2^T dy2; dW1 += dy1 G^T, db1 += sum dy1, dW2 += dy2 X^T, db2 += sum dy2 */
+int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const float* dy2, const float* G, const float* X,
+                         const float* W1, const float* W2, int64_t B, int CI, int CO, float* dG, float* dXres,
+                         float* dW1, float* db1, float* dW2, float* db2, void* stream);
+/* linear layers over the F = C*204 flattened features (btlnk / fc_mean / fc_var / rev_btlnk, models/sts/ae.py:155,206):
+ * mode 0: out[B,D] = A_wide[B,F] W^T + bias; mode 1: out[B,F] = a_small[B,D] W + bias[F]; mode 2: out(=dW) += a_small^T A_wide.
+ * w_is_fd = 0: W is [D,F] (btlnk); 1: W is [F,D] (rev_btlnk). */
+int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_small, const float* A_wide, const float* W, int w_is_fd,
+                        const float* bias, int64_t B, int F, int D, float* out, void* stream);
+/* out[N] += column sums of a[B,N] (bias gradients) */
+int coskad_train_col_sum(coskad_ctx* ctx, const float* a, int64_t B, int N, float* out, void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 /* Sustained FP32-FMA rate of the device (TFLOP/s) from a register-resident FFMA loop; used by
