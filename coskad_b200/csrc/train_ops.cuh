@@ -223,6 +223,17 @@ __global__ void train_bn_finalize_kernel(const double* __restrict__ stats, doubl
   }
 }
 
+// BN1(y1) + BN2(y2) with a fixed operation order (explicit rounding intrinsics: no re-contraction), so that the
+// forward and the two backward kernels see bit-identical pre-activations and hence the same PReLU branch.
+__device__ __forceinline__ float bn_pre(float y1, float y2, float m1, float i1, float m2, float i2, float g1, float be1,
+                                        float g2, float be2, float& h1, float& h2) {
+  h1 = __fmul_rn(__fsub_rn(y1, m1), i1);
+  h2 = __fmul_rn(__fsub_rn(y2, m2), i2);
+  return __fadd_rn(__fmaf_rn(h1, g1, be1), __fmaf_rn(h2, g2, be2));
+}
+// nn.PReLU: positive branch iff x > 0 (ATen prelu backward uses the same strict comparison)
+__device__ __forceinline__ float prelu_strict(float v, float a) { return v > 0.f ? v : a * v; }
+
 // out = PReLU(BN1(y1) + BN2(y2))
 __global__ void train_bn_prelu_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ y2,
                                           const float* __restrict__ mi, const float* __restrict__ g1,
@@ -233,8 +244,10 @@ __global__ void train_bn_prelu_fwd_kernel(const float* __restrict__ y1, const fl
   const float a = slope[0];
   for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int co = static_cast<int>((e / kP) % CO);
-    const float h1 = (y1[e] - mi[co]) * mi[CO + co], h2 = (y2[e] - mi[2 * CO + co]) * mi[3 * CO + co];
-    out[e] = prelu(h1 * g1[co] + be1[co] + h2 * g2[co] + be2[co], a);
+    float h1, h2;
+    const float pre = bn_pre(y1[e], y2[e], mi[co], mi[CO + co], mi[2 * CO + co], mi[3 * CO + co], g1[co], be1[co], g2[co],
+                             be2[co], h1, h2);
+    out[e] = prelu_strict(pre, a);
   }
 }
 
@@ -248,18 +261,18 @@ __global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout,
   const int co = blockIdx.x;
   const float a = slope[0];
   const float m1 = mi[co], i1 = mi[CO + co], m2 = mi[2 * CO + co], i2 = mi[3 * CO + co];
-  const float ga1 = g1[co], ga2 = g2[co], bb = be1[co] + be2[co];
+  const float ga1 = g1[co], ga2 = g2[co], bb1 = be1[co], bb2 = be2[co];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int64_t b = static_cast<int64_t>(blockIdx.y) * nwarp + warp; b < B; b += static_cast<int64_t>(gridDim.y) * nwarp) {
     const int64_t base = (b * CO + co) * kP;
     for (int p = lane; p < kP; p += 32) {
-      const float h1 = (y1[base + p] - m1) * i1, h2 = (y2[base + p] - m2) * i2;
-      const float pre = h1 * ga1 + h2 * ga2 + bb;
+      float h1, h2;
+      const float pre = bn_pre(y1[base + p], y2[base + p], m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2);
       const float d = dout[base + p];
-      const float ds = pre >= 0.f ? d : a * d;
+      const float ds = pre > 0.f ? d : a * d;
       s0 += ds; s1 = fmaf(ds, h1, s1); s2 = fmaf(ds, h2, s2);
-      if (pre < 0.f) sa = fmaf(d, pre, sa);
+      if (!(pre > 0.f)) sa = fmaf(d, pre, sa);
     }
   }
   __shared__ float sh[4][8];
@@ -286,10 +299,11 @@ __global__ void train_bn_prelu_bwd_apply_kernel(const float* __restrict__ dout, 
   const double N = static_cast<double>(B) * kP;
   for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int co = static_cast<int>((e / kP) % CO);
-    const float h1 = (y1[e] - mi[co]) * mi[CO + co], h2 = (y2[e] - mi[2 * CO + co]) * mi[3 * CO + co];
-    const float pre = h1 * g1[co] + be1[co] + h2 * g2[co] + be2[co];
+    float h1, h2;
+    const float pre = bn_pre(y1[e], y2[e], mi[co], mi[CO + co], mi[2 * CO + co], mi[3 * CO + co], g1[co], be1[co], g2[co],
+                             be2[co], h1, h2);
     const float d = dout[e];
-    const float ds = pre >= 0.f ? d : a * d;
+    const float ds = pre > 0.f ? d : a * d;
     const float mds = static_cast<float>(red[co] / N);
     const float m1 = static_cast<float>(red[CO + co] / N), m2 = static_cast<float>(red[2 * CO + co] / N);
     dy1[e] = g1[co] * mi[CO + co] * (ds - mds - h1 * m1);

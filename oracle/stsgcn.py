@@ -47,25 +47,33 @@ def _conv_bn(x: Tensor, sd: Dict[str, Tensor], pfx: str, training: bool,
 
 
 def st_gcnn_layer(x: Tensor, sd: Dict[str, Tensor], pfx: str, training: bool = False,
-                  new_stats: Optional[Dict[str, Tensor]] = None) -> Tensor:
-    """ST_GCNN_layer.forward -- stsgcn.py:94-116 (dropout p=0 in every config; emb branch unused)."""
+                  new_stats: Optional[Dict[str, Tensor]] = None, prelu_mask: Optional[Tensor] = None) -> Tensor:
+    """ST_GCNN_layer.forward -- stsgcn.py:94-116 (dropout p=0 in every config; emb branch unused).
+
+    prelu_mask (test aid): use this boolean "positive branch" pattern instead of ``pre > 0``.  fp32
+    implementations legitimately disagree on the sign of pre-activations that are within rounding of
+    zero; fixing the pattern lets the gradient kernels be compared exactly."""
     if (pfx + '.residual.0.weight') in sd:
         res = _conv_bn(x, sd, pfx + '.residual', training, new_stats)       # stsgcn.py:106
     else:
         res = x                                                               # nn.Identity, :80
     g = graph_contract(x, sd[pfx + '.gcn.A'], sd[pfx + '.gcn.T'])            # :107
     y = _conv_bn(g, sd, pfx + '.tcn', training, new_stats)                   # :108
-    return F.prelu(y + res, sd[pfx + '.prelu.weight'])                       # :109-110
+    pre = y + res
+    if prelu_mask is not None:
+        return torch.where(prelu_mask, pre, sd[pfx + '.prelu.weight'] * pre)
+    return F.prelu(pre, sd[pfx + '.prelu.weight'])                           # :109-110
 
 
 def layer_stack(x: Tensor, sd: Dict[str, Tensor], pfx: str, training: bool = False,
                 new_stats: Optional[Dict[str, Tensor]] = None,
-                return_all: bool = False):
+                return_all: bool = False, prelu_masks: Optional[List[Tensor]] = None):
     """Encoder.forward / Decoder.forward -- models/common/components.py:94-105, 168-179."""
     acts = []
     i = 0
     while f'{pfx}.model.{i}.gcn.A' in sd:
-        x = st_gcnn_layer(x, sd, f'{pfx}.model.{i}', training, new_stats)
+        x = st_gcnn_layer(x, sd, f'{pfx}.model.{i}', training, new_stats,
+                          None if prelu_masks is None else prelu_masks[i])
         acts.append(x)
         i += 1
     return (x, acts) if return_all else x
