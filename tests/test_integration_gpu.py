@@ -1,0 +1,111 @@
+"""GPU integration: task modules + trainer + entry-point flow on a synthetic dataset; AUC parity to 4 decimals
+against the oracle pipeline (oracle geometry + oracle aggregation + the same sklearn call) on the same latents."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aggregate as oagg
+from oracle import geoopt_math as ogm
+from oracle import stsgcn as onet
+
+pytestmark = pytest.mark.gpu
+K = torch.tensor(-1.)
+
+
+def _args(tmp_path, **kw):
+    from coskad_b200 import config as ccfg
+    ns = argparse.Namespace(dataset_choice='synthetic', exp_dir=str(tmp_path), dir_name='run', hyperbolic=True,
+                            static_center=False, use_decoder=False, use_vae=False, latent_dim=16, ae_epochs=3, opt_lr=1e-3,
+                            dataset_batch_size=256, dataset_num_transform=2, projector='linear', validation=True, seed=5,
+                            dataset_synthetic_clips=6)
+    for k, v in kw.items():
+        setattr(ns, k, v)
+    return ccfg.init_sub_args(ns)
+
+
+def _oracle_auc(args, model, ds):
+    """reference pipeline on the CPU: oracle STSE eval forward -> geoopt score -> reference aggregation -> AUC"""
+    from sklearn.metrics import roc_auc_score
+    sd = {k[len('model.'):]: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith('model.')}
+    with torch.no_grad():
+        z = onet.stse_forward(ds.x, sd)
+        c = sd['c']
+        if args.hyperbolic:
+            s = ogm.dist(ogm.project(ogm.expmap0(z, k=K), k=K), c, k=K)
+        else:
+            s = torch.mean((c - z) ** 2, dim=-1)
+    nt = args.dataset_num_transform
+    curves = oagg.aggregate_dataset(s.numpy(), ds.trans.numpy(), ds.meta.numpy(), ds.frames.numpy(), ds.clips, nt)
+    gt = np.concatenate([ds.gts[(s_, c_)] for s_, c_, _ in ds.clips])
+    pds = np.mean(np.stack([np.concatenate(curves[t]) for t in range(nt)], 0), 0)
+    return float(roc_auc_score(gt, pds)), s
+
+
+@pytest.mark.parametrize('hyperbolic,static_center', [(True, False), (True, True), (False, False)])
+def test_train_eval_auc_parity(tmp_path, hyperbolic, static_center):
+    from coskad_b200 import tasks
+    from coskad_b200.data import get_dataset_and_loader
+    from coskad_b200.trainer import Trainer, load_checkpoint
+    import eval_COSKAD
+    torch.manual_seed(0)
+    args, ae_args, *_ = _args(tmp_path, hyperbolic=hyperbolic, static_center=static_center)
+    train_ds, train_loader = get_dataset_and_loader(ae_args, 'train')
+    test_ds, test_loader = get_dataset_and_loader(ae_args, 'test')
+    args.gt_table = (test_ds.clips, test_ds.gts)
+    model = tasks.select_task(args)(args)
+    trainer = Trainer(max_epochs=args.ae_epochs, ckpt_dir=args.ckpt_dir, monitor='validation_auc', mode='max', save_top_k=2)
+    trainer.fit(model, train_loader, test_loader)
+    h = trainer.history
+    assert len(h) == 3 and h[-1]['train_loss_mean'] < h[0]['train_loss_mean'], h
+    assert all(np.isfinite(e['validation_auc']) for e in h)
+    # center: single-process reference semantics on the union of the data
+    assert model.model.c.shape == (16,) and bool(torch.isfinite(model.model.c).all())
+    if not static_center:
+        assert len(model.centers) == 4 if hyperbolic else True
+    # checkpoints: top-2, reference key names
+    cks = trainer.best_checkpoints
+    assert 1 <= len(cks) <= 2
+    sd = torch.load(cks[0], weights_only=False)['state_dict']
+    assert 'model.encoder.model.0.gcn.A' in sd and 'model.btlnk.weight' in sd and 'model.c' in sd
+    # eval entry-point flow on a fresh module from the checkpoint
+    model2 = tasks.select_task(args)(args)
+    auc, per_t, curves = eval_COSKAD.evaluate(args, model2, (test_ds, test_loader), ckpt_path=cks[0])
+    ref_auc, ref_scores = _oracle_auc(args, model2, test_ds)
+    assert round(auc, 4) == round(ref_auc, 4), (auc, ref_auc)
+    assert set(per_t) == {0, 1}
+
+
+def test_center_init_matches_reference_semantics(tmp_path):
+    """setup('fit'): c = weighted_midpoint(project(expmap0(z))) over ALL training windows (hyperbolic_encoder.py:101-123)"""
+    from coskad_b200 import tasks
+    from coskad_b200.data import get_dataset_and_loader
+    from coskad_b200.trainer import Trainer
+    torch.manual_seed(1)
+    args, ae_args, *_ = _args(tmp_path, ae_epochs=0)
+    ds, loader = get_dataset_and_loader(ae_args, 'train')
+    model = tasks.LitEncoder(args)
+    Trainer(max_epochs=0, verbose=False).fit(model, loader)
+    sd = {k[len('model.'):]: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith('model.')}
+    with torch.no_grad():
+        z = onet.stse_forward(ds.x, sd)
+        c_ref = ogm.weighted_midpoint(ogm.project(ogm.expmap0(z, k=K), k=K), k=K)
+    assert torch.allclose(model.model.c.cpu(), c_ref, rtol=1e-4, atol=1e-6), (model.model.c.cpu(), c_ref)
+
+
+def test_autoencoder_task_runs(tmp_path):
+    from coskad_b200 import tasks
+    from coskad_b200.data import get_dataset_and_loader
+    from coskad_b200.trainer import Trainer
+    torch.manual_seed(2)
+    args, ae_args, *_ = _args(tmp_path, hyperbolic=False, use_decoder=True, latent_dim=8, ae_epochs=2)
+    _, train_loader = get_dataset_and_loader(ae_args, 'train')
+    test_ds, test_loader = get_dataset_and_loader(ae_args, 'test')
+    args.gt_table = (test_ds.clips, test_ds.gts)
+    model = tasks.select_task(args)(args)
+    assert isinstance(model, tasks.LitAutoEncoder)
+    tr = Trainer(max_epochs=2, verbose=False).fit(model, train_loader, test_loader)
+    assert tr.history[-1]['train_loss_mean'] < tr.history[0]['train_loss_mean']
+    assert 0.0 <= tr.history[-1]['validation_auc'] <= 1.0
