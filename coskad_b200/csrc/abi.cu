@@ -339,6 +339,16 @@ extern "C" int coskad_dist0(coskad_ctx* ctx, const float* x, int64_t B, int D, f
   return COSKAD_OK;
 }
 
+extern "C" int coskad_ps_sample(coskad_ctx* ctx, const float* mu, const float* t, const float* v, int64_t B, int D,
+                                float* z, void* stream_) {
+  CHECK_BD();
+  if (D < 2 || D > 32) return fail(ctx, COSKAD_ERR_ARG, "ps_sample supports 2 <= D <= 32");
+  if (!mu || !t || !v || !z) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  ps_sample_kernel<<<row_grid(ctx, B), kRowWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(mu, t, v, B, D, z);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
 extern "C" int coskad_poincare_score_bwd(coskad_ctx* ctx, const float* z, const float* center, const float* dscore,
                                          int64_t B, int D, int with_project, float* dz, void* stream_) {
   CHECK_BD();

@@ -79,6 +79,27 @@ __global__ void dist0_kernel(const float* __restrict__ x, int64_t B, int D, floa
   }
 }
 
+// PowerSpherical reparameterised sample from explicit noise (models/sts/vae.py:110,129; power_spherical's
+// _TTransform + _HouseholderRotationTransform): y = [t, sqrt(clamp(1-t^2,1e-7)) v]; u = (e1 - mu)/(|e1 - mu| + 1e-5);
+// z = y - 2 <y,u> u.   mu [B,d], t [B], v [B,d-1] (unit vectors), d <= 32, one warp per row.
+__global__ void ps_sample_kernel(const float* __restrict__ mu, const float* __restrict__ t, const float* __restrict__ v,
+                                 int64_t B, int d, float* __restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    const float tt = t[r];
+    float y = 0.f, u = 0.f;
+    if (lane < d) {
+      y = (lane == 0) ? tt : v[r * (d - 1) + lane - 1] * sqrtf(fmaxf(1.f - tt * tt, 1e-7f));
+      u = ((lane == 0) ? 1.f : 0.f) - mu[r * d + lane];
+    }
+    const float un = sqrtf(warp_sum(u * u)) + 1e-5f;
+    u = u / un;
+    const float dot = warp_sum(y * u);
+    if (lane < d) z[r * d + lane] = y - 2.f * dot * u;
+  }
+}
+
 // ---- center partial sums ----------------------------------------------------------------------
 // POINCARE (gmath.weighted_midpoint, weights=None): gamma_i = lambda_x(x_i) = 2 / max(1 - |x_i|^2, 1e-15)
 // evaluated in float32 like the reference; the sums over windows run in float64.

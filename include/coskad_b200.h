@@ -126,6 +126,10 @@ int coskad_dist(coskad_ctx* ctx, int flavour, const float* a, const float* b, in
                 int64_t B, int D, float* out, void* stream);
 /* dist0(x) = 2 artanh(||x||).   replaces: models/hyperbolic_encoder.py:181 */
 int coskad_dist0(coskad_ctx* ctx, const float* x, int64_t B, int D, float* out, void* stream);
+/* PowerSpherical reparameterised sample from explicit noise: z = Householder_{e1->mu}([t, sqrt(1-t^2) v]);
+ * mu [B,D] unit vectors, t [B] = 2 Beta(alpha,beta) - 1, v [B,D-1] unit vectors.
+ * replaces: PowerSpherical(loc, scale).rsample() models/sts/vae.py:110,129 (power_spherical, un-vendored) */
+int coskad_ps_sample(coskad_ctx* ctx, const float* mu, const float* t, const float* v, int64_t B, int D, float* z, void* stream);
 /* backward of score = dist(project?(expmap0(z)), c) w.r.t. z (training loss, hyperbolic_encoder.py:147-157),
  * arg order dist(c, x) as in training. dz[B,D] = dscore[B] * d score/d z. */
 int coskad_poincare_score_bwd(coskad_ctx* ctx, const float* z, const float* center, const float* dscore,

@@ -126,3 +126,21 @@ def test_frame_id_zero_wraps_and_zero_scores_are_absent():
     assert pose[0, -1] == 0.5 and pose[0, 0] == 0.5 and pose[0, 1] == 0.5
     cur = oagg.person_curve(loss, frames, 6)
     assert np.array_equal(cur, np.array([0.5, 0.5, 0, 0, 0, 0.5]))
+
+
+def test_power_spherical_restatement_properties():
+    """power_spherical is un-vendored upstream (parity unpinned): check defining properties of the restatement"""
+    from oracle import power_spherical as ops
+    g = torch.Generator().manual_seed(0)
+    mu = torch.nn.functional.normalize(torch.randn(2000, 8, generator=g), dim=-1)
+    kappa = torch.full((2000,), 30.0)
+    t, v = ops.draw_noise(kappa, 8, generator=g)
+    z = ops.rsample_from_noise(mu, t, v)
+    assert torch.allclose(z.norm(dim=-1), torch.ones(2000), atol=1e-3)            # samples live on the sphere
+    assert float((z * mu).sum(-1).mean()) > 0.8                                     # concentrated around loc
+    assert torch.allclose((z * mu).sum(-1), t.squeeze(-1), atol=2e-3)               # <z, mu> = t (Householder maps e1 -> mu)
+    # entropy decreases with concentration and tends to the uniform entropy as kappa -> 0
+    k = torch.tensor([1e-4, 1.0, 10.0, 100.0])
+    h = ops.ps_entropy(k, 8)
+    assert bool((h[1:] < h[:-1]).all()) and abs(float(h[0]) - ops.hu_entropy(8)) < 1e-3
+    assert bool((ops.kl_ps_uniform(k, 8) >= -1e-6).all())

@@ -1,0 +1,124 @@
+"""GPU parity of the spherical-VAE variant (use_vae) against the oracle restatements
+(oracle.stsgcn.stsvae_encode: pinned network pieces; oracle.power_spherical: unpinned third-party formulas)."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import power_spherical as ops
+from oracle import stsgcn as onet
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(seed=2):
+    from coskad_b200 import spherical
+    sd = onet.init_state_dict('stsvae', latent_dim=8, seed=seed)
+    m = spherical.STSVAE(2, [32, 16, 32], 64, 8, 12, 17, distribution='ps')
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+def _close(got, ref, rtol=1e-4, atol_scale=1e-5):
+    got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = (got - ref).abs()
+    assert bool((err <= rtol * ref.abs() + atol_scale * float(ref.abs().max())).all()), float(err.max())
+
+
+def test_state_dict_names_match_reference_class():
+    m, sd = _pair()
+    assert sorted(m.state_dict().keys()) == sorted(sd.keys())
+
+
+@pytest.mark.parametrize('B', [1, 5, 700])
+def test_encode_mean_and_concentration(B):
+    m, sd = _pair()
+    x = onet.synth_windows(B, seed=B)
+    with torch.no_grad():
+        zm_r, zv_r = onet.stsvae_encode(x, sd)
+    zm, zv = m.encode(x.cuda())
+    _close(zm, zm_r)
+    _close(zv, zv_r)
+    assert torch.allclose(zm.norm(dim=-1), torch.ones(B, device='cuda'), atol=1e-5)
+    assert float(zv.min()) > 1.0
+
+
+def test_power_spherical_sample_kernel():
+    from coskad_b200.spherical import ps_sample
+    g = torch.Generator().manual_seed(0)
+    mu = torch.nn.functional.normalize(torch.randn(3000, 8, generator=g), dim=-1)
+    mu[0] = torch.tensor([1., 0, 0, 0, 0, 0, 0, 0])           # loc == e1: the reflection degenerates to identity
+    kappa = torch.rand(3000, generator=g) * 50 + 1
+    t, v = ops.draw_noise(kappa, 8, generator=g)
+    ref = ops.rsample_from_noise(mu, t, v)
+    got = ps_sample(mu.cuda(), t.cuda(), v.cuda())
+    _close(got, ref, 1e-4, 1e-6)
+    assert torch.allclose(got.norm(dim=-1).cpu(), torch.ones(3000), atol=1e-3)
+
+
+def test_forward_with_explicit_noise_and_cosine_score():
+    from coskad_b200 import gmath
+    m, sd = _pair()
+    x = onet.synth_windows(300, seed=9)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        zm_r, zv_r = onet.stsvae_encode(x, sd)
+        t, v = ops.draw_noise(zv_r.squeeze(-1), 8, generator=g)
+        z_r = ops.rsample_from_noise(zm_r, t, v)
+        xh_r = onet.stsae_decode(z_r, sd, x.shape)
+        mean_vec = z_r.mean(dim=0, keepdim=True)                                        # spherical_vae.py:113
+        s_r = 1 - torch.nn.functional.cosine_similarity(mean_vec, z_r)                   # eval_COSKAD.py:81
+    with torch.no_grad():
+        z, xh, (q, p, zv) = m(x.cuda(), noise=(t.squeeze(-1).cuda(), v.cuda()))
+    _close(z, z_r, 1e-4, 1e-5)
+    _close(xh, xh_r, 1e-4, 1e-4)
+    _close(gmath.cosine_score(z, mean_vec.view(-1).cuda()), s_r, 1e-4, 1e-5)
+    # deterministic mode: score of Z_mean through the fused kernel's cosine flavour
+    s_det = m.cosine_scores(x.cuda(), mean_vec.cuda(), sample=False)
+    _close(s_det, 1 - torch.nn.functional.cosine_similarity(mean_vec, zm_r), 1e-4, 1e-5)
+    # KL(PS || U) and entropy (unpinned formulas, same on both sides by construction; checks the plumbing)
+    from coskad_b200.spherical import kl_divergence
+    _close(kl_divergence(q, p), ops.kl_ps_uniform(zv_r.squeeze(-1), 8), 1e-4, 1e-5)
+
+
+def test_training_loss_parity_and_finite_grads():
+    """phi*mse + alpha*reg + beta*KL + gamma*mean(1/kappa)  (models/spherical_vae.py:81-107), same noise both sides"""
+    from coskad_b200.losses import calc_reg_loss
+    from coskad_b200.spherical import kl_divergence
+    m, sd = _pair()
+    m.train()
+    x = onet.synth_windows(64, seed=4)
+    zm_r, zv_r = onet.stsvae_encode(x, sd, training=True, new_stats={})
+    g = torch.Generator().manual_seed(3)
+    t, v = ops.draw_noise(zv_r.detach().squeeze(-1), 8, generator=g)
+    z_r = ops.rsample_from_noise(zm_r, t, v)
+    xh_r = onet.stsae_decode(z_r, sd, x.shape, training=True, new_stats={})
+    loss_r = torch.nn.functional.mse_loss(xh_r, x) + 1e-3 * ops.kl_ps_uniform(zv_r.squeeze(-1), 8).mean() + \
+        1e-2 * (1 / zv_r).mean()
+    z, xh, (q, p, zv) = m(x.cuda(), noise=(t.squeeze(-1).cuda(), v.cuda()))
+    loss = torch.nn.functional.mse_loss(xh, x.cuda()) + 1e-3 * kl_divergence(q, p).mean() + 1e-2 * (1 / zv).mean()
+    assert abs(float(loss.detach()) - float(loss_r.detach())) <= 2e-5 * abs(float(loss_r.detach()))
+    (loss + 1e-6 * calc_reg_loss(m)).backward()
+    for k, p_ in m.named_parameters():
+        assert p_.grad is not None and bool(torch.isfinite(p_.grad).all()), k
+    assert float(m.fc_var.weight.grad.abs().max()) > 0 and float(m.encoder.model[0].gcn.A.grad.abs().max()) > 0
+
+
+def test_lit_spherical_vae_epoch(tmp_path):
+    from coskad_b200 import config as ccfg, tasks
+    from coskad_b200.data import get_dataset_and_loader
+    from coskad_b200.trainer import Trainer
+    torch.manual_seed(0)
+    ns = argparse.Namespace(dataset_choice='synthetic', exp_dir=str(tmp_path), dir_name='vae', hyperbolic=False, static_center=True,
+                            use_decoder=False, use_vae=True, latent_dim=8, ae_epochs=2, opt_lr=1e-3, dataset_batch_size=256,
+                            dataset_num_transform=1, projector='linear', validation=True, seed=3, beta=1e-3, gamma=1e-2, phi=1.0)
+    args, ae_args, *_ = ccfg.init_sub_args(ns)
+    _, train_loader = get_dataset_and_loader(ae_args, 'train')
+    test_ds, test_loader = get_dataset_and_loader(ae_args, 'test')
+    args.gt_table = (test_ds.clips, test_ds.gts)
+    model = tasks.select_task(args)(args)
+    tr = Trainer(max_epochs=2, verbose=False).fit(model, train_loader, test_loader)
+    assert model.model.mean_vector is not None and model.model.mean_vector.shape == (1, 8)
+    assert all(np.isfinite(e['loss']) and 0 <= e['validation_auc'] <= 1 for e in tr.history)
