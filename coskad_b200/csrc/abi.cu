@@ -10,8 +10,10 @@
 #include "common.cuh"
 #include "fold.cuh"
 #include "fused_eval.cuh"
+#include "fused_eval_tc.cuh"
 #include "latent_ops.cuh"
 #include "train_ops.cuh"
+#include "tc_test.cuh"
 
 using namespace coskad;
 
@@ -26,6 +28,8 @@ struct coskad_ctx {
   bool enc_set = false, dec_set = false;
   int head_rows = 0;
   FusedParams fp{};
+  FusedTcParams tp{};
+  int fused_impl = 1;      // 1 = tensor-core mixing (fused_eval_tc_kernel), 0 = FP32 CUDA-core kernel
   // scratch
   int32_t* cnt_scratch = nullptr;
   size_t cnt_scratch_elems = 0;
@@ -138,6 +142,12 @@ extern "C" int coskad_set_encoder(coskad_ctx* ctx, int n_layers, const coskad_la
   }
   const size_t oHW = off; off += static_cast<size_t>(kDP) * kF;
   const size_t oHB = off; off += kDP;
+  // tensor-core blobs of the mixing stages (fused_eval_tc.cuh)
+  const size_t oT1 = off; off += align4(tc_blob_floats(8, 32));
+  const size_t oT2 = off; off += align4(tc_blob_floats(32, 32));
+  const size_t oT3 = off; off += align4(tc_blob_floats(32, 32));
+  const size_t oT4X = off; off += align4(tc_blob_floats(32, 64));
+  const size_t oT4G = off; off += align4(tc_blob_floats(32, 64));
   if (!ctx->enc_pack) CK(cudaMalloc(&ctx->enc_pack, off * sizeof(float)));
   for (int i = 0; i < 4; ++i) {
     const bool mf = kEncC[i + 1] < kEncC[i];
@@ -151,6 +161,20 @@ extern "C" int coskad_set_encoder(coskad_ctx* ctx, int n_layers, const coskad_la
   CK_LAUNCH();
   ctx->fp.head_w = ctx->enc_pack + oHW;
   ctx->fp.head_b = ctx->enc_pack + oHB;
+  fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[0], 0, 8, 32, ctx->enc_pack + oT1);
+  CK_LAUNCH();
+  fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[1], 1, 32, 32, ctx->enc_pack + oT2);
+  CK_LAUNCH();
+  fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[2], 0, 32, 32, ctx->enc_pack + oT3);
+  CK_LAUNCH();
+  fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[3], 2, 32, 64, ctx->enc_pack + oT4X);
+  CK_LAUNCH();
+  fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[3], 3, 32, 64, ctx->enc_pack + oT4G);
+  CK_LAUNCH();
+  for (int i = 0; i < 4; ++i) { ctx->tp.eTw[i] = ctx->fp.eTw[i]; ctx->tp.eAw[i] = ctx->fp.eAw[i]; }
+  ctx->tp.tcL1 = ctx->enc_pack + oT1; ctx->tp.tcL2 = ctx->enc_pack + oT2; ctx->tp.tcL3 = ctx->enc_pack + oT3;
+  ctx->tp.tcL4X = ctx->enc_pack + oT4X; ctx->tp.tcL4G = ctx->enc_pack + oT4G;
+  ctx->tp.head_w = ctx->fp.head_w; ctx->tp.head_b = ctx->fp.head_b;
   ctx->head_rows = head_rows;
   ctx->enc_set = true;
   return COSKAD_OK;
@@ -219,6 +243,7 @@ static int ensure_smem_attr(coskad_ctx* ctx) {
   if (ctx->smem_attr_set) return COSKAD_OK;
   CK(cudaFuncSetAttribute(fused_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   CK(cudaFuncSetAttribute(fused_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   ctx->smem_attr_set = true;
   return COSKAD_OK;
 }
@@ -245,8 +270,21 @@ extern "C" int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float
   p.B = B; p.head_rows = ctx->head_rows; p.flavour = flavour;
   // the VAE head stacks fc_var under fc_mean: the geometry sees only the latent rows
   p.D = (ctx->head_rows == 9) ? 8 : ctx->head_rows;
-  fused_eval_kernel<false><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  if (ctx->fused_impl == 1) {
+    FusedTcParams t = ctx->tp;
+    t.x = x; t.center = center; t.z = z; t.score = p.score; t.B = B; t.head_rows = p.head_rows; t.D = p.D; t.flavour = flavour;
+    fused_eval_tc_kernel<<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
+  } else {
+    fused_eval_kernel<false><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  }
   CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_set_fused_impl(coskad_ctx* ctx, int impl) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (impl != 0 && impl != 1) return fail(ctx, COSKAD_ERR_ARG, "fused impl must be 0 (FP32 CUDA cores) or 1 (tcgen05 mixing)");
+  ctx->fused_impl = impl;
   return COSKAD_OK;
 }
 
@@ -285,6 +323,16 @@ extern "C" int coskad_debug_fused_stage(coskad_ctx* ctx, int with_decoder, const
   p.dbg = dbg_out; p.dbg_stage = stage;
   if (with_decoder) fused_eval_kernel<true><<<1, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
   else fused_eval_kernel<false><<<1, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+// test aid: out[128,N] = A[128,K] W^T on the tcgen05 path (3xTF32), W given as K-major canonical images (hi, lo)
+extern "C" int coskad_debug_tc_mix(coskad_ctx* ctx, const float* A, const float* Bhi, const float* Blo, int K, int N,
+                                   int swap_strides, float* out, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (K % 16 != 0 || K < 16 || K > 64 || N % 16 != 0 || N < 16 || N > 64) return fail(ctx, COSKAD_ERR_ARG, "tc test: K,N in {16..64} multiples of 16");
+  CK(cudaSetDevice(ctx->device));
+  tc_mix_test_kernel<<<1, 128, 2 * N * K * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(A, Bhi, Blo, K, N, swap_strides, out);
   CK_LAUNCH();
   return COSKAD_OK;
 }

@@ -60,6 +60,39 @@ __global__ void fold_layer_kernel(coskad_layer_params L, int mix_first, float* T
   if (tid < 4) Wm[K * COUT + COUT + tid] = (tid == 0) ? L.prelu[0] : 0.f;
 }
 
+// ---- tensor-core blobs: [B_hi image Kp*N][B_lo image Kp*N][bias N][slope,0,0,0] -----------------------------------
+// image = canonical K-major, no swizzle: float index ((k/4)*(N/8) + co/8)*32 + (co%8)*4 + (k%4); hi = value with the low
+// 13 mantissa bits cleared (exact TF32), lo = TF32-truncated remainder.
+// mode 0: K = [G (c_in) | X (c_in)] padded to Kp, N = c_out        (normal layer: L1, L3)
+// mode 1: K = X (c_in), N = [U (c_out) | Rsd (c_out)]               (mix-first layer: L2)
+// mode 2: K = X (c_in), N = c_out, residual conv only, no bias       (L4 residual half)
+// mode 3: K = G (c_in), N = c_out, tcn conv, bias + slope            (L4 graph half)
+__global__ void fold_layer_tc_kernel(coskad_layer_params L, int mode, int Kp, int N, float* blob) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int ci_n = L.c_in, co_n = L.c_out;
+  for (int i = tid; i < Kp * N; i += nth) {
+    const int k = i / N, co = i % N;
+    double v = 0.0;
+    if (mode == 0) { if (k < ci_n) v = fold_w1(L, co, k); else if (k < 2 * ci_n) v = fold_w2(L, co, k - ci_n); }
+    else if (mode == 1) { if (k < ci_n) v = (co < co_n) ? fold_w1(L, co, k) : fold_w2(L, co - co_n, k); }
+    else if (mode == 2) { if (k < ci_n) v = fold_w2(L, co, k); }
+    else { if (k < ci_n) v = fold_w1(L, co, k); }
+    const float f = static_cast<float>(v);
+    const float hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);
+    const float lo = __uint_as_float(__float_as_uint(f - hi) & 0xFFFFE000u);
+    const int idx = ((k / 4) * (N / 8) + co / 8) * 32 + (co % 8) * 4 + (k % 4);
+    blob[idx] = hi;
+    blob[Kp * N + idx] = lo;
+  }
+  for (int j = tid; j < N; j += nth) {
+    double b = 0.0;
+    if (mode == 0 || mode == 3) b = fold_b(L, j);
+    else if (mode == 1) b = (j < co_n) ? 0.0 : fold_b(L, j - co_n);
+    blob[2 * Kp * N + j] = static_cast<float>(b);
+  }
+  if (tid < 4) blob[2 * Kp * N + N + tid] = (tid == 0) ? L.prelu[0] : 0.f;
+}
+
 // head rows padded to kDP with zeros
 __global__ void pack_head_kernel(const float* w, const float* b, int rows, float* wp, float* bp) {
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;

@@ -79,11 +79,11 @@ __device__ __forceinline__ void async_copy_floats(float* dst, const float* src, 
 
 // temporal contraction: dst[row][q][v] = sum_t src[row][t][v] * Tw[v][t][q]   (stsgcn.py:154)
 // lanes walk rows (= window*C + channel), v is warp-uniform.  src == dst is allowed.
-template <int ROWS>
+template <int ROWS, int NWARPS = kWarps>
 __device__ __forceinline__ void temporal_stage(const float* src, float* dst, const float* Tw, int warp, int lane) {
   constexpr int CHUNKS = (ROWS + 31) / 32;
   constexpr int NTASK = kV * CHUNKS;
-  for (int task = warp; task < NTASK; task += kWarps) {
+  for (int task = warp; task < NTASK; task += NWARPS) {
     const int v = task % kV;
     const int row = (task / kV) * 32 + lane;
     if (row < ROWS) {
@@ -123,11 +123,11 @@ struct EpiAddResPrelu {
 };
 
 // spatial contraction in place: buf[row][t][w] = epi(sum_v buf[row][t][v] * Aw[t][v][w])   (stsgcn.py:155)
-template <int ROWS, class Epi>
+template <int ROWS, class Epi, int NWARPS = kWarps>
 __device__ __forceinline__ void spatial_stage(float* buf, const float* Aw, const Epi epi, int warp, int lane) {
   constexpr int CHUNKS = (ROWS + 31) / 32;
   constexpr int NTASK = kT * CHUNKS;
-  for (int task = warp; task < NTASK; task += kWarps) {
+  for (int task = warp; task < NTASK; task += NWARPS) {
     const int t = task % kT;
     const int row = (task / kT) * 32 + lane;
     if (row < ROWS) {

@@ -1,0 +1,404 @@
+// fused_eval_tc.cuh -- fused eval hot path, v2: the dense channel mixing (65 % of the MACs) runs on the 5th-gen
+// tensor cores (tcgen05.mma kind::tf32, 3xTF32 split accumulate), the graph contractions, the linear head and the
+// geometry stay on the CUDA cores.  Same arithmetic contract as fused_eval.cuh (see there for the reference
+// citations); score parity rtol 1e-4 is kept by the hi/lo operand split (tc.cuh).
+//
+// Per CTA (one per SM, 384 threads = 12 warps, 227 KB smem, all 512 TMEM columns):
+//   * activations live in shared memory as channel planes [row = window*C + c][205] exactly like v1 (the
+//     contraction stages are unchanged);
+//   * a mixing stage = for each of the 6 M-tiles (window n, position half j: 128 positions) the producer warps read
+//     the K <= 32 input channels of their position from the planes, split them into tf32 hi/lo and tcgen05.st them
+//     into one of two 64-column A buffers in TMEM; one elected thread issues 3 MMAs per 8 channels
+//     (A_hi B_hi + A_lo B_hi + A_hi B_lo) with B = BN-folded weights held in shared memory as canonical K-major
+//     images (hi and lo); accumulators D[128 x N] of all 6 tiles stay in TMEM (6 x 64 columns);
+//   * epilogue: tcgen05.ld -> bias + PReLU -> next layer's planes, or (layer 4) straight into the linear head;
+//   * layer 4 is issued in two phases: the residual half (inputs = H3, known before the graph contraction) is
+//     issued first and executes asynchronously while the CUDA cores run the layer-4 contraction.
+#pragma once
+#include "common.cuh"
+#include "fused_eval.cuh"
+#include "geometry.cuh"
+#include "tc.cuh"
+
+namespace coskad {
+
+constexpr int kTcThreads = 384;
+constexpr int kTcWarps = kTcThreads / 32;        // 12 = 4 TMEM lane quarters x 3 groups
+constexpr int kTcTiles = 2 * kNW;                // M-tiles per CTA tile: (half j, window n) -> ti = j*kNW + n
+constexpr uint32_t kTcColD = 0;                  // D: 64 columns per M-tile
+constexpr uint32_t kTcColA = 64 * kTcTiles;      // A: 2 buffers x (32 hi + 32 lo) columns
+static_assert(kTcColA + 128 <= 512, "TMEM budget");
+
+// blob = [B_hi image Kp*N][B_lo image Kp*N][bias N][slope,0,0,0]
+__host__ __device__ constexpr int tc_blob_floats(int Kp, int N) { return 2 * Kp * N + N + 4; }
+constexpr int kTcWsFloats = tc_blob_floats(32, 32);   // small buffer: L1 (Kp 8), L3
+constexpr int kTcWbFloats = tc_blob_floats(32, 64);   // big buffer: L2, L4 residual half, L4 graph half
+
+struct FusedTcParams {
+  const float* eTw[4];
+  const float* eAw[4];
+  const float* tcL1;      // Kp 8 (G0 c0,c1, X0 c0,c1, 0 x4), N 32
+  const float* tcL2;      // mix-first: K 32 (H1), N 32 = [U 16 | Rsd 16]
+  const float* tcL3;      // K 32 = [G3 16 | H2 16], N 32
+  const float* tcL4X;     // K 32 (H3, residual conv), N 64
+  const float* tcL4G;     // K 32 (G4, tcn conv), N 64, carries bias + slope
+  const float* head_w;    // [16][kF]
+  const float* head_b;    // [16]
+  const float* x;
+  const float* center;
+  float* z;
+  float* score;
+  int64_t B;
+  int head_rows, D, flavour;
+};
+
+constexpr int kTcGB = (kRSmall + 3) & ~3;                             // keep what follows 16-byte aligned (cp.async 16, UMMA descriptors)
+static_assert((2 * kRBig + 2 * kRSmall + kTcGB) % 4 == 0, "weight staging buffers must be 16-byte aligned");
+constexpr int kTcSmemFloats = 2 * kRBig + 2 * kRSmall + kTcGB        // R0, R1, XB[2], GB
+                              + kTwFloats + kAwFloats + kTcWsFloats + kTcWbFloats
+                              + kTcWarps * kNW * kDP + kNW * kDP + 32   // zpart, zfin, center
+                              + 16;                                     // mbarriers (5 x 8 B) + tmem base
+constexpr int kTcSmemBytes = kTcSmemFloats * 4;
+static_assert(kTcSmemBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
+
+struct TcPipe {
+  uint64_t* full;     // [2] A buffer b staged (128 arrivals)
+  uint64_t* empty;    // [2] MMAs reading A buffer b complete (1 arrival: tcgen05.commit)
+  uint64_t* done;     // all MMAs of a phase complete
+  uint32_t tbase;
+  uint32_t n_full[2], n_empty[2], n_done;   // completed-phase counters (identical on every thread)
+};
+
+// One mixing phase over the 6 M-tiles: D[ti] (+)= [src1 | src2](positions of ti, K channels) * B^T.
+// Warps 0-3 stage tiles 0,2,4 into A buffer 0, warps 4-7 tiles 1,3,5 into buffer 1, lane 0 of warp 8 issues.
+// K1 + K2 <= 32; Kp = K rounded up to 8 (the extra columns are staged as zeros).
+template <int K1, int K2, int N>
+__device__ __forceinline__ void tc_mix_phase(TcPipe& P, const float* src1, const float* src2, const float* Bhi, const float* Blo,
+                                             bool accumulate, int warp, int lane) {
+  constexpr int K = K1 + K2;
+  constexpr int Kp = (K + 7) & ~7;
+  static_assert(Kp <= 32 && N % 16 == 0 && N <= 64, "bad mixing phase shape");
+  const int q = warp & 3, sub = warp >> 2;
+  if (sub < 2) {
+    // ---------------- producers
+    const int b = sub;
+    const uint32_t abuf = P.tbase + (static_cast<uint32_t>(q * 32) << 16) + kTcColA + 64u * b;
+    for (int it = 0; it < kTcTiles / 2; ++it) {
+      const int ti = b + 2 * it;
+      const int n = ti % kNW, j = ti / kNW;
+      const int p = j * 128 + q * 32 + lane;
+      const bool valid = p < kP;
+      const int pc = valid ? p : kP - 1;
+      tc::mbar_wait(&P.empty[b], (P.n_empty[b] + it) & 1);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int k0 = 0; k0 < Kp; k0 += 16) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int k = k0 + u;
+          float a = 0.f;
+          if (k < K1) a = src1[(n * K1 + k) * kCS + pc];
+          else if (k < K) a = src2[(n * K2 + (k - K1)) * kCS + pc];
+          if (!valid) a = 0.f;
+          tc::split_tf32(a, hi[u], lo[u]);
+        }
+        tc::tmem_st16(abuf + k0, hi);
+        tc::tmem_st16(abuf + 32 + k0, lo);
+      }
+      tc::wait_st();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&P.full[b]);
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(128, N);
+      constexpr uint32_t lbo = (N / 8) * 128, sbo = 128;
+      const uint32_t bh = tc::smem_u32(Bhi), bl = tc::smem_u32(Blo);
+      for (int ti = 0; ti < kTcTiles; ++ti) {
+        const int b = ti & 1, it = ti >> 1;
+        tc::mbar_wait(&P.full[b], (P.n_full[b] + it) & 1);
+        tc::fence_after_sync();
+        const uint32_t d = P.tbase + kTcColD + 64u * ti;
+        const uint32_t a = P.tbase + kTcColA + 64u * b;
+#pragma unroll
+        for (int kb = 0; kb < Kp / 8; ++kb) {
+          const uint64_t dh = tc::make_smem_desc(bh + kb * 2 * lbo, lbo, sbo);
+          const uint64_t dl = tc::make_smem_desc(bl + kb * 2 * lbo, lbo, sbo);
+          tc::mma_tf32_ts(d, a + kb * 8, dh, idesc, (accumulate || kb > 0) ? 1u : 0u);
+          tc::mma_tf32_ts(d, a + 32 + kb * 8, dh, idesc, 1u);
+          tc::mma_tf32_ts(d, a + kb * 8, dl, idesc, 1u);
+        }
+        tc::mma_commit(&P.empty[b]);
+      }
+      tc::mma_commit(P.done);
+    }
+    __syncwarp();
+  }
+  // every thread advances the phase counters identically (3 completions per A-buffer barrier, 1 for done)
+  P.n_full[0] += kTcTiles / 2; P.n_full[1] += kTcTiles / 2;
+  P.n_empty[0] += kTcTiles / 2; P.n_empty[1] += kTcTiles / 2;
+}
+__device__ __forceinline__ void tc_wait_done(TcPipe& P) {
+  tc::mbar_wait(P.done, P.n_done & 1);
+  P.n_done += 1;
+  tc::fence_after_sync();
+}
+
+// epilogue of layers 1-3: D -> (+bias, PReLU) -> planes dst[(n*COUT + co)][p]; SPLIT: mix-first layout (U | Rsd)
+template <int N, bool SPLIT>
+__device__ __forceinline__ void tc_epilogue_store(const TcPipe& P, float* dst, float* dstR, const float* bias, float slope,
+                                                  int warp, int lane) {
+  const int q = warp & 3, n = warp >> 2;           // group = window
+  constexpr int CO = SPLIT ? N / 2 : N;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ti = j * kNW + n;
+    const int p = j * 128 + q * 32 + lane;
+    const uint32_t d = P.tbase + (static_cast<uint32_t>(q * 32) << 16) + kTcColD + 64u * ti;
+#pragma unroll
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(d + c0, v);
+      tc::wait_ld();
+      if (p < kP) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int co = c0 + u;
+          const float val = __uint_as_float(v[u]) + bias[co];
+          if (SPLIT) {
+            if (co < CO) dst[(n * CO + co) * kCS + p] = val;            // U: bias slot is 0
+            else dstR[(n * CO + co - CO) * kCS + p] = val;              // Rsd + folded bias
+          } else {
+            dst[(n * CO + co) * kCS + p] = prelu(val, slope);
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __grid_constant__ FusedTcParams Pm) {
+  extern __shared__ __align__(128) float smem_tc[];
+  float* R0 = smem_tc;
+  float* R1 = R0 + kRBig;
+  float* XB = R1 + kRBig;
+  float* GB = XB + 2 * kRSmall;
+  float* TB = GB + kTcGB;
+  float* AB = TB + kTwFloats;
+  float* WMs = AB + kAwFloats;
+  float* WMb = WMs + kTcWsFloats;
+  float* zpart = WMb + kTcWbFloats;
+  float* zfin = zpart + kTcWarps * kNW * kDP;
+  float* cen = zfin + kNW * kDP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cen + 32);     // full[2], empty[2], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (Pm.B + kNW - 1) / kNW;
+  // every CTA of the grid has work (grid <= ntiles), so the TMEM allocation below is unconditional
+
+  auto load_x = [&](float* dst, int64_t tile) {
+    const int64_t w0 = tile * kNW;
+    for (int i = tid; i < kNW * 2 * kP; i += kTcThreads) {
+      const int r = i / kP, p = i - r * kP;
+      int64_t w = w0 + (r >> 1);
+      if (w >= Pm.B) w = Pm.B - 1;
+      cp_async4(dst + r * kCS + p, Pm.x + w * (2 * kP) + (r & 1) * kP + p);
+    }
+  };
+  auto acopy = [&](float* dst, const float* src, int nfloats) {
+    for (int i = tid * 4; i < nfloats; i += kTcThreads * 4) cp_async16(dst + i, src + i);
+  };
+  // stage boundary: async copies landed and visible to the tensor-core (async) proxy, TMEM accesses ordered
+  auto boundary = [&]() {
+    cp_async_wait_all();
+    tc::fence_proxy_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+  };
+
+  // ---- prologue ------------------------------------------------------------------------------------
+  if (tid < 32) cen[tid] = (Pm.center != nullptr && tid < Pm.D) ? Pm.center[tid] : 0.f;
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  if (tid == 32) {
+    tc::mbar_init(&bars[0], 128); tc::mbar_init(&bars[1], 128);
+    tc::mbar_init(&bars[2], 1);   tc::mbar_init(&bars[3], 1);
+    tc::mbar_init(&bars[4], 1);
+    tc::fence_mbar_init();
+  }
+  load_x(XB, blockIdx.x);
+  acopy(TB, Pm.eTw[0], kTwFloats);
+  acopy(AB, Pm.eAw[0], kAwFloats);
+  acopy(WMs, Pm.tcL1, tc_blob_floats(8, 32));
+  acopy(WMb, Pm.tcL2, tc_blob_floats(32, 32));
+  cp_async_commit();
+  boundary();
+  TcPipe pipe;
+  pipe.full = &bars[0]; pipe.empty = &bars[2]; pipe.done = &bars[4];
+  pipe.tbase = *tmem_slot;
+  pipe.n_full[0] = pipe.n_full[1] = 0; pipe.n_done = 0;
+  // both A buffers start out free: one manual arrival completes phase 0 of the empty barriers
+  if (tid == 0) { tc::mbar_arrive(&bars[2]); tc::mbar_arrive(&bars[3]); }
+  pipe.n_empty[0] = pipe.n_empty[1] = 0;
+
+  int cur = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+    float* X0 = XB + cur * kRSmall;
+    const int64_t next_tile = tile + gridDim.x;
+
+    // ---- S0: L1 temporal  X0 -> GB
+    boundary();
+    temporal_stage<kNW * kC0, kTcWarps>(X0, GB, TB, warp, lane);
+    // ---- S1: L1 spatial in place on GB
+    boundary();
+    acopy(TB, Pm.eTw[1], kTwFloats);
+    if (next_tile < ntiles) load_x(XB + (cur ^ 1) * kRSmall, next_tile);
+    cp_async_commit();
+    spatial_stage<kNW * kC0, EpiIdentity, kTcWarps>(GB, AB, EpiIdentity{}, warp, lane);
+    // ---- S2: L1 mix on tensor cores: [G0 | X0 | 0] (Kp 8) x W -> H1 (R0, 32 ch)
+    boundary();
+    acopy(AB, Pm.eAw[1], kAwFloats);
+    cp_async_commit();
+    tc_mix_phase<kC0, kC0, kC1>(pipe, GB, X0, WMs, WMs + 8 * kC1, false, warp, lane);
+    tc_wait_done(pipe);
+    tc_epilogue_store<kC1, false>(pipe, R0, nullptr, WMs + 2 * 8 * kC1, WMs[2 * 8 * kC1 + kC1], warp, lane);
+    // ---- S3: L2 (32->16) mix-first on tensor cores: H1 -> U (R1 rows 0..47) | Rsd (R1 rows 48..95)
+    boundary();
+    acopy(WMs, Pm.tcL3, tc_blob_floats(32, 32));
+    cp_async_commit();
+    float* U2 = R1;
+    float* Rsd2 = R1 + kNW * kC2 * kCS;
+    const float slope2 = WMb[2 * 32 * 32 + 32];
+    tc_mix_phase<kC1, 0, 2 * kC2>(pipe, R0, nullptr, WMb, WMb + 32 * 32, false, warp, lane);
+    tc_wait_done(pipe);
+    tc_epilogue_store<2 * kC2, true>(pipe, U2, Rsd2, WMb + 2 * 32 * 32, 0.f, warp, lane);
+    // ---- S4: L2 temporal in place on U
+    boundary();
+    acopy(WMb, Pm.tcL4X, 2 * 32 * 64);
+    cp_async_commit();
+    temporal_stage<kNW * kC2, kTcWarps>(U2, U2, TB, warp, lane);
+    // ---- S5: L2 spatial in place + residual + PReLU -> H2 (R1 rows 0..47)
+    boundary();
+    acopy(TB, Pm.eTw[2], kTwFloats);
+    cp_async_commit();
+    spatial_stage<kNW * kC2, EpiAddResPrelu, kTcWarps>(U2, AB, EpiAddResPrelu{Rsd2, slope2}, warp, lane);
+    // ---- S6: L3 temporal: H2 -> G3 (R1 rows 48..95)
+    boundary();
+    acopy(AB, Pm.eAw[2], kAwFloats);
+    cp_async_commit();
+    float* H2 = R1;
+    float* G3 = R1 + kNW * kC2 * kCS;
+    temporal_stage<kNW * kC2, kTcWarps>(H2, G3, TB, warp, lane);
+    // ---- S7: L3 spatial in place on G3
+    boundary();
+    acopy(TB, Pm.eTw[3], kTwFloats);
+    cp_async_commit();
+    spatial_stage<kNW * kC2, EpiIdentity, kTcWarps>(G3, AB, EpiIdentity{}, warp, lane);
+    // ---- S8: L3 mix on tensor cores: [G3 | H2] x W -> H3 (R0, 32 ch)
+    boundary();
+    acopy(AB, Pm.eAw[3], kAwFloats);
+    cp_async_commit();
+    tc_mix_phase<kC2, kC2, kC3>(pipe, G3, H2, WMs, WMs + 32 * 32, false, warp, lane);
+    tc_wait_done(pipe);
+    tc_epilogue_store<kC3, false>(pipe, R0, nullptr, WMs + 2 * 32 * 32, WMs[2 * 32 * 32 + 32], warp, lane);
+    // ---- S9: L4 residual half issued first (inputs H3 = R0): runs on the tensor cores while the CUDA cores do the
+    //          layer-4 graph contraction below;  L4 temporal: H3 (R0) -> G4 (R1)
+    boundary();
+    acopy(WMs, Pm.tcL1, tc_blob_floats(8, 32));
+    cp_async_commit();
+    tc_mix_phase<kC3, 0, kC4>(pipe, R0, nullptr, WMb, WMb + 32 * 64, false, warp, lane);
+    temporal_stage<kNW * kC3, kTcWarps>(R0, R1, TB, warp, lane);
+    // ---- S10: L4 spatial in place on R1; the residual-half MMAs are long done: reload WMb with the graph half
+    boundary();
+    tc_wait_done(pipe);
+    acopy(TB, Pm.eTw[0], kTwFloats);
+    acopy(WMb, Pm.tcL4G, tc_blob_floats(32, 64));
+    cp_async_commit();
+    spatial_stage<kNW * kC3, EpiIdentity, kTcWarps>(R1, AB, EpiIdentity{}, warp, lane);
+    // ---- S11: L4 graph half accumulates onto D, then PReLU + linear head straight from TMEM (H4 never stored)
+    boundary();
+    acopy(AB, Pm.eAw[0], kAwFloats);
+    cp_async_commit();
+    tc_mix_phase<kC3, 0, kC4>(pipe, R1, nullptr, WMb, WMb + 32 * 64, true, warp, lane);
+    tc_wait_done(pipe);
+    {
+      const float* bias = WMb + 2 * 32 * 64;
+      const float slope4 = bias[kC4];
+      const int q = warp & 3, sub = warp >> 2;
+      float z[kNW][kDP];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n)
+#pragma unroll
+        for (int d = 0; d < kDP; ++d) z[n][d] = 0.f;
+      // 8 units (half j, 16-channel chunk) per lane quarter, split 3/3/2 over the three warp groups
+      const int u0 = sub * 3, u1 = (sub == 2) ? 8 : u0 + 3;
+      for (int unit = u0; unit < u1; ++unit) {
+        const int j = unit >> 2, c0 = (unit & 3) * 16;
+        const int p = j * 128 + q * 32 + lane;
+        uint32_t v[kNW][16];
+#pragma unroll
+        for (int n = 0; n < kNW; ++n)
+          tc::tmem_ld16(pipe.tbase + (static_cast<uint32_t>(q * 32) << 16) + kTcColD + 64u * (j * kNW + n) + c0, v[n]);
+        tc::wait_ld();
+        if (p < kP) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float b = bias[c0 + u];
+            float h[kNW];
+#pragma unroll
+            for (int n = 0; n < kNW; ++n) h[n] = prelu(__uint_as_float(v[n][u]) + b, slope4);
+            const float* wp = Pm.head_w + (c0 + u) * kP + p;
+            float w[kDP];
+#pragma unroll
+            for (int d = 0; d < kDP; ++d) w[d] = __ldg(wp + d * kF);
+#pragma unroll
+            for (int d = 0; d < kDP; ++d)
+#pragma unroll
+              for (int n = 0; n < kNW; ++n) z[n][d] = fmaf(h[n], w[d], z[n][d]);
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < kNW; ++n)
+#pragma unroll
+        for (int d = 0; d < kDP; ++d) {
+          const float s = warp_sum(z[n][d]);
+          if (lane == 0) zpart[warp * (kNW * kDP) + n * kDP + d] = s;
+        }
+    }
+    // ---- S12: head reduce, geometry, score
+    boundary();
+    acopy(WMb, Pm.tcL2, tc_blob_floats(32, 32));
+    cp_async_commit();
+    if (tid < kNW * kDP) {
+      float s = __ldg(Pm.head_b + (tid % kDP));
+#pragma unroll
+      for (int w = 0; w < kTcWarps; ++w) s += zpart[w * (kNW * kDP) + tid];
+      zfin[tid] = s;
+    }
+    __syncthreads();
+    if (warp < kNW) {
+      const int64_t w = tile * kNW + warp;
+      if (w < Pm.B) {
+        float u[1] = {lane < kDP ? zfin[warp * kDP + lane] : 0.f};
+        if (Pm.z != nullptr && lane < Pm.head_rows) Pm.z[w * Pm.head_rows + lane] = u[0];
+        if (Pm.score != nullptr) {
+          if (lane >= Pm.D) u[0] = 0.f;
+          const float c[1] = {cen[lane]};
+          const float sc = score_from_latent<1>(Pm.flavour, u, c, Pm.D);
+          if (lane == 0) Pm.score[w] = sc;
+        }
+      }
+    }
+  }
+  cp_async_wait_all();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(pipe.tbase, 512);
+}
+
+}  // namespace coskad

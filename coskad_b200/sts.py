@@ -144,6 +144,7 @@ class STSE(nn.Module):
         self.projector_hidden_layers = projector_hidden_layers
         self.distance, self.dropout, self.bias, self.device = distance.lower(), dropout, bias, device
         self._ctx: Optional[_lib.Context] = None
+        self.fused_impl = 1      # 1: tcgen05 channel mixing (default), 0: all-FP32 CUDA-core kernel
         self._enc_key = None
         self._dec_key = None
         self.build_model()
@@ -179,6 +180,7 @@ class STSE(nn.Module):
         if self._ctx is None or self._ctx.device != dev:
             self._ctx = _lib.Context(dev, self.n_frames, self.n_joints)
             self._enc_key = self._dec_key = None
+        self._ctx.check(self._ctx.lib.coskad_set_fused_impl(self._ctx.h, int(self.fused_impl)), 'coskad_set_fused_impl')
         return self._ctx
 
     @staticmethod

@@ -101,6 +101,9 @@ int coskad_set_decoder(coskad_ctx* ctx, const float* rev_w /*[F, latent]*/, cons
  * replaces: STSE.forward models/sts/ae.py:108-121 (+ the per-person scoring in eval_COSKAD.py:186-199) */
 int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float* x, const float* center,
                             int64_t B, float* z, float* score, void* stream);
+/* Kernel generation used by coskad_encode_score_fwd: 1 (default) = channel mixing on tcgen05 tensor cores (3xTF32),
+ * 0 = the all-FP32 CUDA-core kernel (kept for A/B measurement and as the decoder path). */
+int coskad_set_fused_impl(coskad_ctx* ctx, int impl);
 /* Euclidean auto-encoder: also runs the decoder and the reconstruction score.
  * xhat (nullable) [B,2,12,17]; rec_score (nullable) [B] = mean_{c,t,v}(x - xhat)^2;
  * lat_score (nullable) [B] = mean_d (c_d - z_d)^2.
@@ -218,6 +221,10 @@ int coskad_measure_fp32_peak(coskad_ctx* ctx, double* tflops, void* stream);
 int coskad_debug_fused_stage(coskad_ctx* ctx, int with_decoder, const float* x, int64_t B, int stage,
                              float* dbg_out, void* stream);
 int coskad_debug_fused_floats(void);
+/* test aid for the tcgen05 plumbing: out[128,N] = A[128,K] W[N,K]^T with 3xTF32; Bhi/Blo are the canonical K-major
+ * shared-memory images of trunc_tf32(W) and W - trunc_tf32(W) */
+int coskad_debug_tc_mix(coskad_ctx* ctx, const float* A, const float* Bhi, const float* Blo, int K, int N,
+                        int swap_strides, float* out, void* stream);
 int coskad_fused_tile_windows(void);
 /* number of kernel launches issued through this ctx since creation */
 int64_t coskad_launch_count(const coskad_ctx* ctx);

@@ -38,9 +38,12 @@ def test_golden_reference_vectors(golden_dir):
     _assert_close(z, torch.from_numpy(g['z']), 'latent vs reference fixture', report=lambda: stage_report(m, sd, x))
 
 
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('B', [1, 2, 3, 4, 5, 7, 448, 1001])
-def test_ragged_batches(B):
+def test_ragged_batches(B, impl):
+    """impl 1: tcgen05 (3xTF32) channel mixing; impl 0: all-FP32 CUDA-core kernel"""
     m, sd = make_pair('stse', 16, seed=0)
+    m.fused_impl = impl
     x = onet.synth_windows(B, seed=B)
     with torch.no_grad():
         ref = onet.stse_forward(x, sd)
@@ -49,10 +52,12 @@ def test_ragged_batches(B):
     _assert_close(z, ref, f'latent B={B}', report=lambda: stage_report(m, sd, x))
 
 
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('shape', ['ubnormal', 'stc'])
-def test_config0_4096_windows(shape):
+def test_config0_4096_windows(shape, impl):
     """BASELINE.json configs[0]: 4096 synthetic 17-joint windows, hyperbolic static-center scoring"""
     m, sd = make_pair('stse', 16, seed=0)
+    m.fused_impl = impl
     x = onet.synth_windows(4096, seed=999, shape=shape)
     with torch.no_grad():
         zr = onet.stse_forward(x, sd)
