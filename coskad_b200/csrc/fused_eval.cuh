@@ -590,3 +590,81 @@ __global__ void __launch_bounds__(kThreads, 1) fused_eval_kernel(const __grid_co
 }
 
 }  // namespace coskad
+
+namespace coskad {
+// ---- register-blocked contraction stages for C = 32 channel layers (rows = kNW * 32) ---------------------------------
+// lane = channel, each lane carries the kNW windows of its channel: every broadcast weight load (2 LSU wavefronts per
+// LDS.128) now feeds kNW x 4 FFMAs instead of 4 -- the R = 1 stages above are LSU-bound by 2.6x (profiles/r01_v2*).
+template <int NWARPS>
+__device__ __forceinline__ void temporal_stage_c32(const float* src, float* dst, const float* Tw, int warp, int lane) {
+  // tasks (v, q-half): 34 tasks; x[n][t] for 3 windows, 6 of the 12 outputs q per task
+  for (int task = warp; task < 2 * kV; task += NWARPS) {
+    const int v = task >> 1, q0 = (task & 1) * 6;
+    float x[kNW][kT], acc[kNW][6];
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      const float* s = src + (n * 32 + lane) * kCS + v;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) x[n][t] = s[t * kV];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[n][q] = 0.f;
+    }
+    const float* w = Tw + v * (kT * kT) + q0;
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      const float2 w01 = *reinterpret_cast<const float2*>(w + t * kT);
+      const float2 w23 = *reinterpret_cast<const float2*>(w + t * kT + 2);
+      const float2 w45 = *reinterpret_cast<const float2*>(w + t * kT + 4);
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) {
+        acc[n][0] = fmaf(x[n][t], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n][t], w01.y, acc[n][1]);
+        acc[n][2] = fmaf(x[n][t], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n][t], w23.y, acc[n][3]);
+        acc[n][4] = fmaf(x[n][t], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n][t], w45.y, acc[n][5]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      float* d = dst + (n * 32 + lane) * kCS + v;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) d[(q0 + q) * kV] = acc[n][q];
+    }
+  }
+}
+
+template <int NWARPS>
+__device__ __forceinline__ void spatial_stage_c32(float* buf, const float* Aw, int warp, int lane) {
+  for (int t = warp; t < kT; t += NWARPS) {
+    float g[kNW][kV], acc[kNW][kV];
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      const float* s = buf + (n * 32 + lane) * kCS + t * kV;
+#pragma unroll
+      for (int v = 0; v < kV; ++v) { g[n][v] = s[v]; acc[n][v] = 0.f; }
+    }
+    const float4* a4 = reinterpret_cast<const float4*>(Aw + t * (kV * kAW));
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = a4[v * 5 + j];
+#pragma unroll
+        for (int n = 0; n < kNW; ++n) {
+          acc[n][4 * j + 0] = fmaf(g[n][v], w.x, acc[n][4 * j + 0]);
+          acc[n][4 * j + 1] = fmaf(g[n][v], w.y, acc[n][4 * j + 1]);
+          acc[n][4 * j + 2] = fmaf(g[n][v], w.z, acc[n][4 * j + 2]);
+          acc[n][4 * j + 3] = fmaf(g[n][v], w.w, acc[n][4 * j + 3]);
+        }
+      }
+      const float w16 = Aw[t * (kV * kAW) + v * kAW + 16];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) acc[n][16] = fmaf(g[n][v], w16, acc[n][16]);
+    }
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      float* s = buf + (n * 32 + lane) * kCS + t * kV;
+#pragma unroll
+      for (int w = 0; w < kV; ++w) s[w] = acc[n][w];
+    }
+  }
+}
+}  // namespace coskad
