@@ -172,7 +172,7 @@ extern "C" int coskad_set_encoder(coskad_ctx* ctx, int n_layers, const coskad_la
   fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[3], 3, 32, 64, ctx->enc_pack + oT4G);
   CK_LAUNCH();
   for (int i = 0; i < 4; ++i) { ctx->tp.eTw[i] = ctx->fp.eTw[i]; ctx->tp.eAw[i] = ctx->fp.eAw[i]; }
-  ctx->tp.tcL1 = ctx->enc_pack + oT1; ctx->tp.tcL2 = ctx->enc_pack + oT2; ctx->tp.tcL3 = ctx->enc_pack + oT3;
+  ctx->tp.mixL1 = ctx->fp.eWm[0]; ctx->tp.tcL2 = ctx->enc_pack + oT2; ctx->tp.tcL3 = ctx->enc_pack + oT3;
   ctx->tp.tcL4X = ctx->enc_pack + oT4X; ctx->tp.tcL4G = ctx->enc_pack + oT4G;
   ctx->tp.head_w = ctx->fp.head_w; ctx->tp.head_b = ctx->fp.head_b;
   ctx->head_rows = head_rows;

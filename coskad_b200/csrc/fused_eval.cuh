@@ -157,13 +157,13 @@ __device__ __forceinline__ void spatial_stage(float* buf, const float* Aw, const
 // channel mixing: acc[n][j] = sum_k in_k[n][p] * Wm[k][co0+j]; lanes walk positions, each thread
 // keeps kNW windows x RCO output channels in registers.  Inputs k < K1 come from src1 (rows
 // n*K1+k), the rest from src2 (rows n*K2+k-K1).
-template <int K1, int K2, int COUT, int RCO, class Epi>
+template <int K1, int K2, int COUT, int RCO, class Epi, int NWARPS = kWarps>
 __device__ __forceinline__ void mix_stage(const float* src1, const float* src2, const float* Wm, Epi& epi,
                                           int warp, int lane) {
   static_assert(RCO % 4 == 0 && COUT % RCO == 0, "bad register tile");
   constexpr int NCO = COUT / RCO;
   constexpr int NTASK = kPCH * NCO;
-  for (int task = warp; task < NTASK; task += kWarps) {
+  for (int task = warp; task < NTASK; task += NWARPS) {
     const int p = (task % kPCH) * 32 + lane;
     const int co0 = (task / kPCH) * RCO;
     const bool valid = p < kP;
@@ -664,6 +664,54 @@ __device__ __forceinline__ void spatial_stage_c32(float* buf, const float* Aw, i
       float* s = buf + (n * 32 + lane) * kCS + t * kV;
 #pragma unroll
       for (int w = 0; w < kV; ++w) s[w] = acc[n][w];
+    }
+  }
+}
+}  // namespace coskad
+
+namespace coskad {
+// ---- layer-1 contraction stages (rows = kNW * 2 = 6): lanes = (row, output group) instead of rows only --------------
+// With 2 input channels the generic stages keep 6 of 32 lanes busy; here a warp task covers one joint v (temporal) or
+// one frame t (spatial) for all 6 rows, each lane producing 3 (4) of the 12 (17) outputs.
+template <int NWARPS>
+__device__ __forceinline__ void temporal_stage_l1(const float* src, float* dst, const float* Tw, int warp, int lane) {
+  constexpr int ROWS = kNW * kC0;                 // 6
+  const int row = lane % ROWS, qg = lane / ROWS;  // qg 0..3 -> outputs q = 3 qg .. 3 qg + 2 (lanes >= 24 idle)
+  for (int v = warp; v < kV; v += NWARPS) {
+    if (qg < 4) {
+      const float* s = src + row * kCS + v;
+      const float* w = Tw + v * (kT * kT) + 3 * qg;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) {
+        const float x = s[t * kV];
+        a0 = fmaf(x, w[t * kT + 0], a0); a1 = fmaf(x, w[t * kT + 1], a1); a2 = fmaf(x, w[t * kT + 2], a2);
+      }
+      float* d = dst + row * kCS + v;
+      d[(3 * qg + 0) * kV] = a0; d[(3 * qg + 1) * kV] = a1; d[(3 * qg + 2) * kV] = a2;
+    }
+  }
+}
+template <int NWARPS>
+__device__ __forceinline__ void spatial_stage_l1(float* buf, const float* Aw, int warp, int lane) {
+  constexpr int ROWS = kNW * kC0;                 // 6
+  const int row = lane % ROWS, wg = lane / ROWS;  // wg 0..4 -> outputs w = 4 wg .. 4 wg + 3 (w < 17; lanes >= 30 idle)
+  for (int t = warp; t < kT; t += NWARPS) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float* s = buf + row * kCS + t * kV;
+    if (wg < 5) {
+      const float4* a4 = reinterpret_cast<const float4*>(Aw + t * (kV * kAW)) + wg;
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+        const float g = s[v];
+        const float4 w = a4[v * 5];
+        acc[0] = fmaf(g, w.x, acc[0]); acc[1] = fmaf(g, w.y, acc[1]); acc[2] = fmaf(g, w.z, acc[2]); acc[3] = fmaf(g, w.w, acc[3]);
+      }
+    }
+    __syncwarp();      // every lane of the row has read its 17 inputs before anyone overwrites them (in place)
+    if (wg < 5) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (4 * wg + j < kV) s[4 * wg + j] = acc[j];
     }
   }
 }

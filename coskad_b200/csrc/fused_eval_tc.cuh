@@ -37,7 +37,7 @@ constexpr int kTcWbFloats = tc_blob_floats(32, 64);   // big buffer: L2, L4 resi
 struct FusedTcParams {
   const float* eTw[4];
   const float* eAw[4];
-  const float* tcL1;      // Kp 8 (G0 c0,c1, X0 c0,c1, 0 x4), N 32
+  const float* mixL1;     // FP32 blob of layer 1 (fused_eval.cuh mix layout: [4][32] + bias + slope): K = 4 is too thin for an MMA
   const float* tcL2;      // mix-first: K 32 (H1), N 32 = [U 16 | Rsd 16]
   const float* tcL3;      // K 32 = [G3 16 | H2 16], N 32
   const float* tcL4X;     // K 32 (H3, residual conv), N 64
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   load_x(XB, blockIdx.x);
   acopy(TB, Pm.eTw[0], kTwFloats);
   acopy(AB, Pm.eAw[0], kAwFloats);
-  acopy(WMs, Pm.tcL1, tc_blob_floats(8, 32));
+  acopy(WMs, Pm.mixL1, mix_blob_floats(4, 32));
   acopy(WMb, Pm.tcL2, tc_blob_floats(32, 32));
   cp_async_commit();
   boundary();
@@ -252,20 +252,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 
     // ---- S0: L1 temporal  X0 -> GB
     boundary();
-    temporal_stage<kNW * kC0, kTcWarps>(X0, GB, TB, warp, lane);
+    temporal_stage_l1<kTcWarps>(X0, GB, TB, warp, lane);
     // ---- S1: L1 spatial in place on GB
     boundary();
     acopy(TB, Pm.eTw[1], kTwFloats);
     if (next_tile < ntiles) load_x(XB + (cur ^ 1) * kRSmall, next_tile);
     cp_async_commit();
-    spatial_stage<kNW * kC0, EpiIdentity, kTcWarps>(GB, AB, EpiIdentity{}, warp, lane);
-    // ---- S2: L1 mix on tensor cores: [G0 | X0 | 0] (Kp 8) x W -> H1 (R0, 32 ch)
+    spatial_stage_l1<kTcWarps>(GB, AB, warp, lane);
+    // ---- S2: L1 mix (K = 4) on the FP32 pipe: [G0 | X0] x W -> H1 (R0, 32 ch)
     boundary();
     acopy(AB, Pm.eAw[1], kAwFloats);
     cp_async_commit();
-    tc_mix_phase<kC0, kC0, kC1>(pipe, GB, X0, WMs, WMs + 8 * kC1, false, warp, lane);
-    tc_wait_done(pipe);
-    tc_epilogue_store<kC1, false>(pipe, R0, nullptr, WMs + 2 * 8 * kC1, WMs[2 * 8 * kC1 + kC1], warp, lane);
+    {
+      EpiStorePrelu<kC1> epi{R0, WMs + 4 * kC1, WMs[4 * kC1 + kC1]};
+      mix_stage<kC0, kC0, kC1, 32, EpiStorePrelu<kC1>, kTcWarps>(GB, X0, WMs, epi, warp, lane);
+    }
     // ---- S3: L2 (32->16) mix-first on tensor cores: H1 -> U (R1 rows 0..47) | Rsd (R1 rows 48..95)
     boundary();
     acopy(WMs, Pm.tcL3, tc_blob_floats(32, 32));
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     // ---- S9: L4 residual half issued first (inputs H3 = R0): runs on the tensor cores while the CUDA cores do the
     //          layer-4 graph contraction below;  L4 temporal: H3 (R0) -> G4 (R1)
     boundary();
-    acopy(WMs, Pm.tcL1, tc_blob_floats(8, 32));
+    acopy(WMs, Pm.mixL1, mix_blob_floats(4, 32));
     cp_async_commit();
     tc_mix_phase<kC3, 0, kC4>(pipe, R0, nullptr, WMb, WMb + 32 * 64, false, warp, lane);
     temporal_stage_c32<kTcWarps>(R0, R1, TB, warp, lane);
