@@ -716,3 +716,83 @@ __device__ __forceinline__ void spatial_stage_l1(float* buf, const float* Aw, in
   }
 }
 }  // namespace coskad
+
+namespace coskad {
+// ---- contraction stages for C = 16 channel layers (rows = kNW * 16): lane = (channel, output half), kNW windows per lane
+template <int NWARPS>
+__device__ __forceinline__ void temporal_stage_c16(const float* src, float* dst, const float* Tw, int warp, int lane) {
+  const int c = lane & 15, q0 = (lane >> 4) * 6;          // half 0: q 0..5, half 1: q 6..11
+  for (int v = warp; v < kV; v += NWARPS) {
+    float x[kNW][kT], acc[kNW][6];
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      const float* s = src + (n * 16 + c) * kCS + v;
+#pragma unroll
+      for (int t = 0; t < kT; ++t) x[n][t] = s[t * kV];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[n][q] = 0.f;
+    }
+    const float* w = Tw + v * (kT * kT) + q0;
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      const float2 w01 = *reinterpret_cast<const float2*>(w + t * kT);
+      const float2 w23 = *reinterpret_cast<const float2*>(w + t * kT + 2);
+      const float2 w45 = *reinterpret_cast<const float2*>(w + t * kT + 4);
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) {
+        acc[n][0] = fmaf(x[n][t], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n][t], w01.y, acc[n][1]);
+        acc[n][2] = fmaf(x[n][t], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n][t], w23.y, acc[n][3]);
+        acc[n][4] = fmaf(x[n][t], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n][t], w45.y, acc[n][5]);
+      }
+    }
+    __syncwarp();      // in-place use: both halves have read the column before either writes it
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      float* d = dst + (n * 16 + c) * kCS + v;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) d[(q0 + q) * kV] = acc[n][q];
+    }
+  }
+}
+
+// half 0: outputs w 0..7 (two LDS.128 per v), half 1: outputs w 8..16 (two LDS.128 + one LDS.32 per v)
+template <class Epi, int NWARPS>
+__device__ __forceinline__ void spatial_stage_c16(float* buf, const float* Aw, const Epi epi, int warp, int lane) {
+  const int c = lane & 15, h = lane >> 4;
+  for (int t = warp; t < kT; t += NWARPS) {
+    float g[kNW][kV], acc[kNW][9];
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      const float* s = buf + (n * 16 + c) * kCS + t * kV;
+#pragma unroll
+      for (int v = 0; v < kV; ++v) g[n][v] = s[v];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) acc[n][j] = 0.f;
+    }
+    const float* a = Aw + t * (kV * kAW) + 8 * h;
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      const float4 w0 = *reinterpret_cast<const float4*>(a + v * kAW);
+      const float4 w1 = *reinterpret_cast<const float4*>(a + v * kAW + 4);
+      const float w8 = a[v * kAW + 8];                  // half 1: w = 16; half 0: w = 8 (belongs to half 1, discarded)
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) {
+        acc[n][0] = fmaf(g[n][v], w0.x, acc[n][0]); acc[n][1] = fmaf(g[n][v], w0.y, acc[n][1]);
+        acc[n][2] = fmaf(g[n][v], w0.z, acc[n][2]); acc[n][3] = fmaf(g[n][v], w0.w, acc[n][3]);
+        acc[n][4] = fmaf(g[n][v], w1.x, acc[n][4]); acc[n][5] = fmaf(g[n][v], w1.y, acc[n][5]);
+        acc[n][6] = fmaf(g[n][v], w1.z, acc[n][6]); acc[n][7] = fmaf(g[n][v], w1.w, acc[n][7]);
+        acc[n][8] = fmaf(g[n][v], w8, acc[n][8]);
+      }
+    }
+    __syncwarp();      // in place: both halves have read the 17 inputs of their rows
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      const int row = n * 16 + c;
+      float* s = buf + row * kCS + t * kV;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[8 * h + j] = epi(acc[n][j], row, t * kV + 8 * h + j);
+      if (h == 1) s[16] = epi(acc[n][8], row, t * kV + 16);
+    }
+  }
+}
+}  // namespace coskad

@@ -281,24 +281,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     boundary();
     acopy(WMb, Pm.tcL4X, 2 * 32 * 64);
     cp_async_commit();
-    temporal_stage<kNW * kC2, kTcWarps>(U2, U2, TB, warp, lane);
+    temporal_stage_c16<kTcWarps>(U2, U2, TB, warp, lane);
     // ---- S5: L2 spatial in place + residual + PReLU -> H2 (R1 rows 0..47)
     boundary();
     acopy(TB, Pm.eTw[2], kTwFloats);
     cp_async_commit();
-    spatial_stage<kNW * kC2, EpiAddResPrelu, kTcWarps>(U2, AB, EpiAddResPrelu{Rsd2, slope2}, warp, lane);
+    spatial_stage_c16<EpiAddResPrelu, kTcWarps>(U2, AB, EpiAddResPrelu{Rsd2, slope2}, warp, lane);
     // ---- S6: L3 temporal: H2 -> G3 (R1 rows 48..95)
     boundary();
     acopy(AB, Pm.eAw[2], kAwFloats);
     cp_async_commit();
     float* H2 = R1;
     float* G3 = R1 + kNW * kC2 * kCS;
-    temporal_stage<kNW * kC2, kTcWarps>(H2, G3, TB, warp, lane);
+    temporal_stage_c16<kTcWarps>(H2, G3, TB, warp, lane);
     // ---- S7: L3 spatial in place on G3
     boundary();
     acopy(TB, Pm.eTw[3], kTwFloats);
     cp_async_commit();
-    spatial_stage<kNW * kC2, EpiIdentity, kTcWarps>(G3, AB, EpiIdentity{}, warp, lane);
+    spatial_stage_c16<EpiIdentity, kTcWarps>(G3, AB, EpiIdentity{}, warp, lane);
     // ---- S8: L3 mix on tensor cores: [G3 | H2] x W -> H3 (R0, 32 ch)
     boundary();
     acopy(AB, Pm.eAw[3], kAwFloats);
