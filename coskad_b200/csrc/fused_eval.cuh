@@ -594,32 +594,35 @@ __global__ void __launch_bounds__(kThreads, 1) fused_eval_kernel(const __grid_co
 namespace coskad {
 // ---- register-blocked contraction stages for C = 32 channel layers (rows = kNW * 32) ---------------------------------
 // lane = channel, each lane carries the kNW windows of its channel: every broadcast weight load (2 LSU wavefronts per
-// LDS.128) now feeds kNW x 4 FFMAs instead of 4 -- the R = 1 stages above are LSU-bound by 2.6x (profiles/r01_v2*).
+// LDS.128) feeds kNW x 4 FFMAs instead of 4 -- the R = 1 stages above are LSU-bound by 2.6x (profiles/r01_v2*).
+// The contraction index (t or v) is a real loop (not unrolled): each warp runs a task exactly once per tile, so fully
+// unrolled bodies are straight-line code with no reuse and the warps starve on instruction fetch
+// (profiles/r01_v3*: stall_no_inst 25-35 % of the samples of these stages).
 template <int NWARPS>
 __device__ __forceinline__ void temporal_stage_c32(const float* src, float* dst, const float* Tw, int warp, int lane) {
-  // tasks (v, q-half): 34 tasks; x[n][t] for 3 windows, 6 of the 12 outputs q per task
+  // tasks (v, q-half): 34 tasks; 6 of the 12 outputs q per task
   for (int task = warp; task < 2 * kV; task += NWARPS) {
     const int v = task >> 1, q0 = (task & 1) * 6;
-    float x[kNW][kT], acc[kNW][6];
+    float acc[kNW][6];
 #pragma unroll
-    for (int n = 0; n < kNW; ++n) {
-      const float* s = src + (n * 32 + lane) * kCS + v;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) x[n][t] = s[t * kV];
+    for (int n = 0; n < kNW; ++n)
 #pragma unroll
       for (int q = 0; q < 6; ++q) acc[n][q] = 0.f;
-    }
+    const float* s = src + lane * kCS + v;
     const float* w = Tw + v * (kT * kT) + q0;
-#pragma unroll
+#pragma unroll 2
     for (int t = 0; t < kT; ++t) {
+      float x[kNW];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) x[n] = s[n * 32 * kCS + t * kV];
       const float2 w01 = *reinterpret_cast<const float2*>(w + t * kT);
       const float2 w23 = *reinterpret_cast<const float2*>(w + t * kT + 2);
       const float2 w45 = *reinterpret_cast<const float2*>(w + t * kT + 4);
 #pragma unroll
       for (int n = 0; n < kNW; ++n) {
-        acc[n][0] = fmaf(x[n][t], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n][t], w01.y, acc[n][1]);
-        acc[n][2] = fmaf(x[n][t], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n][t], w23.y, acc[n][3]);
-        acc[n][4] = fmaf(x[n][t], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n][t], w45.y, acc[n][5]);
+        acc[n][0] = fmaf(x[n], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n], w01.y, acc[n][1]);
+        acc[n][2] = fmaf(x[n], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n], w23.y, acc[n][3]);
+        acc[n][4] = fmaf(x[n], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n], w45.y, acc[n][5]);
       }
     }
 #pragma unroll
@@ -634,36 +637,38 @@ __device__ __forceinline__ void temporal_stage_c32(const float* src, float* dst,
 template <int NWARPS>
 __device__ __forceinline__ void spatial_stage_c32(float* buf, const float* Aw, int warp, int lane) {
   for (int t = warp; t < kT; t += NWARPS) {
-    float g[kNW][kV], acc[kNW][kV];
+    float acc[kNW][kV];
 #pragma unroll
-    for (int n = 0; n < kNW; ++n) {
-      const float* s = buf + (n * 32 + lane) * kCS + t * kV;
+    for (int n = 0; n < kNW; ++n)
 #pragma unroll
-      for (int v = 0; v < kV; ++v) { g[n][v] = s[v]; acc[n][v] = 0.f; }
-    }
-    const float4* a4 = reinterpret_cast<const float4*>(Aw + t * (kV * kAW));
-#pragma unroll
+      for (int w = 0; w < kV; ++w) acc[n][w] = 0.f;
+    float* s = buf + lane * kCS + t * kV;
+    const float* a = Aw + t * (kV * kAW);
+#pragma unroll 1
     for (int v = 0; v < kV; ++v) {
+      float g[kNW];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) g[n] = s[n * 32 * kCS + v];
+      const float4* a4 = reinterpret_cast<const float4*>(a + v * kAW);
+      const float w16 = a[v * kAW + 16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 w = a4[v * 5 + j];
+        const float4 w = a4[j];
 #pragma unroll
         for (int n = 0; n < kNW; ++n) {
-          acc[n][4 * j + 0] = fmaf(g[n][v], w.x, acc[n][4 * j + 0]);
-          acc[n][4 * j + 1] = fmaf(g[n][v], w.y, acc[n][4 * j + 1]);
-          acc[n][4 * j + 2] = fmaf(g[n][v], w.z, acc[n][4 * j + 2]);
-          acc[n][4 * j + 3] = fmaf(g[n][v], w.w, acc[n][4 * j + 3]);
+          acc[n][4 * j + 0] = fmaf(g[n], w.x, acc[n][4 * j + 0]);
+          acc[n][4 * j + 1] = fmaf(g[n], w.y, acc[n][4 * j + 1]);
+          acc[n][4 * j + 2] = fmaf(g[n], w.z, acc[n][4 * j + 2]);
+          acc[n][4 * j + 3] = fmaf(g[n], w.w, acc[n][4 * j + 3]);
         }
       }
-      const float w16 = Aw[t * (kV * kAW) + v * kAW + 16];
 #pragma unroll
-      for (int n = 0; n < kNW; ++n) acc[n][16] = fmaf(g[n][v], w16, acc[n][16]);
+      for (int n = 0; n < kNW; ++n) acc[n][16] = fmaf(g[n], w16, acc[n][16]);
     }
 #pragma unroll
     for (int n = 0; n < kNW; ++n) {
-      float* s = buf + (n * 32 + lane) * kCS + t * kV;
 #pragma unroll
-      for (int w = 0; w < kV; ++w) s[w] = acc[n][w];
+      for (int w = 0; w < kV; ++w) s[n * 32 * kCS + w] = acc[n][w];
     }
   }
 }
@@ -723,26 +728,26 @@ template <int NWARPS>
 __device__ __forceinline__ void temporal_stage_c16(const float* src, float* dst, const float* Tw, int warp, int lane) {
   const int c = lane & 15, q0 = (lane >> 4) * 6;          // half 0: q 0..5, half 1: q 6..11
   for (int v = warp; v < kV; v += NWARPS) {
-    float x[kNW][kT], acc[kNW][6];
+    float acc[kNW][6];
 #pragma unroll
-    for (int n = 0; n < kNW; ++n) {
-      const float* s = src + (n * 16 + c) * kCS + v;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) x[n][t] = s[t * kV];
+    for (int n = 0; n < kNW; ++n)
 #pragma unroll
       for (int q = 0; q < 6; ++q) acc[n][q] = 0.f;
-    }
+    const float* s = src + c * kCS + v;
     const float* w = Tw + v * (kT * kT) + q0;
-#pragma unroll
+#pragma unroll 2
     for (int t = 0; t < kT; ++t) {
+      float x[kNW];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) x[n] = s[n * 16 * kCS + t * kV];
       const float2 w01 = *reinterpret_cast<const float2*>(w + t * kT);
       const float2 w23 = *reinterpret_cast<const float2*>(w + t * kT + 2);
       const float2 w45 = *reinterpret_cast<const float2*>(w + t * kT + 4);
 #pragma unroll
       for (int n = 0; n < kNW; ++n) {
-        acc[n][0] = fmaf(x[n][t], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n][t], w01.y, acc[n][1]);
-        acc[n][2] = fmaf(x[n][t], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n][t], w23.y, acc[n][3]);
-        acc[n][4] = fmaf(x[n][t], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n][t], w45.y, acc[n][5]);
+        acc[n][0] = fmaf(x[n], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n], w01.y, acc[n][1]);
+        acc[n][2] = fmaf(x[n], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n], w23.y, acc[n][3]);
+        acc[n][4] = fmaf(x[n], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n], w45.y, acc[n][5]);
       }
     }
     __syncwarp();      // in-place use: both halves have read the column before either writes it
@@ -760,38 +765,38 @@ template <class Epi, int NWARPS>
 __device__ __forceinline__ void spatial_stage_c16(float* buf, const float* Aw, const Epi epi, int warp, int lane) {
   const int c = lane & 15, h = lane >> 4;
   for (int t = warp; t < kT; t += NWARPS) {
-    float g[kNW][kV], acc[kNW][9];
+    float acc[kNW][9];
 #pragma unroll
-    for (int n = 0; n < kNW; ++n) {
-      const float* s = buf + (n * 16 + c) * kCS + t * kV;
-#pragma unroll
-      for (int v = 0; v < kV; ++v) g[n][v] = s[v];
+    for (int n = 0; n < kNW; ++n)
 #pragma unroll
       for (int j = 0; j < 9; ++j) acc[n][j] = 0.f;
-    }
+    const float* s = buf + c * kCS + t * kV;
     const float* a = Aw + t * (kV * kAW) + 8 * h;
-#pragma unroll
+#pragma unroll 1
     for (int v = 0; v < kV; ++v) {
+      float g[kNW];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) g[n] = s[n * 16 * kCS + v];
       const float4 w0 = *reinterpret_cast<const float4*>(a + v * kAW);
       const float4 w1 = *reinterpret_cast<const float4*>(a + v * kAW + 4);
       const float w8 = a[v * kAW + 8];                  // half 1: w = 16; half 0: w = 8 (belongs to half 1, discarded)
 #pragma unroll
       for (int n = 0; n < kNW; ++n) {
-        acc[n][0] = fmaf(g[n][v], w0.x, acc[n][0]); acc[n][1] = fmaf(g[n][v], w0.y, acc[n][1]);
-        acc[n][2] = fmaf(g[n][v], w0.z, acc[n][2]); acc[n][3] = fmaf(g[n][v], w0.w, acc[n][3]);
-        acc[n][4] = fmaf(g[n][v], w1.x, acc[n][4]); acc[n][5] = fmaf(g[n][v], w1.y, acc[n][5]);
-        acc[n][6] = fmaf(g[n][v], w1.z, acc[n][6]); acc[n][7] = fmaf(g[n][v], w1.w, acc[n][7]);
-        acc[n][8] = fmaf(g[n][v], w8, acc[n][8]);
+        acc[n][0] = fmaf(g[n], w0.x, acc[n][0]); acc[n][1] = fmaf(g[n], w0.y, acc[n][1]);
+        acc[n][2] = fmaf(g[n], w0.z, acc[n][2]); acc[n][3] = fmaf(g[n], w0.w, acc[n][3]);
+        acc[n][4] = fmaf(g[n], w1.x, acc[n][4]); acc[n][5] = fmaf(g[n], w1.y, acc[n][5]);
+        acc[n][6] = fmaf(g[n], w1.z, acc[n][6]); acc[n][7] = fmaf(g[n], w1.w, acc[n][7]);
+        acc[n][8] = fmaf(g[n], w8, acc[n][8]);
       }
     }
     __syncwarp();      // in place: both halves have read the 17 inputs of their rows
 #pragma unroll
     for (int n = 0; n < kNW; ++n) {
       const int row = n * 16 + c;
-      float* s = buf + row * kCS + t * kV;
+      float* d = buf + row * kCS + t * kV;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[8 * h + j] = epi(acc[n][j], row, t * kV + 8 * h + j);
-      if (h == 1) s[16] = epi(acc[n][8], row, t * kV + 16);
+      for (int j = 0; j < 8; ++j) d[8 * h + j] = epi(acc[n][j], row, t * kV + 8 * h + j);
+      if (h == 1) d[16] = epi(acc[n][8], row, t * kV + 16);
     }
   }
 }
