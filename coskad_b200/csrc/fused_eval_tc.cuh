@@ -57,7 +57,7 @@ static_assert((2 * kRBig + 2 * kRSmall + kTcGB) % 4 == 0, "weight staging buffer
 constexpr int kTcSmemFloats = 2 * kRBig + 2 * kRSmall + kTcGB        // R0, R1, XB[2], GB
                               + kTwFloats + kAwFloats + kTcWsFloats + kTcWbFloats
                               + kTcWarps * kNW * kDP + kNW * kDP + 32   // zpart, zfin, center
-                              + 16;                                     // mbarriers (5 x 8 B) + tmem base
+                              + 32;                                     // mbarriers (11 x 8 B) + tmem base
 constexpr int kTcSmemBytes = kTcSmemFloats * 4;
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
 
@@ -180,6 +180,96 @@ __device__ __forceinline__ void tc_epilogue_store(const TcPipe& P, float* dst, f
   tc::fence_before_sync();
 }
 
+
+// ---- N = 32 mixing phases (layers 2 and 3): self-contained per warp group ---------------------------------------------
+// Warp group g (4 warps = the 4 TMEM lane quarters) owns window n = g: it stages the two M-tiles (position halves j) of
+// its window into its own A buffers, syncs on a 128-thread named barrier, its first lane issues the 12 MMAs of the tile
+// and commits to a per-tile mbarrier, and the same warps run the epilogue of their tiles as soon as that barrier flips.
+// No cross-group hand-off, all 12 warps produce.  TMEM columns of group g: A(j) = 160 g + 64 j, D(0) = 160 g + 128,
+// D(1) = 160 g (aliases A(0): the MMAs of tile 1 are issued by the same thread after those of tile 0 and the tensor
+// pipe executes them in issue order, so A(0) is dead when D(1) is first written).
+constexpr uint32_t kSmGroupCols = 160;
+static_assert(kSmGroupCols * kNW <= 512, "TMEM budget of the small phases");
+__device__ __forceinline__ uint32_t sm_col_a(int g, int j) { return kSmGroupCols * g + 64u * j; }
+__device__ __forceinline__ uint32_t sm_col_d(int g, int j) { return j == 0 ? kSmGroupCols * g + 128u : kSmGroupCols * g; }
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+struct SmallPipe {
+  uint64_t* done;     // [6] = (g, j)
+  uint32_t tbase;
+  uint32_t uses;      // completed small phases (identical on every thread): wait parity = uses & 1
+};
+
+// 32 staged channels (hi at +0..31, lo at +32..63) of one thread's position -> this warp's lanes of A buffer `abuf`
+__device__ __forceinline__ void sm_store_a(uint32_t abuf, const float (&a)[32]) {
+#pragma unroll
+  for (int k0 = 0; k0 < 32; k0 += 16) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) tc::split_tf32(a[k0 + u], hi[u], lo[u]);
+    tc::tmem_st16(abuf + k0, hi);
+    tc::tmem_st16(abuf + 32 + k0, lo);
+  }
+}
+// tile staged (all 4 warps of the group): publish, then one lane issues D = A(32 ch) x B^T (3xTF32) and commits
+template <int N>
+__device__ __forceinline__ void sm_publish_and_issue(const SmallPipe& P, int g, int j, int q, int lane, const float* Bhi, const float* Blo) {
+  tc::wait_st();
+  tc::fence_before_sync();
+  group_bar(g);
+  if (q == 0 && lane == 0) {
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::make_idesc_tf32(128, N);
+    constexpr uint32_t lbo = (N / 8) * 128, sbo = 128;
+    const uint32_t bh = tc::smem_u32(Bhi), bl = tc::smem_u32(Blo);
+    const uint32_t d = P.tbase + sm_col_d(g, j), a = P.tbase + sm_col_a(g, j);
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      const uint64_t dh = tc::make_smem_desc(bh + kb * 2 * lbo, lbo, sbo);
+      const uint64_t dl = tc::make_smem_desc(bl + kb * 2 * lbo, lbo, sbo);
+      tc::mma_tf32_ts(d, a + kb * 8, dh, idesc, kb > 0 ? 1u : 0u);
+      tc::mma_tf32_ts(d, a + 32 + kb * 8, dh, idesc, 1u);
+      tc::mma_tf32_ts(d, a + kb * 8, dl, idesc, 1u);
+    }
+    tc::mma_commit(&P.done[g * 2 + j]);
+  }
+  __syncwarp();
+}
+// epilogue of the small phases: D (32 columns) -> (+bias, PReLU) -> planes; SPLIT: mix-first layout (U | Rsd)
+template <bool SPLIT>
+__device__ __forceinline__ void sm_epilogue(const SmallPipe& P, int g, int q, int lane, float* dst, float* dstR, const float* bias,
+                                            float slope) {
+  constexpr int CO = SPLIT ? 16 : 32;
+  const int n = g;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (j == 1 && q == 3) break;                      // positions >= 224 do not exist
+    const int p = j * 128 + q * 32 + lane;
+    tc::mbar_wait(&P.done[g * 2 + j], P.uses & 1);
+    tc::fence_after_sync();
+    const uint32_t d = P.tbase + (static_cast<uint32_t>(q * 32) << 16) + sm_col_d(g, j);
+    uint32_t v0[16], v1[16];
+    tc::tmem_ld16(d, v0);
+    tc::tmem_ld16(d + 16, v1);
+    tc::wait_ld();
+    if (p < kP) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const float a = __uint_as_float(v0[u]) + bias[u];
+        const float b = __uint_as_float(v1[u]) + bias[16 + u];
+        if (SPLIT) {
+          dst[(n * CO + u) * kCS + p] = a;              // U: bias slot is 0
+          dstR[(n * CO + u) * kCS + p] = b;             // Rsd + folded bias
+        } else {
+          dst[(n * CO + u) * kCS + p] = prelu(a, slope);
+          dst[(n * CO + 16 + u) * kCS + p] = prelu(b, slope);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __grid_constant__ FusedTcParams Pm) {
   extern __shared__ __align__(128) float smem_tc[];
   float* R0 = smem_tc;
@@ -193,8 +283,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   float* zpart = WMb + kTcWbFloats;
   float* zfin = zpart + kTcWarps * kNW * kDP;
   float* cen = zfin + kNW * kDP;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cen + 32);     // full[2], empty[2], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cen + 32);     // full[2], empty[2], done, small-phase done[6]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (Pm.B + kNW - 1) / kNW;
@@ -228,6 +318,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     tc::mbar_init(&bars[0], 128); tc::mbar_init(&bars[1], 128);
     tc::mbar_init(&bars[2], 1);   tc::mbar_init(&bars[3], 1);
     tc::mbar_init(&bars[4], 1);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) tc::mbar_init(&bars[5 + i], 1);
     tc::fence_mbar_init();
   }
   load_x(XB, blockIdx.x);
@@ -244,6 +336,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   // both A buffers start out free: one manual arrival completes phase 0 of the empty barriers
   if (tid == 0) { tc::mbar_arrive(&bars[2]); tc::mbar_arrive(&bars[3]); }
   pipe.n_empty[0] = pipe.n_empty[1] = 0;
+  SmallPipe spipe;
+  spipe.done = &bars[5]; spipe.tbase = pipe.tbase; spipe.uses = 0;
+  const int gq = warp & 3, gg = warp >> 2;          // TMEM lane quarter, warp group (= window in the small phases)
 
   int cur = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1) {
@@ -259,27 +354,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     if (next_tile < ntiles) load_x(XB + (cur ^ 1) * kRSmall, next_tile);
     cp_async_commit();
     spatial_stage_l1<kTcWarps>(GB, AB, warp, lane);
-    // ---- S2: L1 mix (K = 4) on the FP32 pipe: [G0 | X0] x W -> H1 (R0, 32 ch)
+    // ---- S2+S3: L1 mix (K = 4, FP32 pipe, registers) -> H1 split straight into the TMEM A operand (never stored) ->
+    //             L2 (32->16) mix-first on tensor cores: U (R1 rows 0..47) | Rsd (R1 rows 48..95)
     boundary();
     acopy(AB, Pm.eAw[1], kAwFloats);
-    cp_async_commit();
-    {
-      EpiStorePrelu<kC1> epi{R0, WMs + 4 * kC1, WMs[4 * kC1 + kC1]};
-      mix_stage<kC0, kC0, kC1, 32, EpiStorePrelu<kC1>, kTcWarps>(GB, X0, WMs, epi, warp, lane);
-    }
-    // ---- S3: L2 (32->16) mix-first on tensor cores: H1 -> U (R1 rows 0..47) | Rsd (R1 rows 48..95)
-    boundary();
-    acopy(WMs, Pm.tcL3, tc_blob_floats(32, 32));
     cp_async_commit();
     float* U2 = R1;
     float* Rsd2 = R1 + kNW * kC2 * kCS;
     const float slope2 = WMb[2 * 32 * 32 + 32];
-    tc_mix_phase<kC1, 0, 2 * kC2>(pipe, R0, nullptr, WMb, WMb + 32 * 32, false, warp, lane);
-    tc_wait_done(pipe);
-    tc_epilogue_store<2 * kC2, true>(pipe, U2, Rsd2, WMb + 2 * 32 * 32, 0.f, warp, lane);
+    {
+      const int n = gg;
+      const bool has1 = gq < 3;                        // tile j = 1 holds positions 128..203: none in quarter 3
+      float h[2][kC1];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int c = 0; c < kC1; ++c) h[jj][c] = 0.f;
+      float in[2][4];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int p = jj * 128 + gq * 32 + lane;
+        const int pc = p < kP ? p : kP - 1;
+        in[jj][0] = GB[(n * 2 + 0) * kCS + pc]; in[jj][1] = GB[(n * 2 + 1) * kCS + pc];
+        in[jj][2] = X0[(n * 2 + 0) * kCS + pc]; in[jj][3] = X0[(n * 2 + 1) * kCS + pc];
+      }
+      const float4* w4 = reinterpret_cast<const float4*>(WMs);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c4 = 0; c4 < kC1 / 4; ++c4) {
+          const float4 w = w4[k * (kC1 / 4) + c4];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            h[jj][4 * c4 + 0] = fmaf(in[jj][k], w.x, h[jj][4 * c4 + 0]);
+            h[jj][4 * c4 + 1] = fmaf(in[jj][k], w.y, h[jj][4 * c4 + 1]);
+            h[jj][4 * c4 + 2] = fmaf(in[jj][k], w.z, h[jj][4 * c4 + 2]);
+            h[jj][4 * c4 + 3] = fmaf(in[jj][k], w.w, h[jj][4 * c4 + 3]);
+          }
+        }
+      const float slope1 = WMs[4 * kC1 + kC1];
+#pragma unroll
+      for (int c = 0; c < kC1; ++c) {
+        const float b = WMs[4 * kC1 + c];
+        h[0][c] = prelu(h[0][c] + b, slope1);
+        h[1][c] = prelu(h[1][c] + b, slope1);
+      }
+      const uint32_t lane_base = spipe.tbase + (static_cast<uint32_t>(gq * 32) << 16);
+      sm_store_a(lane_base + sm_col_a(gg, 0), h[0]);
+      sm_publish_and_issue<32>(spipe, gg, 0, gq, lane, WMb, WMb + 32 * 32);
+      if (has1) sm_store_a(lane_base + sm_col_a(gg, 1), h[1]);
+      sm_publish_and_issue<32>(spipe, gg, 1, gq, lane, WMb, WMb + 32 * 32);
+    }
+    sm_epilogue<true>(spipe, gg, gq, lane, U2, Rsd2, WMb + 2 * 32 * 32, 0.f);
+    spipe.uses += 1;
     // ---- S4: L2 temporal in place on U
     boundary();
     acopy(WMb, Pm.tcL4X, 2 * 32 * 64);
+    acopy(WMs, Pm.tcL3, tc_blob_floats(32, 32));
     cp_async_commit();
     temporal_stage_c16<kTcWarps>(U2, U2, TB, warp, lane);
     // ---- S5: L2 spatial in place + residual + PReLU -> H2 (R1 rows 0..47)
@@ -303,9 +434,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     boundary();
     acopy(AB, Pm.eAw[3], kAwFloats);
     cp_async_commit();
-    tc_mix_phase<kC2, kC2, kC3>(pipe, G3, H2, WMs, WMs + 32 * 32, false, warp, lane);
-    tc_wait_done(pipe);
-    tc_epilogue_store<kC3, false>(pipe, R0, nullptr, WMs + 2 * 32 * 32, WMs[2 * 32 * 32 + 32], warp, lane);
+    {
+      const int n = gg;
+      const uint32_t lane_base = spipe.tbase + (static_cast<uint32_t>(gq * 32) << 16);
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj == 0 || gq < 3) {
+          const int p = jj * 128 + gq * 32 + lane;
+          const int pc = p < kP ? p : kP - 1;
+          float a[32];
+#pragma unroll
+          for (int k = 0; k < kC2; ++k) {
+            a[k] = G3[(n * kC2 + k) * kCS + pc];
+            a[kC2 + k] = H2[(n * kC2 + k) * kCS + pc];
+          }
+          sm_store_a(lane_base + sm_col_a(gg, jj), a);
+        }
+        sm_publish_and_issue<32>(spipe, gg, jj, gq, lane, WMs, WMs + 32 * 32);
+      }
+    }
+    sm_epilogue<false>(spipe, gg, gq, lane, R0, nullptr, WMs + 2 * 32 * 32, WMs[2 * 32 * 32 + 32]);
+    spipe.uses += 1;
     // ---- S9: L4 residual half issued first (inputs H3 = R0): runs on the tensor cores while the CUDA cores do the
     //          layer-4 graph contraction below;  L4 temporal: H3 (R0) -> G4 (R1)
     boundary();
