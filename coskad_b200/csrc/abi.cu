@@ -142,6 +142,7 @@ extern "C" int coskad_set_encoder(coskad_ctx* ctx, int n_layers, const coskad_la
   }
   const size_t oHW = off; off += static_cast<size_t>(kDP) * kF;
   const size_t oHB = off; off += kDP;
+  const size_t oHW4 = off; off += static_cast<size_t>(kDP) * kF;
   // tensor-core blobs of the mixing stages (fused_eval_tc.cuh)
   const size_t oT1 = off; off += align4(tc_blob_floats(8, 32));
   const size_t oT2 = off; off += align4(tc_blob_floats(32, 32));
@@ -161,6 +162,9 @@ extern "C" int coskad_set_encoder(coskad_ctx* ctx, int n_layers, const coskad_la
   CK_LAUNCH();
   ctx->fp.head_w = ctx->enc_pack + oHW;
   ctx->fp.head_b = ctx->enc_pack + oHB;
+  pack_head4_kernel<<<64, 256, 0, st>>>(head_w, head_rows, ctx->enc_pack + oHW4);
+  CK_LAUNCH();
+  ctx->tp.head_w4 = ctx->enc_pack + oHW4;
   fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[0], 0, 8, 32, ctx->enc_pack + oT1);
   CK_LAUNCH();
   fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[1], 1, 32, 32, ctx->enc_pack + oT2);

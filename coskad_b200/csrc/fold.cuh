@@ -104,6 +104,23 @@ __global__ void pack_head_kernel(const float* w, const float* b, int rows, float
   for (int64_t i = tid; i < kDP; i += nth) bp[i] = (i < rows && b != nullptr) ? b[i] : 0.f;
 }
 
+// head weights for the tensor-core kernel's head stage: wq[c][dq][p][4] = w[4 dq + i][c*204 + p] (rows >= `rows` are 0), so
+// that a lane (= position p) fetches 4 latent rows of its (c, p) feature with one LDG.128 and a warp's request covers
+// 512 contiguous bytes
+__global__ void pack_head4_kernel(const float* w, int rows, float* wq) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < static_cast<int64_t>(kDP) * kF; i += nth) {
+    const int e = static_cast<int>(i & 3);
+    const int64_t r = i >> 2;
+    const int p = static_cast<int>(r % kP);
+    const int dq = static_cast<int>((r / kP) % (kDP / 4));
+    const int c = static_cast<int>(r / (kP * (kDP / 4)));
+    const int d = 4 * dq + e;
+    wq[i] = (d < rows) ? w[static_cast<int64_t>(d) * kF + c * kP + p] : 0.f;
+  }
+}
+
 // ---- decoder first layer collapse (float64) -----------------------------------------------------
 // basis e < DL: In_e[ci][p] = rev_w[(ci*204+p)*DL + e];  e == DL: rev_b[ci*204+p]
 __global__ void dec_basis_kernel(const float* rev_w, const float* rev_b, int DL, int CI, double* In) {

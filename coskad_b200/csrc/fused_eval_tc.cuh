@@ -43,6 +43,7 @@ struct FusedTcParams {
   const float* tcL4X;     // K 32 (H3, residual conv), N 64
   const float* tcL4G;     // K 32 (G4, tcn conv), N 64, carries bias + slope
   const float* head_w;    // [16][kF]
+  const float* head_w4;   // [64][4][204][4]: (c, dq, p, i) = head_w[4 dq + i][c*204 + p] (fold.cuh pack_head4_kernel)
   const float* head_b;    // [16]
   const float* x;
   const float* center;
@@ -479,11 +480,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       const float* bias = WMb + 2 * 32 * 64;
       const float slope4 = bias[kC4];
       const int q = warp & 3, sub = warp >> 2;
-      float z[kNW][kDP];
+      unsigned long long z2[kNW][kDP / 2];           // packed (d, d+1) accumulators for fma.rn.f32x2
 #pragma unroll
       for (int n = 0; n < kNW; ++n)
 #pragma unroll
-        for (int d = 0; d < kDP; ++d) z[n][d] = 0.f;
+        for (int dp = 0; dp < kDP / 2; ++dp) z2[n][dp] = 0ull;
       // 8 units (half j, 16-channel chunk) per lane quarter, split 3/3/2 over the three warp groups
       const int u0 = sub * 3, u1 = (sub == 2) ? 8 : u0 + 3;
       for (int unit = u0; unit < u1; ++unit) {
@@ -498,27 +499,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const float b = bias[c0 + u];
-            float h[kNW];
+            // 4 x LDG.128: the 16 latent rows of feature (c0+u, p), as 8 (d, d+1) pairs
+            const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(Pm.head_w4) + static_cast<size_t>((c0 + u) * (kDP / 4)) * kP + p;
+            unsigned long long w2[kDP / 2];
 #pragma unroll
-            for (int n = 0; n < kNW; ++n) h[n] = prelu(__uint_as_float(v[n][u]) + b, slope4);
-            const float* wp = Pm.head_w + (c0 + u) * kP + p;
-            float w[kDP];
+            for (int dq = 0; dq < kDP / 4; ++dq) {
+              const ulonglong2 w = __ldg(wp + dq * kP);
+              w2[2 * dq] = w.x; w2[2 * dq + 1] = w.y;
+            }
 #pragma unroll
-            for (int d = 0; d < kDP; ++d) w[d] = __ldg(wp + d * kF);
+            for (int n = 0; n < kNW; ++n) {
+              const float h = prelu(__uint_as_float(v[n][u]) + b, slope4);
+              unsigned long long hh;
+              asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "r"(__float_as_uint(h)));
 #pragma unroll
-            for (int d = 0; d < kDP; ++d)
-#pragma unroll
-              for (int n = 0; n < kNW; ++n) z[n][d] = fmaf(h[n], w[d], z[n][d]);
+              for (int dp = 0; dp < kDP / 2; ++dp) tc::ffma2(z2[n][dp], hh, w2[dp]);
+            }
           }
         }
       }
+      // cross-lane reduction of the 48 partial sums by recursive halving (48 SHFL instead of 240): after the four
+      // halving steps lane L holds the 3 sums with index 24 b4 + 12 b3 + 6 b2 + 3 b1 + {0,1,2} (b_i = bit i of L),
+      // already combined over 16 lanes; the last step adds the lane pair
+      float r[kNW * kDP];
 #pragma unroll
       for (int n = 0; n < kNW; ++n)
 #pragma unroll
-        for (int d = 0; d < kDP; ++d) {
-          const float s = warp_sum(z[n][d]);
-          if (lane == 0) zpart[warp * (kNW * kDP) + n * kDP + d] = s;
+        for (int dp = 0; dp < kDP / 2; ++dp) {
+          r[n * kDP + 2 * dp] = __uint_as_float(static_cast<uint32_t>(z2[n][dp] & 0xffffffffull));
+          r[n * kDP + 2 * dp + 1] = __uint_as_float(static_cast<uint32_t>(z2[n][dp] >> 32));
         }
+      int idx = 0;
+#pragma unroll
+      for (int step = 0; step < 4; ++step) {
+        const int off = 16 >> step;                  // lane offset 16, 8, 4, 2
+        const int half = (kNW * kDP / 2) >> step;    // values kept: 24, 12, 6, 3
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float keep = up ? r[i + half] : r[i];
+          const float send = up ? r[i] : r[i + half];
+          r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        idx += up ? half : 0;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
+      if ((lane & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) zpart[warp * (kNW * kDP) + idx + i] = r[i];
+      }
     }
     // ---- S12: head reduce, geometry, score
     boundary();
