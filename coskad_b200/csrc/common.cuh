@@ -54,6 +54,19 @@ __device__ __forceinline__ float half_warp_sum(float v) {
   return v;
 }
 
+// packed FP32 FMA (sm_100a FFMA2): d.{lo,hi} += a.{lo,hi} * b.{lo,hi}; one issue slot for two FMAs (measured 92 % of
+// the scalar FFMA rate in FLOP terms, scratch/ubench/ffma2.cu) -- used where the FP32 stages are issue-bound
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long dup2(float x) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "r"(__float_as_uint(x)));
+  return r;
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { return __uint_as_float(static_cast<uint32_t>(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi2(unsigned long long v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+
 __device__ __forceinline__ float prelu(float v, float a) { return v >= 0.f ? v : a * v; }
 
 }  // namespace coskad

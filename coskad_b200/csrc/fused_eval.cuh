@@ -600,36 +600,34 @@ namespace coskad {
 // (profiles/r01_v3*: stall_no_inst 25-35 % of the samples of these stages).
 template <int NWARPS>
 __device__ __forceinline__ void temporal_stage_c32(const float* src, float* dst, const float* Tw, int warp, int lane) {
-  // tasks (v, q-half): 34 tasks; 6 of the 12 outputs q per task
+  // tasks (v, q-half): 34 tasks; 6 of the 12 outputs q per task, accumulated as 3 packed pairs (FFMA2)
   for (int task = warp; task < 2 * kV; task += NWARPS) {
     const int v = task >> 1, q0 = (task & 1) * 6;
-    float acc[kNW][6];
+    unsigned long long acc[kNW][3];
 #pragma unroll
     for (int n = 0; n < kNW; ++n)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) acc[n][q] = 0.f;
+      for (int q = 0; q < 3; ++q) acc[n][q] = 0ull;
     const float* s = src + lane * kCS + v;
     const float* w = Tw + v * (kT * kT) + q0;
 #pragma unroll 2
     for (int t = 0; t < kT; ++t) {
-      float x[kNW];
+      unsigned long long x[kNW];
 #pragma unroll
-      for (int n = 0; n < kNW; ++n) x[n] = s[n * 32 * kCS + t * kV];
-      const float2 w01 = *reinterpret_cast<const float2*>(w + t * kT);
-      const float2 w23 = *reinterpret_cast<const float2*>(w + t * kT + 2);
-      const float2 w45 = *reinterpret_cast<const float2*>(w + t * kT + 4);
+      for (int n = 0; n < kNW; ++n) x[n] = dup2(s[n * 32 * kCS + t * kV]);
+      const unsigned long long w01 = *reinterpret_cast<const unsigned long long*>(w + t * kT);
+      const unsigned long long w23 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 2);
+      const unsigned long long w45 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 4);
 #pragma unroll
       for (int n = 0; n < kNW; ++n) {
-        acc[n][0] = fmaf(x[n], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n], w01.y, acc[n][1]);
-        acc[n][2] = fmaf(x[n], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n], w23.y, acc[n][3]);
-        acc[n][4] = fmaf(x[n], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n], w45.y, acc[n][5]);
+        ffma2(acc[n][0], x[n], w01); ffma2(acc[n][1], x[n], w23); ffma2(acc[n][2], x[n], w45);
       }
     }
 #pragma unroll
     for (int n = 0; n < kNW; ++n) {
       float* d = dst + (n * 32 + lane) * kCS + v;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) d[(q0 + q) * kV] = acc[n][q];
+      for (int q = 0; q < 3; ++q) { d[(q0 + 2 * q) * kV] = lo2(acc[n][q]); d[(q0 + 2 * q + 1) * kV] = hi2(acc[n][q]); }
     }
   }
 }
@@ -637,11 +635,14 @@ __device__ __forceinline__ void temporal_stage_c32(const float* src, float* dst,
 template <int NWARPS>
 __device__ __forceinline__ void spatial_stage_c32(float* buf, const float* Aw, int warp, int lane) {
   for (int t = warp; t < kT; t += NWARPS) {
-    float acc[kNW][kV];
+    unsigned long long acc[kNW][8];     // outputs w = 0..15 as packed pairs (FFMA2)
+    float acc16[kNW];                   // w = 16
 #pragma unroll
-    for (int n = 0; n < kNW; ++n)
+    for (int n = 0; n < kNW; ++n) {
 #pragma unroll
-      for (int w = 0; w < kV; ++w) acc[n][w] = 0.f;
+      for (int w = 0; w < 8; ++w) acc[n][w] = 0ull;
+      acc16[n] = 0.f;
+    }
     float* s = buf + lane * kCS + t * kV;
     const float* a = Aw + t * (kV * kAW);
 #pragma unroll 1
@@ -649,26 +650,25 @@ __device__ __forceinline__ void spatial_stage_c32(float* buf, const float* Aw, i
       float g[kNW];
 #pragma unroll
       for (int n = 0; n < kNW; ++n) g[n] = s[n * 32 * kCS + v];
-      const float4* a4 = reinterpret_cast<const float4*>(a + v * kAW);
+      const ulonglong2* a4 = reinterpret_cast<const ulonglong2*>(a + v * kAW);
       const float w16 = a[v * kAW + 16];
+      unsigned long long g2[kNW];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) g2[n] = dup2(g[n]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 w = a4[j];
+        const ulonglong2 w = a4[j];
 #pragma unroll
-        for (int n = 0; n < kNW; ++n) {
-          acc[n][4 * j + 0] = fmaf(g[n], w.x, acc[n][4 * j + 0]);
-          acc[n][4 * j + 1] = fmaf(g[n], w.y, acc[n][4 * j + 1]);
-          acc[n][4 * j + 2] = fmaf(g[n], w.z, acc[n][4 * j + 2]);
-          acc[n][4 * j + 3] = fmaf(g[n], w.w, acc[n][4 * j + 3]);
-        }
+        for (int n = 0; n < kNW; ++n) { ffma2(acc[n][2 * j], g2[n], w.x); ffma2(acc[n][2 * j + 1], g2[n], w.y); }
       }
 #pragma unroll
-      for (int n = 0; n < kNW; ++n) acc[n][16] = fmaf(g[n], w16, acc[n][16]);
+      for (int n = 0; n < kNW; ++n) acc16[n] = fmaf(g[n], w16, acc16[n]);
     }
 #pragma unroll
     for (int n = 0; n < kNW; ++n) {
 #pragma unroll
-      for (int w = 0; w < kV; ++w) s[n * 32 * kCS + w] = acc[n][w];
+      for (int w = 0; w < 8; ++w) { s[n * 32 * kCS + 2 * w] = lo2(acc[n][w]); s[n * 32 * kCS + 2 * w + 1] = hi2(acc[n][w]); }
+      s[n * 32 * kCS + 16] = acc16[n];
     }
   }
 }
@@ -728,26 +728,24 @@ template <int NWARPS>
 __device__ __forceinline__ void temporal_stage_c16(const float* src, float* dst, const float* Tw, int warp, int lane) {
   const int c = lane & 15, q0 = (lane >> 4) * 6;          // half 0: q 0..5, half 1: q 6..11
   for (int v = warp; v < kV; v += NWARPS) {
-    float acc[kNW][6];
+    unsigned long long acc[kNW][3];
 #pragma unroll
     for (int n = 0; n < kNW; ++n)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) acc[n][q] = 0.f;
+      for (int q = 0; q < 3; ++q) acc[n][q] = 0ull;
     const float* s = src + c * kCS + v;
     const float* w = Tw + v * (kT * kT) + q0;
 #pragma unroll 2
     for (int t = 0; t < kT; ++t) {
-      float x[kNW];
+      unsigned long long x[kNW];
 #pragma unroll
-      for (int n = 0; n < kNW; ++n) x[n] = s[n * 16 * kCS + t * kV];
-      const float2 w01 = *reinterpret_cast<const float2*>(w + t * kT);
-      const float2 w23 = *reinterpret_cast<const float2*>(w + t * kT + 2);
-      const float2 w45 = *reinterpret_cast<const float2*>(w + t * kT + 4);
+      for (int n = 0; n < kNW; ++n) x[n] = dup2(s[n * 16 * kCS + t * kV]);
+      const unsigned long long w01 = *reinterpret_cast<const unsigned long long*>(w + t * kT);
+      const unsigned long long w23 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 2);
+      const unsigned long long w45 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 4);
 #pragma unroll
       for (int n = 0; n < kNW; ++n) {
-        acc[n][0] = fmaf(x[n], w01.x, acc[n][0]); acc[n][1] = fmaf(x[n], w01.y, acc[n][1]);
-        acc[n][2] = fmaf(x[n], w23.x, acc[n][2]); acc[n][3] = fmaf(x[n], w23.y, acc[n][3]);
-        acc[n][4] = fmaf(x[n], w45.x, acc[n][4]); acc[n][5] = fmaf(x[n], w45.y, acc[n][5]);
+        ffma2(acc[n][0], x[n], w01); ffma2(acc[n][1], x[n], w23); ffma2(acc[n][2], x[n], w45);
       }
     }
     __syncwarp();      // in-place use: both halves have read the column before either writes it
@@ -755,7 +753,7 @@ __device__ __forceinline__ void temporal_stage_c16(const float* src, float* dst,
     for (int n = 0; n < kNW; ++n) {
       float* d = dst + (n * 16 + c) * kCS + v;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) d[(q0 + q) * kV] = acc[n][q];
+      for (int q = 0; q < 3; ++q) { d[(q0 + 2 * q) * kV] = lo2(acc[n][q]); d[(q0 + 2 * q + 1) * kV] = hi2(acc[n][q]); }
     }
   }
 }
@@ -765,11 +763,14 @@ template <class Epi, int NWARPS>
 __device__ __forceinline__ void spatial_stage_c16(float* buf, const float* Aw, const Epi epi, int warp, int lane) {
   const int c = lane & 15, h = lane >> 4;
   for (int t = warp; t < kT; t += NWARPS) {
-    float acc[kNW][9];
+    unsigned long long acc[kNW][4];     // outputs 8 h .. 8 h + 7 as packed pairs (FFMA2)
+    float acc8[kNW];
 #pragma unroll
-    for (int n = 0; n < kNW; ++n)
+    for (int n = 0; n < kNW; ++n) {
 #pragma unroll
-      for (int j = 0; j < 9; ++j) acc[n][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[n][j] = 0ull;
+      acc8[n] = 0.f;
+    }
     const float* s = buf + c * kCS + t * kV;
     const float* a = Aw + t * (kV * kAW) + 8 * h;
 #pragma unroll 1
@@ -777,16 +778,15 @@ __device__ __forceinline__ void spatial_stage_c16(float* buf, const float* Aw, c
       float g[kNW];
 #pragma unroll
       for (int n = 0; n < kNW; ++n) g[n] = s[n * 16 * kCS + v];
-      const float4 w0 = *reinterpret_cast<const float4*>(a + v * kAW);
-      const float4 w1 = *reinterpret_cast<const float4*>(a + v * kAW + 4);
+      const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(a + v * kAW);
+      const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(a + v * kAW + 4);
       const float w8 = a[v * kAW + 8];                  // half 1: w = 16; half 0: w = 8 (belongs to half 1, discarded)
 #pragma unroll
       for (int n = 0; n < kNW; ++n) {
-        acc[n][0] = fmaf(g[n], w0.x, acc[n][0]); acc[n][1] = fmaf(g[n], w0.y, acc[n][1]);
-        acc[n][2] = fmaf(g[n], w0.z, acc[n][2]); acc[n][3] = fmaf(g[n], w0.w, acc[n][3]);
-        acc[n][4] = fmaf(g[n], w1.x, acc[n][4]); acc[n][5] = fmaf(g[n], w1.y, acc[n][5]);
-        acc[n][6] = fmaf(g[n], w1.z, acc[n][6]); acc[n][7] = fmaf(g[n], w1.w, acc[n][7]);
-        acc[n][8] = fmaf(g[n], w8, acc[n][8]);
+        const unsigned long long g2 = dup2(g[n]);
+        ffma2(acc[n][0], g2, w0.x); ffma2(acc[n][1], g2, w0.y);
+        ffma2(acc[n][2], g2, w1.x); ffma2(acc[n][3], g2, w1.y);
+        acc8[n] = fmaf(g[n], w8, acc8[n]);
       }
     }
     __syncwarp();      // in place: both halves have read the 17 inputs of their rows
@@ -795,8 +795,11 @@ __device__ __forceinline__ void spatial_stage_c16(float* buf, const float* Aw, c
       const int row = n * 16 + c;
       float* d = buf + row * kCS + t * kV;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[8 * h + j] = epi(acc[n][j], row, t * kV + 8 * h + j);
-      if (h == 1) d[16] = epi(acc[n][8], row, t * kV + 16);
+      for (int j = 0; j < 4; ++j) {
+        d[8 * h + 2 * j] = epi(lo2(acc[n][j]), row, t * kV + 8 * h + 2 * j);
+        d[8 * h + 2 * j + 1] = epi(hi2(acc[n][j]), row, t * kV + 8 * h + 2 * j + 1);
+      }
+      if (h == 1) d[16] = epi(acc8[n], row, t * kV + 16);
     }
   }
 }

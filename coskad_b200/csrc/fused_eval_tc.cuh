@@ -510,10 +510,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 #pragma unroll
             for (int n = 0; n < kNW; ++n) {
               const float h = prelu(__uint_as_float(v[n][u]) + b, slope4);
-              unsigned long long hh;
-              asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "r"(__float_as_uint(h)));
+              const unsigned long long hh = dup2(h);
 #pragma unroll
-              for (int dp = 0; dp < kDP / 2; ++dp) tc::ffma2(z2[n][dp], hh, w2[dp]);
+              for (int dp = 0; dp < kDP / 2; ++dp) ffma2(z2[n][dp], hh, w2[dp]);
             }
           }
         }

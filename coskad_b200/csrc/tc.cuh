@@ -98,12 +98,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 
-// packed FP32 FMA (sm_100a FFMA2): d.{lo,hi} += a.{lo,hi} * b.{lo,hi}; one issue slot for two FMAs (measured 92 % of
-// the scalar FFMA rate in FLOP terms, scratch/ubench/ffma2.cu) -- used where the FP32 stages are issue-bound
-__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-}
-
 __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(a) & 0xFFFFE000u;
   lo = __float_as_uint(a - __uint_as_float(hi)) & 0xFFFFE000u;
