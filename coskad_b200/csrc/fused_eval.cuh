@@ -598,37 +598,50 @@ namespace coskad {
 // The contraction index (t or v) is a real loop (not unrolled): each warp runs a task exactly once per tile, so fully
 // unrolled bodies are straight-line code with no reuse and the warps starve on instruction fetch
 // (profiles/r01_v3*: stall_no_inst 25-35 % of the samples of these stages).
-template <int NWARPS>
-__device__ __forceinline__ void temporal_stage_c32(const float* src, float* dst, const float* Tw, int warp, int lane) {
-  // tasks (v, q-half): 34 tasks; 6 of the 12 outputs q per task, accumulated as 3 packed pairs (FFMA2)
-  for (int task = warp; task < 2 * kV; task += NWARPS) {
-    const int v = task >> 1, q0 = (task & 1) * 6;
-    unsigned long long acc[kNW][3];
+// one task (v, q-half) of the C = 32 temporal contraction: 6 of the 12 outputs q, accumulated as 3 packed pairs (FFMA2)
+__device__ __forceinline__ void temporal_task_c32(const float* src, float* dst, const float* Tw, int task, int lane) {
+  const int v = task >> 1, q0 = (task & 1) * 6;
+  unsigned long long acc[kNW][3];
 #pragma unroll
-    for (int n = 0; n < kNW; ++n)
+  for (int n = 0; n < kNW; ++n)
 #pragma unroll
-      for (int q = 0; q < 3; ++q) acc[n][q] = 0ull;
-    const float* s = src + lane * kCS + v;
-    const float* w = Tw + v * (kT * kT) + q0;
-#pragma unroll 2
-    for (int t = 0; t < kT; ++t) {
-      unsigned long long x[kNW];
+    for (int q = 0; q < 3; ++q) acc[n][q] = 0ull;
+  const float* s = src + lane * kCS + v;
+  const float* w = Tw + v * (kT * kT) + q0;
+#pragma unroll 4
+  for (int t = 0; t < kT; ++t) {
+    unsigned long long x[kNW];
 #pragma unroll
-      for (int n = 0; n < kNW; ++n) x[n] = dup2(s[n * 32 * kCS + t * kV]);
-      const unsigned long long w01 = *reinterpret_cast<const unsigned long long*>(w + t * kT);
-      const unsigned long long w23 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 2);
-      const unsigned long long w45 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 4);
-#pragma unroll
-      for (int n = 0; n < kNW; ++n) {
-        ffma2(acc[n][0], x[n], w01); ffma2(acc[n][1], x[n], w23); ffma2(acc[n][2], x[n], w45);
-      }
-    }
+    for (int n = 0; n < kNW; ++n) x[n] = dup2(s[n * 32 * kCS + t * kV]);
+    const unsigned long long w01 = *reinterpret_cast<const unsigned long long*>(w + t * kT);
+    const unsigned long long w23 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 2);
+    const unsigned long long w45 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 4);
 #pragma unroll
     for (int n = 0; n < kNW; ++n) {
-      float* d = dst + (n * 32 + lane) * kCS + v;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) { d[(q0 + 2 * q) * kV] = lo2(acc[n][q]); d[(q0 + 2 * q + 1) * kV] = hi2(acc[n][q]); }
+      ffma2(acc[n][0], x[n], w01); ffma2(acc[n][1], x[n], w23); ffma2(acc[n][2], x[n], w45);
     }
+  }
+#pragma unroll
+  for (int n = 0; n < kNW; ++n) {
+    float* d = dst + (n * 32 + lane) * kCS + v;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { d[(q0 + 2 * q) * kV] = lo2(acc[n][q]); d[(q0 + 2 * q + 1) * kV] = hi2(acc[n][q]); }
+  }
+}
+// next task from a shared-memory counter (zeroed by the caller before the preceding barrier); warp-uniform result
+__device__ __forceinline__ int next_task(int* ctr, int lane) {
+  int tk = 0;
+  if (lane == 0) tk = atomicAdd(ctr, 1);
+  return __shfl_sync(0xffffffffu, tk, 0);
+}
+// `ctr` != nullptr: tasks are handed out dynamically -- used where the warps enter the stage at different times
+template <int NWARPS>
+__device__ __forceinline__ void temporal_stage_c32(const float* src, float* dst, const float* Tw, int warp, int lane,
+                                                   int* ctr = nullptr) {
+  for (int task = warp;; task += NWARPS) {        // 34 tasks (v, q-half)
+    if (ctr != nullptr) task = next_task(ctr, lane);
+    if (task >= 2 * kV) break;
+    temporal_task_c32(src, dst, Tw, task, lane);
   }
 }
 
@@ -735,7 +748,7 @@ __device__ __forceinline__ void temporal_stage_c16(const float* src, float* dst,
       for (int q = 0; q < 3; ++q) acc[n][q] = 0ull;
     const float* s = src + c * kCS + v;
     const float* w = Tw + v * (kT * kT) + q0;
-#pragma unroll 2
+#pragma unroll 4
     for (int t = 0; t < kT; ++t) {
       unsigned long long x[kNW];
 #pragma unroll
