@@ -1,0 +1,42 @@
+"""training-step timing on one GPU: hyperbolic dynamic-center step (fwd + bwd + Adam), batch 2048 (BASELINE configs[4])"""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from coskad_b200 import synth, gmath, _lib
+from coskad_b200.losses import calc_reg_loss
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+dev = torch.device('cuda', 0)
+m = synth.make_model('stse', 16, seed=0, device=dev).train()
+opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+g = torch.Generator(device=dev).manual_seed(999)
+x = torch.empty(B, 2, 12, 17, device=dev)
+synth.synth_windows_(x, g)
+c = torch.zeros(16, device=dev); c[0] = 0.1
+acc = gmath.center_accumulator(16, dev)
+
+def step():
+    hidden = m(x)
+    reg = calc_reg_loss(m)
+    dist_c, hid = gmath.poincare_score(hidden, c, True)
+    gmath.center_partial(hid, acc, _lib.SCORE_POINCARE)
+    loss = dist_c.mean() + 1e-6 * reg
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+    return loss
+
+for _ in range(5): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+N = 20
+t0 = time.perf_counter(); e0.record()
+for _ in range(N): l = step()
+e1.record(); torch.cuda.synchronize(); t1 = time.perf_counter()
+ms = e0.elapsed_time(e1) / N
+print(f'B={B}: {ms:.3f} ms/step (device), {(t1-t0)/N*1e3:.3f} ms/step (wall) -> {B/ms*1e3:.0f} windows/s, loss {float(l):.4f}')
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=28, max_name_column_width=60))
