@@ -374,30 +374,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     }
   };
 
+  // ---- layer-1 graph contraction of the FIRST tile (all warps).  For every later tile it is done one tile ahead by the
+  //      three warps of TMEM lane quarter 3 during the head stage, where they have half the work of the other quarters
+  //      (positions 224..255 do not exist): see the end of stage S11.
+  boundary();
+  temporal_stage_l1<kTcWarps>(XB, GB, TB, warp, lane);
+  boundary();
+  spatial_stage_l1<kTcWarps>(GB, AB, warp, lane);
+
   int cur = 0;
   int64_t last_tile = -1;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1) {
     float* X0 = XB + cur * kRSmall;
     const int64_t next_tile = tile + gridDim.x;
 
-    // ---- S0: L1 temporal  X0 -> GB
-    boundary();
-    acopy(WMb, Pm.tcL2, tc_blob_floats(32, 32));        // WMb: free since the head of the previous tile
-    cp_async_commit();
-    if (last_tile >= 0) finalize(last_tile, cur ^ 1);
-    last_tile = tile;
-    temporal_stage_l1<kTcWarps>(X0, GB, TB, warp, lane);
-    // ---- S1: L1 spatial in place on GB
-    boundary();
-    acopy(TB, Pm.eTw[1], kTwFloats);
-    if (next_tile < ntiles) load_x(XB + (cur ^ 1) * kRSmall, next_tile);
-    cp_async_commit();
-    spatial_stage_l1<kTcWarps>(GB, AB, warp, lane);
     // ---- S2+S3: L1 mix (K = 4, FP32 pipe, registers) -> H1 split straight into the TMEM A operand (never stored) ->
     //             L2 (32->16) mix-first on tensor cores: U (R1 rows 0..47) | Rsd (R1 rows 48..95)
     boundary();
     acopy(AB, Pm.eAw[1], kAwFloats);
+    acopy(TB, Pm.eTw[1], kTwFloats);
+    if (next_tile < ntiles) load_x(XB + (cur ^ 1) * kRSmall, next_tile);
     cp_async_commit();
+    if (last_tile >= 0) finalize(last_tile, cur ^ 1);
+    last_tile = tile;
     float* U2 = R1;
     float* Rsd2 = R1 + kNW * kC2 * kCS;
     const float slope2 = WMb[2 * 32 * 32 + 32];
@@ -515,8 +514,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     spatial_stage_c32<kTcWarps>(R1, AB, warp, lane);
     // ---- S11: L4 graph half accumulates onto D, then PReLU + linear head straight from TMEM (H4 never stored)
     boundary();
-    acopy(AB, Pm.eAw[0], kAwFloats);
-    cp_async_commit();
     pipe.half = &bars[11];
     tc_mix_phase<kC3, 0, kC4>(pipe, R1, nullptr, WMb, WMb + 32 * 64, true, warp, lane);
     pipe.half = nullptr;
@@ -535,7 +532,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 #pragma unroll
         for (int dp = 0; dp < kDP / 2; ++dp) z2[n][dp] = 0ull;
       // 8 units (half j, 16-channel chunk) per lane quarter, split 3/3/2 over the three warp groups
-      const int u0 = sub * 3, u1 = (sub == 2) ? 8 : u0 + 3;
+      // (quarter 3 holds no j = 1 positions: its 4 units go 2/2/0, and its warps run the next tile's layer 1 afterwards)
+      const int u0 = q < 3 ? sub * 3 : sub * 2, u1 = q < 3 ? ((sub == 2) ? 8 : u0 + 3) : (sub == 2 ? u0 : u0 + 2);
       for (int unit = u0; unit < u1; ++unit) {
         const int j = unit >> 2, c0 = (unit & 3) * 16;
         const int p = j * 128 + q * 32 + lane;
@@ -599,6 +597,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 #pragma unroll
         for (int i = 0; i < 3; ++i) zpart[(cur * kTcWarps + warp) * (kNW * kDP) + idx + i] = r[i];
       }
+    }
+    // ---- layer-1 graph contraction of the NEXT tile on the three quarter-3 warps (they had half the head work).
+    //      All MMAs of this tile are complete (tc_wait_done above), so the weight images in WMb are dead (the head of
+    //      the other warps only reads the bias block behind them): stage the layer-2 blob there; AB (layer-4 A) is dead
+    //      since S10: stage the layer-1 A.  TB already holds the layer-1 T (loaded during S10).
+    if (gq == 3 && next_tile < ntiles) {
+      const int t96 = gg * 32 + lane;
+      for (int i = t96 * 4; i < tc_blob_floats(32, 32); i += 96 * 4) cp_async16(WMb + i, Pm.tcL2 + i);
+      for (int i = t96 * 4; i < kAwFloats; i += 96 * 4) cp_async16(AB + i, Pm.eAw[0] + i);
+      cp_async_commit();
+      float* Xn = XB + (cur ^ 1) * kRSmall;
+      temporal_stage_l1<3>(Xn, GB, TB, gg, lane);
+      cp_async_wait_all();
+      asm volatile("bar.sync 4, 96;" ::: "memory");
+      spatial_stage_l1<3>(GB, AB, gg, lane);
     }
   }
   cp_async_wait_all();
