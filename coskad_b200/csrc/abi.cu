@@ -614,9 +614,13 @@ extern "C" int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const flo
   switch (CO) { case 2: LAUNCH_BD(2); break; case 16: LAUNCH_BD(16); break; case 32: LAUNCH_BD(32); break; default: LAUNCH_BD(64); break; }
 #undef LAUNCH_BD
   CK_LAUNCH();
-  const size_t smem2 = sizeof(float) * 2 * (CO + CI) * kWC;
+  const size_t smem2 = sizeof(float) * 2 * (CO + CI) * kWCS;
+  if ((CO >= 4 && CO % 4) || (CI >= 4 && CI % 4) || (CO / (CO < 4 ? CO : 4)) * (CI / (CI < 4 ? CI : 4)) > 128 ||
+      (CO / (CO < 4 ? CO : 4)) * (CI / (CI < 4 ? CI : 4)) < 8)
+    return fail(ctx, COSKAD_ERR_ARG, "train_mix_bwd: unsupported channel pair %d -> %d", CI, CO);
+  CK(cudaFuncSetAttribute(train_mix_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
   int g2 = static_cast<int>((B * kP + kWC - 1) / kWC);
-  if (g2 > ctx->sm_count * 4) g2 = ctx->sm_count * 4;
+  if (g2 > ctx->sm_count * 2) g2 = ctx->sm_count * 2;
   train_mix_bwd_weight_kernel<<<g2, kTrainThreads, smem2, st>>>(dy1, dy2, G, X, B, CI, CO, dW1, db1, dW2, db2);
   CK_LAUNCH();
   return COSKAD_OK;

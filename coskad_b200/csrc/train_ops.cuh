@@ -338,24 +338,37 @@ __global__ void train_mix_bwd_data_kernel(const float* __restrict__ dy1, const f
   }
 }
 
-// dW1[co,ci] += sum_e dy1[e,co] G[e,ci]; db1[co] += sum_e dy1[e,co]; same for the residual branch.
-// Each block stages a chunk of kWC (b,p) elements of all channels in shared memory; every thread owns
-// (co, ci) pairs in registers across the block's chunks; one atomicAdd per pair per block at the end.
-constexpr int kWC = 32;
-__global__ void train_mix_bwd_weight_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
-                                            const float* __restrict__ G, const float* __restrict__ X, int64_t B,
-                                            int CI, int CO, float* dW1, float* db1, float* dW2, float* db2) {
-  extern __shared__ float sm[];
-  float* d1s = sm;                       // [CO][kWC]
-  float* d2s = d1s + CO * kWC;           // [CO][kWC]
-  float* gs = d2s + CO * kWC;            // [CI][kWC]
-  float* xs = gs + CI * kWC;             // [CI][kWC]
-  constexpr int MAXP = 16;               // pairs per thread: CO*CI <= 4096 with 256 threads
-  float a1[MAXP], a2[MAXP];
+// dW1[co,ci] += sum_e dy1[e,co] G[e,ci]; db1[co] += sum_e dy1[e,co]; same for the residual branch (e = (b,p)).
+// A split-K "GEMM" with tiny M x N (<= 64 x 64) and K = B*204: every block stages chunks of kWC elements e of all channels
+// in shared memory as rows [c][kWC + 4] (row stride = 4 mod 32 banks: LDS.128 of 8 consecutive rows is conflict free),
+// every thread owns a 4 x 4 tile of (co, ci) pairs with STRIDED members (co = cot + i*NOT, ci = cit + j*NCT, so that the
+// lanes of a quarter warp read consecutive rows) and, when there are fewer than 256 tiles, one of the k-slices of the
+// chunk; 16 LDS.128 feed 128 FMAs.  One atomicAdd per pair per thread at the end.
+constexpr int kWC = 128;
+constexpr int kWCS = kWC + 4;
+__global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
+    const float* __restrict__ dy1, const float* __restrict__ dy2, const float* __restrict__ G, const float* __restrict__ X,
+    int64_t B, int CI, int CO, float* dW1, float* db1, float* dW2, float* db2) {
+  extern __shared__ __align__(16) float sm[];
+  float* d1s = sm;                       // [CO][kWCS]
+  float* d2s = d1s + CO * kWCS;          // [CO][kWCS]
+  float* gs = d2s + CO * kWCS;           // [CI][kWCS]
+  float* xs = gs + CI * kWCS;            // [CI][kWCS]
+  const int TCO = CO < 4 ? CO : 4, TCI = CI < 4 ? CI : 4;
+  const int NOT = CO / TCO, NCT = CI / TCI;              // tiles along co / ci
+  const int ntile = NOT * NCT;                           // <= 128 for every configured layer
+  const int nks = kTrainThreads / ntile;                 // k-slices (>= 2)
+  const int kslice = kWC / nks;                          // multiple of 4: ntile >= 8
+  const int tile = threadIdx.x % ntile, ks = threadIdx.x / ntile;
+  const int cit = tile % NCT, cot = tile / NCT;
+  const bool active = ks < nks;
+  float a1[4][4], a2[4][4], bs1[4], bs2[4];
 #pragma unroll
-  for (int j = 0; j < MAXP; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
-  float bsum1 = 0.f, bsum2 = 0.f;        // thread co < CO owns the bias sums
-  const int npair = CO * CI;
+  for (int i = 0; i < 4; ++i) {
+    bs1[i] = 0.f; bs2[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a1[i][j] = 0.f; a2[i][j] = 0.f; }
+  }
   const int64_t E = B * kP;
   for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * kWC; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * kWC) {
     __syncthreads();
@@ -366,37 +379,56 @@ __global__ void train_mix_bwd_weight_kernel(const float* __restrict__ dy1, const
       const int64_t b = valid ? e / kP : 0;
       const int p = valid ? static_cast<int>(e - b * kP) : 0;
       if (c < CO) {
-        d1s[c * kWC + k] = valid ? dy1[(b * CO + c) * kP + p] : 0.f;
-        d2s[c * kWC + k] = valid ? dy2[(b * CO + c) * kP + p] : 0.f;
+        d1s[c * kWCS + k] = valid ? dy1[(b * CO + c) * kP + p] : 0.f;
+        d2s[c * kWCS + k] = valid ? dy2[(b * CO + c) * kP + p] : 0.f;
       } else {
-        gs[(c - CO) * kWC + k] = valid ? G[(b * CI + (c - CO)) * kP + p] : 0.f;
-        xs[(c - CO) * kWC + k] = valid ? X[(b * CI + (c - CO)) * kP + p] : 0.f;
+        gs[(c - CO) * kWCS + k] = valid ? G[(b * CI + (c - CO)) * kP + p] : 0.f;
+        xs[(c - CO) * kWCS + k] = valid ? X[(b * CI + (c - CO)) * kP + p] : 0.f;
       }
     }
     __syncthreads();
+    if (active) {
+      for (int k = ks * kslice; k < (ks + 1) * kslice; k += 4) {
+        float4 d1[4], d2[4], g[4], x[4];
 #pragma unroll
-    for (int j = 0; j < MAXP; ++j) {
-      const int pr = threadIdx.x + j * kTrainThreads;
-      if (pr < npair) {
-        const int co = pr / CI, ci = pr % CI;
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < kWC; ++k) { s1 = fmaf(d1s[co * kWC + k], gs[ci * kWC + k], s1); s2 = fmaf(d2s[co * kWC + k], xs[ci * kWC + k], s2); }
-        a1[j] += s1; a2[j] += s2;
+        for (int i = 0; i < 4; ++i) {
+          const int co = (i < TCO) ? cot + i * NOT : cot;
+          const int ci = (i < TCI) ? cit + i * NCT : cit;
+          d1[i] = *reinterpret_cast<const float4*>(d1s + co * kWCS + k);
+          d2[i] = *reinterpret_cast<const float4*>(d2s + co * kWCS + k);
+          g[i] = *reinterpret_cast<const float4*>(gs + ci * kWCS + k);
+          x[i] = *reinterpret_cast<const float4*>(xs + ci * kWCS + k);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a1[i][j] = fmaf(d1[i].x, g[j].x, a1[i][j]); a1[i][j] = fmaf(d1[i].y, g[j].y, a1[i][j]);
+            a1[i][j] = fmaf(d1[i].z, g[j].z, a1[i][j]); a1[i][j] = fmaf(d1[i].w, g[j].w, a1[i][j]);
+            a2[i][j] = fmaf(d2[i].x, x[j].x, a2[i][j]); a2[i][j] = fmaf(d2[i].y, x[j].y, a2[i][j]);
+            a2[i][j] = fmaf(d2[i].z, x[j].z, a2[i][j]); a2[i][j] = fmaf(d2[i].w, x[j].w, a2[i][j]);
+          }
+          bs1[i] += (d1[i].x + d1[i].y) + (d1[i].z + d1[i].w);
+          bs2[i] += (d2[i].x + d2[i].y) + (d2[i].z + d2[i].w);
+        }
       }
     }
-    if (threadIdx.x < CO) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int k = 0; k < kWC; ++k) { s1 += d1s[threadIdx.x * kWC + k]; s2 += d2s[threadIdx.x * kWC + k]; }
-      bsum1 += s1; bsum2 += s2;
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i >= TCO) break;
+      const int co = cot + i * NOT;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= TCI) break;
+        const int ci = cit + j * NCT;
+        atomicAdd(dW1 + co * CI + ci, a1[i][j]);
+        atomicAdd(dW2 + co * CI + ci, a2[i][j]);
+      }
+      if (cit == 0) { if (db1) atomicAdd(db1 + co, bs1[i]); if (db2) atomicAdd(db2 + co, bs2[i]); }
     }
   }
-#pragma unroll
-  for (int j = 0; j < MAXP; ++j) {
-    const int pr = threadIdx.x + j * kTrainThreads;
-    if (pr < npair) { atomicAdd(dW1 + pr, a1[j]); atomicAdd(dW2 + pr, a2[j]); }
-  }
-  if (threadIdx.x < CO) { if (db1) atomicAdd(db1 + threadIdx.x, bsum1); if (db2) atomicAdd(db2 + threadIdx.x, bsum2); }
 }
 
 // ---- linear layers over the flattened features ------------------------------------------------------
