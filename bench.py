@@ -262,8 +262,8 @@ def run_ours(args):
     ach_tf = FLOP_PER_WINDOW * W / (k_ms * 1e-3) / 1e12
     ach_gb = BYTES_PER_WINDOW * W / (k_ms * 1e-3) / 1e9
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    # ncu dram__bytes_read+write of one launch (profiles/r01_v2_fused_eval_tc.md: 223.8 MB for 131 072 windows)
-    traffic_per_window = 223.78e6 / 131072
+    # ncu dram__bytes_read+write of one launch (profiles/r01_v5_fused_eval_tc.md: 215.26 + 6.23 MB for 131 072 windows)
+    traffic_per_window = 221.49e6 / 131072
     roofline = {'bound': 'fp32_fma', 'achieved': ach_tf, 'peak': fp32_peak_measured, 'unit': 'TFLOP/s',
                 'frac': ach_tf / fp32_peak_measured if fp32_peak_measured else None,
                 'traffic': traffic_per_window * W, 'traffic_unit': 'bytes per launch (ncu dram read+write, scaled from the profiled launch)',
@@ -274,7 +274,8 @@ def run_ours(args):
                 'note': 'algorithmic FLOPs (3.947 MFLOP/window, SURVEY.md 8-d) over the launch time, against the FP32-FMA '
                         'peak: the fused path is compute bound (2 400 FLOP/B). 65 % of the MACs (channel mixing) execute on '
                         'tcgen05 kind::tf32 with 3xTF32 split operands, the graph contractions and the linear head on the '
-                        'FP32 pipe; roofline_hbm gives the HBM view of the same launch'}
+                        'FP32 pipe (packed FFMA2); the head stage streams 835 KB of weights per 3-window tile from L2 and '
+                        'runs at the per-SM L2 fetch rate; roofline_hbm gives the HBM view of the same launch'}
     roofline_hbm = {'bound': 'hbm', 'achieved': ach_gb, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gb / hbm_peak,
                     'traffic': traffic_per_window * W, 'bytes_per_window': BYTES_PER_WINDOW,
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'}
