@@ -1,0 +1,28 @@
+"""throughput of the other fused eval variants: auto-encoder (decoder + reconstruction score, latent 8) and D=8 encoder"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from coskad_b200 import synth, _lib
+dev = torch.device('cuda', 0)
+B = 262144
+g = torch.Generator(device=dev).manual_seed(999)
+x = torch.empty(B, 2, 12, 17, device=dev); synth.synth_windows_(x, g)
+def timeit(fn, n=5):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+ae = synth.make_model('stsae', 8, seed=0, device=dev)
+c = torch.zeros(8, device=dev)
+ms = timeit(lambda: ae.autoencode_score(x, center=c, want_xhat=False))
+print(f'STSAE D=8 encode+decode+rec score: {ms:.2f} ms -> {B/ms*1e3/1e6:.2f} M windows/s')
+e8 = synth.make_model('stse', 8, seed=0, device=dev)
+ms = timeit(lambda: e8.encode_score(x, _lib.SCORE_EUCLID, center=c, want_latent=False))
+print(f'STSE D=8 euclid score: {ms:.2f} ms -> {B/ms*1e3/1e6:.2f} M windows/s')
+e16 = synth.make_model('stse', 16, seed=0, device=dev)
+c16 = torch.zeros(16, device=dev)
+ms = timeit(lambda: e16.encode_score(x, _lib.SCORE_POINCARE, center=c16, want_latent=False))
+print(f'STSE D=16 poincare score: {ms:.2f} ms -> {B/ms*1e3/1e6:.2f} M windows/s')
