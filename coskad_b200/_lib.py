@@ -36,6 +36,8 @@ SIGNATURES = {
     'coskad_set_encoder': (C.c_int, [c_ctx_p, C.c_int, C.POINTER(LayerParams), c_float_p, c_float_p, C.c_int, C.c_void_p]),
     'coskad_set_decoder': (C.c_int, [c_ctx_p, c_float_p, c_float_p, C.c_int, C.c_int, C.POINTER(LayerParams), C.c_void_p]),
     'coskad_encode_score_fwd': (C.c_int, [c_ctx_p, C.c_int, c_float_p, c_float_p, C.c_int64, c_float_p, c_float_p, C.c_void_p]),
+    'coskad_encode_score_traj_fwd': (C.c_int, [c_ctx_p, C.c_int, c_float_p, C.c_int64, C.c_void_p, C.c_void_p, c_float_p, C.c_int,
+                                               c_float_p, C.c_int64, c_float_p, c_float_p, C.c_void_p]),
     'coskad_set_fused_impl': (C.c_int, [c_ctx_p, C.c_int]),
     'coskad_autoencode_score_fwd': (C.c_int, [c_ctx_p, c_float_p, c_float_p, C.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, C.c_void_p]),
     'coskad_geom_map': (C.c_int, [c_ctx_p, C.c_int, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),

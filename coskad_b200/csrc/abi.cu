@@ -257,11 +257,10 @@ static int fused_grid(const coskad_ctx* ctx, int64_t B) {
   return static_cast<int>(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);   // persistent: one CTA per SM
 }
 
-extern "C" int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float* x, const float* center, int64_t B,
-                                       float* z, float* score, void* stream_) {
-  if (!ctx) return COSKAD_ERR_ARG;
+static int launch_encode_score(coskad_ctx* ctx, int flavour, const float* x, const float* traj, int64_t traj_rows,
+                               const int64_t* win_row, const int32_t* trans, const float* mats, int n_mats,
+                               const float* center, int64_t B, float* z, float* score, void* stream_) {
   if (!ctx->enc_set) return fail(ctx, COSKAD_ERR_STATE, "coskad_set_encoder has not been called");
-  if (B < 0 || (B > 0 && !x)) return fail(ctx, COSKAD_ERR_ARG, "bad x/B");
   if (flavour < COSKAD_SCORE_NONE || flavour > COSKAD_SCORE_POINCARE_HM) return fail(ctx, COSKAD_ERR_ARG, "unknown flavour %d", flavour);
   if (flavour != COSKAD_SCORE_NONE && (!score || !center)) return fail(ctx, COSKAD_ERR_ARG, "score/center is NULL for flavour %d", flavour);
   if (B == 0) return COSKAD_OK;
@@ -274,15 +273,34 @@ extern "C" int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float
   p.B = B; p.head_rows = ctx->head_rows; p.flavour = flavour;
   // the VAE head stacks fc_var under fc_mean: the geometry sees only the latent rows
   p.D = (ctx->head_rows == 9) ? 8 : ctx->head_rows;
-  if (ctx->fused_impl == 1) {
+  if (ctx->fused_impl == 1 || traj != nullptr) {
     FusedTcParams t = ctx->tp;
     t.x = x; t.center = center; t.z = z; t.score = p.score; t.B = B; t.head_rows = p.head_rows; t.D = p.D; t.flavour = flavour;
+    t.traj = traj; t.win_row = win_row; t.traj_rows = traj_rows; t.trans = trans; t.mats = mats; t.n_mats = n_mats;
     fused_eval_tc_kernel<<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
   } else {
     fused_eval_kernel<false><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
   }
   CK_LAUNCH();
   return COSKAD_OK;
+}
+
+extern "C" int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float* x, const float* center, int64_t B,
+                                       float* z, float* score, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (B < 0 || (B > 0 && !x)) return fail(ctx, COSKAD_ERR_ARG, "bad x/B");
+  return launch_encode_score(ctx, flavour, x, nullptr, 0, nullptr, nullptr, nullptr, 0, center, B, z, score, stream_);
+}
+
+extern "C" int coskad_encode_score_traj_fwd(coskad_ctx* ctx, int flavour, const float* traj, int64_t traj_rows,
+                                            const int64_t* win_row, const int32_t* trans, const float* mats, int n_mats,
+                                            const float* center, int64_t N, float* z, float* score, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (N < 0 || (N > 0 && (!traj || !win_row))) return fail(ctx, COSKAD_ERR_ARG, "bad traj/win_row/N");
+  if (N > 0 && traj_rows < kT) return fail(ctx, COSKAD_ERR_ARG, "traj_rows (%lld) is shorter than one window (%d frames)",
+                                           static_cast<long long>(traj_rows), kT);
+  if (trans != nullptr && (!mats || n_mats < 1)) return fail(ctx, COSKAD_ERR_ARG, "trans given without transformation matrices");
+  return launch_encode_score(ctx, flavour, nullptr, traj, traj_rows, win_row, trans, mats, n_mats, center, N, z, score, stream_);
 }
 
 extern "C" int coskad_set_fused_impl(coskad_ctx* ctx, int impl) {

@@ -51,6 +51,13 @@ struct FusedTcParams {
   float* score;
   int64_t B;
   int head_rows, D, flavour;
+  // optional front end (coskad_encode_score_traj_fwd): windows gathered from trajectory rows + test-time affine transform
+  const float* traj;          // [traj_rows, 2*kV] (x0,y0,x1,y1,.. per frame), nullptr = windows come from x
+  const int64_t* win_row;     // [B] first trajectory row of window i
+  int64_t traj_rows;
+  const int* trans;           // [B] index into mats, nullptr = no transform
+  const float* mats;          // [n_mats][6]: x' = m0 x + m1 y + m2, y' = m3 x + m4 y + m5
+  int n_mats;
 };
 
 constexpr int kTcGB = (kRSmall + 3) & ~3;                             // keep what follows 16-byte aligned (cp.async 16, UMMA descriptors)
@@ -300,11 +307,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 
   auto load_x = [&](float* dst, int64_t tile) {
     const int64_t w0 = tile * kNW;
-    for (int i = tid; i < kNW * 2 * kP; i += kTcThreads) {
-      const int r = i / kP, p = i - r * kP;
-      int64_t w = w0 + (r >> 1);
+    if (Pm.traj == nullptr) {
+      for (int i = tid; i < kNW * 2 * kP; i += kTcThreads) {
+        const int r = i / kP, p = i - r * kP;
+        int64_t w = w0 + (r >> 1);
+        if (w >= Pm.B) w = Pm.B - 1;
+        cp_async4(dst + r * kCS + p, Pm.x + w * (2 * kP) + (r & 1) * kP + p);
+      }
+    } else {
+      // window = kT consecutive trajectory rows of 2*kV interleaved coordinates: 408 contiguous floats in (t, v, c) order,
+      // de-interleaved into the two channel planes (the sliding windows are never materialised in HBM)
+      for (int i = tid; i < kNW * 2 * kP; i += kTcThreads) {
+        const int n = i / (2 * kP), e = i - n * (2 * kP);      // e = p*2 + c
+        int64_t w = w0 + n;
+        if (w >= Pm.B) w = Pm.B - 1;
+        int64_t row = Pm.win_row[w];
+        row = row < 0 ? 0 : (row > Pm.traj_rows - kT ? Pm.traj_rows - kT : row);
+        cp_async4(dst + (n * 2 + (e & 1)) * kCS + (e >> 1), Pm.traj + row * (2 * kV) + e);
+      }
+    }
+  };
+  // test-time affine transform of a landed input tile, in place (utils/dataset_utils.py:270-284 apply_pose_transform)
+  auto transform_x = [&](float* buf, int64_t tile, int t0, int nthreads) {
+    if (Pm.trans == nullptr) return;
+    for (int i = t0; i < kNW * kP; i += nthreads) {
+      const int n = i / kP, p = i - n * kP;
+      int64_t w = tile * kNW + n;
       if (w >= Pm.B) w = Pm.B - 1;
-      cp_async4(dst + r * kCS + p, Pm.x + w * (2 * kP) + (r & 1) * kP + p);
+      int ti = Pm.trans[w];
+      ti = ti < 0 ? 0 : (ti >= Pm.n_mats ? Pm.n_mats - 1 : ti);
+      const float* m = Pm.mats + ti * 6;
+      const float x = buf[(n * 2) * kCS + p], y = buf[(n * 2 + 1) * kCS + p];
+      buf[(n * 2) * kCS + p] = fmaf(__ldg(m + 0), x, fmaf(__ldg(m + 1), y, __ldg(m + 2)));
+      buf[(n * 2 + 1) * kCS + p] = fmaf(__ldg(m + 3), x, fmaf(__ldg(m + 4), y, __ldg(m + 5)));
     }
   };
   auto acopy = [&](float* dst, const float* src, int nfloats) {
@@ -378,6 +413,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   //      three warps of TMEM lane quarter 3 during the head stage, where they have half the work of the other quarters
   //      (positions 224..255 do not exist): see the end of stage S11.
   boundary();
+  if (Pm.trans != nullptr) { transform_x(XB, blockIdx.x, tid, kTcThreads); __syncthreads(); }
   temporal_stage_l1<kTcWarps>(XB, GB, TB, warp, lane);
   boundary();
   spatial_stage_l1<kTcWarps>(GB, AB, warp, lane);
@@ -608,6 +644,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       for (int i = t96 * 4; i < kAwFloats; i += 96 * 4) cp_async16(AB + i, Pm.eAw[0] + i);
       cp_async_commit();
       float* Xn = XB + (cur ^ 1) * kRSmall;
+      if (Pm.trans != nullptr) { transform_x(Xn, next_tile, t96, 96); asm volatile("bar.sync 4, 96;" ::: "memory"); }
       temporal_stage_l1<3>(Xn, GB, TB, gg, lane);
       cp_async_wait_all();
       asm volatile("bar.sync 4, 96;" ::: "memory");

@@ -250,6 +250,48 @@ class STSE(nn.Module):
         return Z, score
 
 
+    @torch.no_grad()
+    def encode_score_traj(self, traj: torch.Tensor, win_row: torch.Tensor, trans: Optional[torch.Tensor] = None,
+                          mats: Optional[torch.Tensor] = None, flavour: int = _lib.SCORE_NONE,
+                          center: Optional[torch.Tensor] = None, want_latent: bool = True
+                          ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Fused eval hot path fed from trajectories: window construction (utils/preprocessing.py:58-89) and the
+        test-time affine transforms (utils/dataset.py:65-74, utils/dataset_utils.py:255-310) happen inside the kernel.
+
+        ``traj`` [rows, 2*V] float32 (x0,y0,x1,y1,.. per frame: the reference's scaled ``trajectory.coordinates`` rows,
+        persons concatenated); window i = the ``n_frames`` consecutive rows from ``win_row[i]``; ``trans`` [N] indexes
+        ``mats`` [n_mats, 2, 3] (rows 0,1 of the affine matrices).  Returns (Z, score) like :meth:`encode_score`."""
+        if traj.dim() != 2 or traj.shape[1] != 2 * self.n_joints or not traj.is_cuda:
+            raise ValueError(f'traj must be a CUDA tensor [rows, {2 * self.n_joints}], got {tuple(traj.shape)} on {traj.device}')
+        traj = traj.to(torch.float32).contiguous()
+        win_row = win_row.to(device=traj.device, dtype=torch.int64).contiguous()
+        N = win_row.numel()
+        if (trans is None) != (mats is None):
+            raise ValueError('trans and mats must be given together')
+        n_mats = 0
+        if trans is not None:
+            trans = trans.to(device=traj.device, dtype=torch.int32).contiguous()
+            mats = mats.to(device=traj.device, dtype=torch.float32).reshape(-1, 6).contiguous()
+            n_mats = mats.shape[0]
+            if trans.numel() != N:
+                raise ValueError('trans must have one entry per window')
+        if not any(p.is_cuda for p in self.parameters()):
+            raise _lib.CoskadError('the model must live on the CUDA device of traj (there is no CPU path)')
+        ctx = self._context(traj)
+        self._sync_encoder(ctx)
+        rows = self._head()[2]
+        Z = torch.empty((N, rows), device=traj.device, dtype=torch.float32) if want_latent else None
+        score = cen = None
+        if flavour != _lib.SCORE_NONE:
+            cen = (self.c if center is None else center).to(device=traj.device, dtype=torch.float32).contiguous().view(-1)
+            score = torch.empty((N,), device=traj.device, dtype=torch.float32)
+        rc = ctx.lib.coskad_encode_score_traj_fwd(ctx.h, int(flavour), traj.data_ptr(), traj.shape[0], win_row.data_ptr(),
+                                                  _lib._ptr(trans), _lib._ptr(mats), n_mats, _lib._ptr(cen), N,
+                                                  _lib._ptr(Z), _lib._ptr(score), _lib.stream_ptr(traj.device))
+        ctx.check(rc, 'coskad_encode_score_traj_fwd')
+        return Z, score
+
+
 class STSAE(STSE):
     """models/sts/ae.py:168-264 -- encoder + rev_btlnk + STS-GCN decoder; forward returns (Z, X_hat)."""
 

@@ -101,6 +101,20 @@ int coskad_set_decoder(coskad_ctx* ctx, const float* rev_w /*[F, latent]*/, cons
  * replaces: STSE.forward models/sts/ae.py:108-121 (+ the per-person scoring in eval_COSKAD.py:186-199) */
 int coskad_encode_score_fwd(coskad_ctx* ctx, int flavour, const float* x, const float* center,
                             int64_t B, float* z, float* score, void* stream);
+/* Same path fed from TRAJECTORIES: window construction and the test-time affine transforms happen on the device, in the
+ * kernel's input stage, so the 12x (stride-1 sliding windows) x n_transform redundant window tensor is never materialised.
+ *   traj [traj_rows, 2*V] float32: the reference's per-person coordinate rows (x0,y0,x1,y1,.. per frame, after scaling;
+ *        trajectory.coordinates), any number of persons concatenated;
+ *   win_row [N] int64: window i = the 12 consecutive rows starting at win_row[i] (x[c][t][v] = traj[win_row[i]+t][2v+c]),
+ *        clamped to [0, traj_rows-12];
+ *   trans [N] int32 (nullable) indexes mats [n_mats][6] = rows 0,1 of the 3x3 affine matrices (get_aff_trans_mat):
+ *        x' = m0 x + m1 y + m2,  y' = m3 x + m4 y + m5.
+ * replaces: the window materialisation utils/preprocessing.py:58-89 (_aggregate_rnn_autoencoder_data) and
+ * PoseDatasetRobust.__getitem__ utils/dataset.py:65-74 -> apply_pose_transform utils/dataset_utils.py:270-284,
+ * feeding STSE.forward models/sts/ae.py:108-121 */
+int coskad_encode_score_traj_fwd(coskad_ctx* ctx, int flavour, const float* traj, int64_t traj_rows,
+                                 const int64_t* win_row, const int32_t* trans, const float* mats /*[n_mats,6]*/, int n_mats,
+                                 const float* center, int64_t N, float* z, float* score, void* stream);
 /* Kernel generation used by coskad_encode_score_fwd: 1 (default) = channel mixing on tcgen05 tensor cores (3xTF32),
  * 0 = the all-FP32 CUDA-core kernel (kept for A/B measurement and as the decoder path). */
 int coskad_set_fused_impl(coskad_ctx* ctx, int impl);

@@ -177,6 +177,27 @@ def main() -> None:
     np.savez(os.path.join(GOLD, 'aggregate_ref.npz'), scores=scores, trans=trans, meta=meta, frames=frames,
              clips=np.asarray(clips, dtype=np.int64), curves=np.concatenate(ref_curves),
              pad_in=fr, pad_out=ref_eu.pad_scores(fr.copy(), np.zeros(20), 2))
+    # ---- window construction + test-time transforms (utils/dataset_utils.py, utils/preprocessing.py, utils/dataset.py) ----
+    from oracle import windows as owin
+    import utils.dataset_utils as ref_du      # noqa: E402  (reference)
+    import utils.preprocessing as ref_pp      # noqa: E402
+    ref_mats = np.stack([t.trans_mat.numpy() for t in ref_du.ae_trans_list], 0)
+    assert np.array_equal(ref_mats, owin.ae_trans_mats()), 'oracle.windows affine matrices differ from ae_trans_list'
+    rng = np.random.default_rng(5)
+    traj = (rng.standard_normal((40, 34)) * 0.4).astype(np.float32)
+    traj[rng.random((40, 17)).repeat(2, 1) < 0.05] = 0.0                     # missing joints stay (0, 0)
+    Xw, _ = ref_pp._aggregate_rnn_autoencoder_data(traj, input_length=12, input_gap=0, pred_length=0)
+    starts = owin.sliding_starts(traj.shape[0], 12, 1)
+    assert Xw.shape[0] == len(starts)
+    # PoseDatasetRobust.gen_dataset (utils/dataset.py:253-273): reshape (N,T,17,2), conf channel 1.0, transpose to (N,C,T,V)
+    segs = np.empty((*Xw.shape[:2], 17, 3)); segs[..., :2] = Xw.reshape(*Xw.shape[:2], 17, 2); segs[..., 2] = 1.0
+    segs = np.transpose(segs, (0, 3, 1, 2)).astype(np.float32)
+    assert np.array_equal(segs[:, :2], owin.windows_from_rows(traj, starts)), 'oracle.windows window layout differs'
+    ref_tr = np.stack([np.stack([t(np.array(w)) for w in segs], 0) for t in ref_du.ae_trans_list], 0)    # [5, N, 3, 12, 17]
+    or_tr = np.stack([np.stack([owin.apply_pose_transform(w, m) for w in segs], 0) for m in owin.ae_trans_mats()], 0)
+    assert np.array_equal(ref_tr, or_tr), 'oracle.windows apply_pose_transform differs from the reference'
+    np.savez(os.path.join(GOLD, 'windows_ref.npz'), traj=traj, starts=starts, mats=ref_mats, windows=segs[:, :2],
+             transformed=ref_tr[:, :, :2].astype(np.float32))
     print('golden fixtures written to', GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print('  ', fn, os.path.getsize(os.path.join(GOLD, fn)), 'bytes')

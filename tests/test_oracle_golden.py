@@ -144,3 +144,20 @@ def test_power_spherical_restatement_properties():
     h = ops.ps_entropy(k, 8)
     assert bool((h[1:] < h[:-1]).all()) and abs(float(h[0]) - ops.hu_entropy(8)) < 1e-3
     assert bool((ops.kl_ps_uniform(k, 8) >= -1e-6).all())
+
+
+def test_windows_oracle_matches_reference_vectors(golden_dir):
+    """window construction + test-time transforms vs outputs of the reference's own utils.preprocessing /
+    utils.dataset_utils (fixture written by oracle/gen_golden.py)"""
+    from oracle import windows as owin
+    g = _load(golden_dir, 'windows_ref.npz')
+    assert np.array_equal(owin.ae_trans_mats(), g['mats'])
+    assert np.array_equal(owin.sliding_starts(g['traj'].shape[0], 12, 1), g['starts'])
+    w = owin.windows_from_rows(g['traj'], g['starts'])
+    assert np.array_equal(w, g['windows'])
+    for t, m in enumerate(g['mats']):
+        tr = np.stack([owin.apply_pose_transform(x, m) for x in w], 0).astype(np.float32)
+        assert np.array_equal(tr, g['transformed'][t])
+    # identity transform first, x-flip second (utils/dataset_utils.py:304-306)
+    assert np.array_equal(g['transformed'][0], w)
+    assert np.array_equal(g['transformed'][1][:, 0], -w[:, 0]) and np.array_equal(g['transformed'][1][:, 1], w[:, 1])
