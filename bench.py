@@ -217,6 +217,7 @@ def run_ours(args):
 
     # ---- e2e through the public host API: pinned host windows -> scores on the host ----------------
     e2e = None
+    e2e_traj = None
     if not args.no_e2e:
         hs = HostScorer(model, _lib.SCORE_POINCARE, chunk=131072, device=local)
         xh = torch.empty((W, 2, 12, 17), dtype=torch.float32).pin_memory()
@@ -241,6 +242,43 @@ def run_ours(args):
                'steps': n_e2e, 'note': 'HostScorer: pinned host chunk -> H2D (copy stream) -> fused kernel -> D2H scores'}
         if rank == 0 and not bool(torch.isfinite(oh).all()):
             raise SystemExit('non-finite scores in the e2e pass')
+        # ---- the same W windows scored from host TRAJECTORIES (window construction + 5 test-time transforms in-kernel)
+        from coskad_b200.pipeline import TrajectoryScorer
+        n_tr, plen = 5, 300                                    # num_transform of the UBnormal configs; frames per person
+        per_person = plen - 12 + 1
+        persons = max(1, W // (n_tr * per_person))
+        base = torch.arange(per_person, dtype=torch.int64).repeat(persons) + \
+            torch.arange(persons, dtype=torch.int64).repeat_interleave(per_person) * plen
+        rows_h = base.repeat(n_tr).pin_memory()
+        trans_h = torch.arange(n_tr, dtype=torch.int32).repeat_interleave(base.numel()).pin_memory()
+        traj_h = torch.empty((persons * plen, 34), dtype=torch.float32).pin_memory()
+        traj_h.copy_(x[: (persons * plen * 34 + 407) // 408].reshape(-1)[: persons * plen * 34].view(-1, 34))
+        import math as _m
+        c45 = _m.cos(_m.radians(45.0))
+        mats = torch.tensor([[[1, 0, 0], [0, 1, 0]], [[-1, 0, 0], [0, 1, 0]], [[0, -1, 0], [1, 0, 0]],
+                             [[0, 1, 0], [1, 0, 0]], [[c45, -c45, 0], [c45, c45, 0]]], dtype=torch.float32)
+        ts = TrajectoryScorer(model, _lib.SCORE_POINCARE, device=local)
+        oh2 = torch.empty(rows_h.numel(), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            ts.score(traj_h, rows_h, trans_h, mats, oh2, center=center)
+        barrier()
+        ts.h2d_bytes = ts.d2h_bytes = 0
+        e0.record()
+        for _ in range(n_e2e):
+            ts.score(traj_h, rows_h, trans_h, mats, oh2, center=center)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_traj = {'value': rows_h.numel() * world * n_e2e / (float(t.item()) * 1e-3), 'unit': 'windows/s',
+                    'h2d_bytes_per_step': ts.h2d_bytes // n_e2e, 'd2h_bytes_per_step': ts.d2h_bytes // n_e2e,
+                    'windows_per_step_per_gpu': rows_h.numel(), 'steps': n_e2e,
+                    'note': 'TrajectoryScorer: pinned host trajectory rows [frames, 34] + window start rows + transform ids -> '
+                            'H2D -> fused kernel builds the stride-1 windows and applies the 5 test-time affine transforms '
+                            'in its input stage -> D2H scores'}
+        if rank == 0 and not bool(torch.isfinite(oh2).all()):
+            raise SystemExit('non-finite scores in the trajectory e2e pass')
 
     if rank != 0:
         if world > 1:
@@ -296,7 +334,7 @@ def run_ours(args):
                    'windows_per_step_per_gpu': W, 'resident_windows_per_gpu': nchunks * W,
                    'l2_policy': 'inputs larger than L2: each step reads a distinct 1.7 GB chunk',
                    'parallelism': f'window-sharded x{world}' + (', NCCL all-gather of scores per step' if world > 1 else '')},
-        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'roofline_hbm': roofline_hbm,
+        'e2e': e2e, 'e2e_traj': e2e_traj, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'roofline_hbm': roofline_hbm,
         'cpu_baseline': cpu_baseline,
     }
     print(json.dumps(line))

@@ -71,3 +71,42 @@ class HostScorer:
 def score_windows_host(model, x_host: torch.Tensor, flavour: int = _lib.SCORE_POINCARE, chunk: int = 131072,
                        center: Optional[torch.Tensor] = None) -> torch.Tensor:
     return HostScorer(model, flavour, chunk).score(x_host, center=center)
+
+
+class TrajectoryScorer:
+    """Host trajectories in, anomaly scores out, through the trajectory front end of the fused kernel.
+
+    What eval_COSKAD.py:107-120 does with ``get_dataset_and_loader`` (sliding windows materialised on the host, one copy
+    per test-time transform) + ``predict``: here only the scaled trajectory rows (136 B per frame) and two index arrays
+    cross PCIe -- with stride-1 windows and ``num_transform`` = 5 that is ~40x fewer bytes than the window tensor -- and
+    the windows are assembled and transformed inside the kernel's input stage (``coskad_encode_score_traj_fwd``)."""
+
+    def __init__(self, model, flavour: int = _lib.SCORE_POINCARE, device: Optional[int] = None):
+        self.model, self.flavour = model, flavour
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    @torch.no_grad()
+    def score(self, traj_host: torch.Tensor, win_row_host: torch.Tensor, trans_host: Optional[torch.Tensor] = None,
+              mats: Optional[torch.Tensor] = None, out_host: Optional[torch.Tensor] = None,
+              center: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """traj_host [rows, 2V] f32, win_row_host [N] i64, trans_host [N] i32 (optional, with mats [n,2,3]) -> scores [N]"""
+        assert not traj_host.is_cuda and traj_host.dtype == torch.float32 and traj_host.is_contiguous()
+        N = win_row_host.numel()
+        if out_host is None:
+            out_host = torch.empty(N, dtype=torch.float32).pin_memory()
+        comp = torch.cuda.current_stream(self.device)
+        traj = traj_host.to(self.device, non_blocking=True)
+        rows = win_row_host.to(self.device, non_blocking=True)
+        self.h2d_bytes += traj_host.numel() * 4 + N * 8
+        tr = mt = None
+        if trans_host is not None:
+            tr = trans_host.to(torch.int32).to(self.device, non_blocking=True)
+            mt = mats.to(self.device, dtype=torch.float32)
+            self.h2d_bytes += N * 4 + mt.numel() * 4
+        _, s = self.model.encode_score_traj(traj, rows, tr, mt, flavour=self.flavour, center=center, want_latent=False)
+        out_host.copy_(s, non_blocking=True)
+        self.d2h_bytes += N * 4
+        comp.synchronize()
+        return out_host
