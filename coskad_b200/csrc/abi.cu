@@ -247,7 +247,8 @@ static int ensure_smem_attr(coskad_ctx* ctx) {
   if (ctx->smem_attr_set) return COSKAD_OK;
   CK(cudaFuncSetAttribute(fused_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   CK(cudaFuncSetAttribute(fused_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  CK(cudaFuncSetAttribute(fused_eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   ctx->smem_attr_set = true;
   return COSKAD_OK;
 }
@@ -277,7 +278,7 @@ static int launch_encode_score(coskad_ctx* ctx, int flavour, const float* x, con
     FusedTcParams t = ctx->tp;
     t.x = x; t.center = center; t.z = z; t.score = p.score; t.B = B; t.head_rows = p.head_rows; t.D = p.D; t.flavour = flavour;
     t.traj = traj; t.win_row = win_row; t.traj_rows = traj_rows; t.trans = trans; t.mats = mats; t.n_mats = n_mats;
-    fused_eval_tc_kernel<<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
+    fused_eval_tc_kernel<false><<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
   } else {
     fused_eval_kernel<false><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
   }
@@ -324,7 +325,17 @@ extern "C" int coskad_autoencode_score_fwd(coskad_ctx* ctx, const float* x, cons
   FusedParams p = ctx->fp;
   p.x = x; p.center = center; p.z = z; p.score = lat_score; p.xhat = xhat; p.rec_score = rec_score;
   p.B = B; p.head_rows = ctx->head_rows; p.D = ctx->head_rows; p.flavour = COSKAD_SCORE_EUCLID;
-  fused_eval_kernel<true><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  if (ctx->fused_impl == 1) {
+    // tensor-core encoder + FP32 decoder stages in one kernel
+    FusedTcParams t = ctx->tp;
+    t.x = x; t.center = center; t.z = z; t.score = lat_score; t.B = B; t.head_rows = p.head_rows; t.D = p.D; t.flavour = p.flavour;
+    t.dM = p.dM; t.dm0 = p.dm0; t.d_slope0 = p.d_slope0; t.DL = p.DL;
+    for (int i = 0; i < 3; ++i) { t.dTw[i] = p.dTw[i]; t.dAw[i] = p.dAw[i]; t.dWm[i] = p.dWm[i]; }
+    t.xhat = xhat; t.rec_score = rec_score;
+    fused_eval_tc_kernel<true><<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
+  } else {
+    fused_eval_kernel<true><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
+  }
   CK_LAUNCH();
   return COSKAD_OK;
 }

@@ -58,13 +58,23 @@ struct FusedTcParams {
   const int* trans;           // [B] index into mats, nullptr = no transform
   const float* mats;          // [n_mats][6]: x' = m0 x + m1 y + m2, y' = m3 x + m4 y + m5
   int n_mats;
+  // decoder (fused_eval_tc_kernel<true>, auto-encoder): same blobs as FusedParams (fused_eval.cuh)
+  const float* dM;            // [32*204][DL] folded rev_btlnk + first decoder layer
+  const float* dm0;           // [32*204]
+  float d_slope0;
+  int DL;
+  const float* dTw[3];
+  const float* dAw[3];
+  const float* dWm[3];
+  float* xhat;                // [B,2,12,17] or null
+  float* rec_score;           // [B] or null
 };
 
 constexpr int kTcGB = (kRSmall + 3) & ~3;                             // keep what follows 16-byte aligned (cp.async 16, UMMA descriptors)
 static_assert((2 * kRBig + 2 * kRSmall + kTcGB) % 4 == 0, "weight staging buffers must be 16-byte aligned");
 constexpr int kTcSmemFloats = 2 * kRBig + 2 * kRSmall + kTcGB        // R0, R1, XB[2], GB
                               + kTwFloats + kAwFloats + kTcWsFloats + kTcWbFloats
-                              + 2 * kTcWarps * kNW * kDP + 32           // zpart[2], center
+                              + 2 * kTcWarps * kNW * kDP + kNW * kDP + 32   // zpart[2], zfin, center
                               + 32;                                     // mbarriers (11 x 8 B) + tmem base
 constexpr int kTcSmemBytes = kTcSmemFloats * 4;
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
@@ -285,6 +295,7 @@ __device__ __forceinline__ void sm_epilogue(const SmallPipe& P, int g, int q, in
   tc::fence_before_sync();
 }
 
+template <bool kDec>
 __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __grid_constant__ FusedTcParams Pm) {
   extern __shared__ __align__(128) float smem_tc[];
   float* R0 = smem_tc;
@@ -296,7 +307,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   float* WMs = AB + kAwFloats;
   float* WMb = WMs + kTcWsFloats;
   float* zpart = WMb + kTcWbFloats;
-  float* cen = zpart + 2 * kTcWarps * kNW * kDP;
+  float* zfin = zpart + 2 * kTcWarps * kNW * kDP;        // decoder variant: latents of the tile
+  float* cen = zfin + kNW * kDP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(cen + 32);     // full[2], empty[2], done, small-phase done[6]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);   // bars[11]: layer-4 graph half, j = 0 tiles complete
   int* task_ctr = reinterpret_cast<int*>(tmem_slot + 1);          // dynamic task hand-out of the layer-4 temporal stage
@@ -392,7 +404,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     const int n = warp - (kTcWarps - kNW);
     if (n < 0) return;
     const int64_t w = ftile * kNW + n;
-    if (w >= Pm.B) return;
+    if (w >= Pm.B) {                                   // ragged last tile: the decoder still runs on a finite dummy latent
+      if (kDec && lane < kDP) zfin[n * kDP + lane] = 0.f;
+      return;
+    }
     float s = 0.f;
     if (lane < kDP) {
       s = __ldg(Pm.head_b + lane);
@@ -400,6 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       for (int ww = 0; ww < kTcWarps; ++ww) s += zpart[(buf * kTcWarps + ww) * (kNW * kDP) + n * kDP + lane];
     }
     float u[1] = {s};
+    if (kDec && lane < kDP) zfin[n * kDP + lane] = s;
     if (Pm.z != nullptr && lane < Pm.head_rows) Pm.z[w * Pm.head_rows + lane] = u[0];
     if (Pm.score != nullptr) {
       if (lane >= Pm.D) u[0] = 0.f;
@@ -431,7 +447,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     acopy(TB, Pm.eTw[1], kTwFloats);
     if (next_tile < ntiles) load_x(XB + (cur ^ 1) * kRSmall, next_tile);
     cp_async_commit();
-    if (last_tile >= 0) finalize(last_tile, cur ^ 1);
+    if (!kDec && last_tile >= 0) finalize(last_tile, cur ^ 1);
     last_tile = tile;
     float* U2 = R1;
     float* Rsd2 = R1 + kNW * kC2 * kCS;
@@ -533,7 +549,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     // ---- S9: L4 residual half issued first (inputs H3 = R0): runs on the tensor cores while the CUDA cores do the
     //          layer-4 graph contraction below;  L4 temporal: H3 (R0) -> G4 (R1)
     boundary();
-    acopy(WMs, Pm.mixL1, mix_blob_floats(4, 32));
+    if (!kDec) acopy(WMs, Pm.mixL1, mix_blob_floats(4, 32));      // (the decoder needs WMs; it reloads the blob at S21)
     cp_async_commit();
     // (the producer warps take a temporal task after each staged tile instead of blocking on the A-buffer hand-off)
     tc_mix_phase<kC3, 0, kC4>(pipe, R0, nullptr, WMb, WMb + 32 * 64, false, warp, lane, [&]() {
@@ -640,7 +656,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     //      since S10: stage the layer-1 A.  TB already holds the layer-1 T (loaded during S10).
     if (gq == 3 && next_tile < ntiles) {
       const int t96 = gg * 32 + lane;
-      for (int i = t96 * 4; i < tc_blob_floats(32, 32); i += 96 * 4) cp_async16(WMb + i, Pm.tcL2 + i);
+      if (!kDec) for (int i = t96 * 4; i < tc_blob_floats(32, 32); i += 96 * 4) cp_async16(WMb + i, Pm.tcL2 + i);
       for (int i = t96 * 4; i < kAwFloats; i += 96 * 4) cp_async16(AB + i, Pm.eAw[0] + i);
       cp_async_commit();
       float* Xn = XB + (cur ^ 1) * kRSmall;
@@ -650,11 +666,124 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       asm volatile("bar.sync 4, 96;" ::: "memory");
       spatial_stage_l1<3>(GB, AB, gg, lane);
     }
+
+    if constexpr (kDec) {
+      // ================= decoder (models/sts/ae.py:210-230, models/common/components.py:168-179) on the FP32 pipe ==========
+      // ---- S12: latents of this tile (the decoder consumes them), stage weights of the first decoder layers
+      boundary();
+      acopy(TB, Pm.dTw[0], kTwFloats);
+      acopy(AB, Pm.dAw[0], kAwFloats);
+      acopy(WMs, Pm.dWm[0], mix_blob_floats(32, 32));
+      acopy(WMb, Pm.dWm[1], mix_blob_floats(32, 32));
+      cp_async_commit();
+      finalize(tile, cur);
+      __syncthreads();
+      // ---- S13: folded first decoder layer: H = PReLU(M z + m0) -> R0 (32 ch)
+      //      (rev_btlnk models/sts/ae.py:222 + decoder layer 0 linear part, collapsed at set_decoder)
+      {
+        const int DL = Pm.DL;
+        for (int i = tid; i < kC1 * kP; i += kTcThreads) {
+          const int co = i / kP, p = i - co * kP;
+          const float m0 = __ldg(Pm.dm0 + i);
+          float o[kNW];
+#pragma unroll
+          for (int n = 0; n < kNW; ++n) o[n] = m0;
+          const float4* m4 = reinterpret_cast<const float4*>(Pm.dM + static_cast<size_t>(i) * DL);
+          for (int d4 = 0; d4 < DL / 4; ++d4) {
+            const float4 m = __ldg(m4 + d4);
+#pragma unroll
+            for (int n = 0; n < kNW; ++n) {
+              const float* zz = zfin + n * kDP + d4 * 4;
+              o[n] = fmaf(m.x, zz[0], o[n]);
+              o[n] = fmaf(m.y, zz[1], o[n]);
+              o[n] = fmaf(m.z, zz[2], o[n]);
+              o[n] = fmaf(m.w, zz[3], o[n]);
+            }
+          }
+#pragma unroll
+          for (int n = 0; n < kNW; ++n) R0[(n * kC1 + co) * kCS + p] = prelu(o[n], Pm.d_slope0);
+        }
+      }
+      // ---- S14: D2 (32->16) mix-first: R0 -> U (R1 rows 0..47), Rsd (rows 48..95)
+      boundary();
+      float* Ud = R1;
+      float* Rsdd = R1 + kNW * kC2 * kCS;
+      const float dslope1 = WMs[kC1 * 2 * kC2 + 2 * kC2];
+      {
+        EpiSplit<kC2> epi{Ud, Rsdd, WMs + kC1 * 2 * kC2};
+        mix_stage<kC1, 0, 2 * kC2, 16, EpiSplit<kC2>, kTcWarps>(R0, nullptr, WMs, epi, warp, lane);
+      }
+      // ---- S15: D2 temporal in place
+      boundary();
+      acopy(WMs, Pm.dWm[2], mix_blob_floats(32, 4));
+      cp_async_commit();
+      temporal_stage_c16<kTcWarps>(Ud, Ud, TB, warp, lane);
+      // ---- S16: D2 spatial + residual + PReLU -> R1 rows 0..47
+      boundary();
+      acopy(TB, Pm.dTw[1], kTwFloats);
+      cp_async_commit();
+      spatial_stage_c16<EpiAddResPrelu, kTcWarps>(Ud, AB, EpiAddResPrelu{Rsdd, dslope1}, warp, lane);
+      // ---- S17: D3 (16->32) temporal: R1 rows 0..47 -> rows 48..95
+      boundary();
+      acopy(AB, Pm.dAw[1], kAwFloats);
+      cp_async_commit();
+      temporal_stage_c16<kTcWarps>(R1, R1 + kNW * kC2 * kCS, TB, warp, lane);
+      // ---- S18: D3 spatial in place
+      boundary();
+      acopy(TB, Pm.dTw[2], kTwFloats);
+      cp_async_commit();
+      spatial_stage_c16<EpiIdentity, kTcWarps>(R1 + kNW * kC2 * kCS, AB, EpiIdentity{}, warp, lane);
+      // ---- S19: D3 mix -> R0 (32 ch)
+      boundary();
+      acopy(AB, Pm.dAw[2], kAwFloats);
+      cp_async_commit();
+      {
+        EpiStorePrelu<kC3> epi{R0, WMb + 2 * kC2 * kC3, WMb[2 * kC2 * kC3 + kC3]};
+        mix_stage<kC2, kC2, kC3, 16, EpiStorePrelu<kC3>, kTcWarps>(R1 + kNW * kC2 * kCS, R1, WMb, epi, warp, lane);
+      }
+      // ---- S20: D4 (32->2) mix-first: R0 -> U (R1 rows 0..5), Rsd (R1 rows 6..11); GB stays reserved for the next tile's
+      //           layer-1 output
+      boundary();
+      acopy(WMb, Pm.tcL2, tc_blob_floats(32, 32));
+      cp_async_commit();
+      float* U4 = R1;
+      float* Rsd4 = R1 + kNW * kC0 * kCS;
+      const float dslope3 = WMs[kC3 * 2 * kC0 + 2 * kC0];
+      {
+        EpiSplit<kC0> epi{U4, Rsd4, WMs + kC3 * 2 * kC0};
+        mix_stage<kC3, 0, 2 * kC0, 4, EpiSplit<kC0>, kTcWarps>(R0, nullptr, WMs, epi, warp, lane);
+      }
+      // ---- S21: D4 temporal in place
+      boundary();
+      acopy(WMs, Pm.mixL1, mix_blob_floats(4, 32));
+      cp_async_commit();
+      temporal_stage<kNW * kC0, kTcWarps>(U4, U4, TB, warp, lane);
+      // ---- S22: D4 spatial + residual + PReLU -> xhat in U4
+      boundary();
+      spatial_stage<kNW * kC0, EpiAddResPrelu, kTcWarps>(U4, AB, EpiAddResPrelu{Rsd4, dslope3}, warp, lane);
+      // ---- S23: reconstruction score mean_{c,t,v}(x - xhat)^2, optional xhat store
+      boundary();
+      if (warp < kNW) {
+        const int64_t w = tile * kNW + warp;
+        if (w < Pm.B) {
+          float s = 0.f;
+          for (int i = lane; i < 2 * kP; i += 32) {
+            const int c = i / kP, p = i - c * kP;
+            const float xh = U4[(warp * 2 + c) * kCS + p];
+            const float d = X0[(warp * 2 + c) * kCS + p] - xh;
+            s = fmaf(d, d, s);
+            if (Pm.xhat != nullptr) Pm.xhat[w * (2 * kP) + i] = xh;
+          }
+          s = warp_sum(s);
+          if (lane == 0 && Pm.rec_score != nullptr) Pm.rec_score[w] = s / static_cast<float>(2 * kP);
+        }
+      }
+    }
   }
   cp_async_wait_all();
   tc::fence_before_sync();
   __syncthreads();
-  if (last_tile >= 0) finalize(last_tile, cur ^ 1);
+  if (!kDec && last_tile >= 0) finalize(last_tile, cur ^ 1);
   if (warp == 0) tc::tmem_dealloc(pipe.tbase, 512);
 }
 

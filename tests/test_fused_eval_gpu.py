@@ -137,9 +137,12 @@ def test_autoencoder_golden(golden_dir):
     _assert_close(xh, torch.from_numpy(g['xhat']), 'AE reconstruction vs reference fixture', atol_scale=1e-4)
 
 
+@pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('B', [1, 5, 1000])
-def test_autoencoder_scores(B):
+def test_autoencoder_scores(B, impl):
+    """impl 1: tensor-core encoder + FP32 decoder stages in fused_eval_tc_kernel<true>; impl 0: the all-FP32 kernel"""
     m, sd = make_pair('stsae', 8, seed=1)
+    m.fused_impl = impl
     x = onet.synth_windows(B, seed=10 + B)
     c = torch.full((8,), 0.02)
     with torch.no_grad():
