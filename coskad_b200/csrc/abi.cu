@@ -208,6 +208,9 @@ extern "C" int coskad_set_decoder(coskad_ctx* ctx, const float* rev_w, const flo
     oA[i] = off; off += kAwFloats;
     oW[i] = off; off += align4(mix_blob_floats(K, CO));
   }
+  // tensor-core blobs of decoder layers 1 (32->16, mix-first) and 2 (16->32): same shapes as encoder layers 2 and 3
+  const size_t oTD2 = off; off += align4(tc_blob_floats(32, 32));
+  const size_t oTD3 = off; off += align4(tc_blob_floats(32, 32));
   if (!ctx->dec_pack) CK(cudaMalloc(&ctx->dec_pack, off * sizeof(float)));
   // layer 0 collapse in float64
   const int rows = (DL + 1) * kC4;
@@ -233,6 +236,12 @@ extern "C" int coskad_set_decoder(coskad_ctx* ctx, const float* rev_w, const flo
     ctx->fp.dAw[i] = ctx->dec_pack + oA[i];
     ctx->fp.dWm[i] = ctx->dec_pack + oW[i];
   }
+  fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[1], 1, 32, 32, ctx->dec_pack + oTD2);
+  CK_LAUNCH();
+  fold_layer_tc_kernel<<<8, 256, 0, st>>>(L[2], 0, 32, 32, ctx->dec_pack + oTD3);
+  CK_LAUNCH();
+  ctx->tp.tcD2 = ctx->dec_pack + oTD2;
+  ctx->tp.tcD3 = ctx->dec_pack + oTD3;
   CK(cudaStreamSynchronize(st));
   cudaFree(In); cudaFree(G1); cudaFree(G);
   ctx->fp.dM = ctx->dec_pack + oM;

@@ -15,6 +15,7 @@
 //   * layer 4 is issued in two phases: the residual half (inputs = H3, known before the graph contraction) is
 //     issued first and executes asynchronously while the CUDA cores run the layer-4 contraction.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "fused_eval.cuh"
 #include "geometry.cuh"
@@ -66,6 +67,8 @@ struct FusedTcParams {
   const float* dTw[3];
   const float* dAw[3];
   const float* dWm[3];
+  const float* tcD2;          // tensor-core blobs of decoder layers 1 (32->16 mix-first) and 2 (16->32)
+  const float* tcD3;
   float* xhat;                // [B,2,12,17] or null
   float* rec_score;           // [B] or null
 };
@@ -425,6 +428,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     }
   };
 
+  // N = 32 mixing phase from channel planes: A = [src1 (k1 channels) | src2 (32 - k1 channels)] of this group's window, staged
+  // and issued per warp group (see SmallPipe); the caller runs sm_epilogue and advances spipe.uses
+  auto small_mix = [&](const float* src1, auto k1c, const float* src2, const float* blob) {
+    constexpr int k1 = decltype(k1c)::value;
+    const int n = gg;
+    const uint32_t lane_base = spipe.tbase + (static_cast<uint32_t>(gq * 32) << 16);
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      if (jj == 0 || gq < 3) {
+        const int p = jj * 128 + gq * 32 + lane;
+        const int pc = p < kP ? p : kP - 1;
+        float a[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          a[k] = (k < k1) ? src1[(n * k1 + k) * kCS + pc] : src2[(n * (32 - k1) + (k - k1)) * kCS + pc];
+        sm_store_a(lane_base + sm_col_a(gg, jj), a);
+      }
+      sm_publish_and_issue<32>(spipe, gg, jj, gq, lane, blob, blob + 32 * 32);
+    }
+  };
+
   // ---- layer-1 graph contraction of the FIRST tile (all warps).  For every later tile it is done one tile ahead by the
   //      three warps of TMEM lane quarter 3 during the head stage, where they have half the work of the other quarters
   //      (positions 224..255 do not exist): see the end of stage S11.
@@ -525,25 +549,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     acopy(AB, Pm.eAw[3], kAwFloats);
     cp_async_commit();
     if (tid == 0) *task_ctr = 0;
-    {
-      const int n = gg;
-      const uint32_t lane_base = spipe.tbase + (static_cast<uint32_t>(gq * 32) << 16);
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        if (jj == 0 || gq < 3) {
-          const int p = jj * 128 + gq * 32 + lane;
-          const int pc = p < kP ? p : kP - 1;
-          float a[32];
-#pragma unroll
-          for (int k = 0; k < kC2; ++k) {
-            a[k] = G3[(n * kC2 + k) * kCS + pc];
-            a[kC2 + k] = H2[(n * kC2 + k) * kCS + pc];
-          }
-          sm_store_a(lane_base + sm_col_a(gg, jj), a);
-        }
-        sm_publish_and_issue<32>(spipe, gg, jj, gq, lane, WMs, WMs + 32 * 32);
-      }
-    }
+    small_mix(G3, std::integral_constant<int, kC2>{}, H2, WMs);
     sm_epilogue<false>(spipe, gg, gq, lane, R0, nullptr, WMs + 2 * 32 * 32, WMs[2 * 32 * 32 + 32]);
     spipe.uses += 1;
     // ---- S9: L4 residual half issued first (inputs H3 = R0): runs on the tensor cores while the CUDA cores do the
@@ -673,8 +679,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       boundary();
       acopy(TB, Pm.dTw[0], kTwFloats);
       acopy(AB, Pm.dAw[0], kAwFloats);
-      acopy(WMs, Pm.dWm[0], mix_blob_floats(32, 32));
-      acopy(WMb, Pm.dWm[1], mix_blob_floats(32, 32));
+      acopy(WMs, Pm.tcD2, tc_blob_floats(32, 32));
+      acopy(WMb, Pm.tcD3, tc_blob_floats(32, 32));
       cp_async_commit();
       finalize(tile, cur);
       __syncthreads();
@@ -708,11 +714,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       boundary();
       float* Ud = R1;
       float* Rsdd = R1 + kNW * kC2 * kCS;
-      const float dslope1 = WMs[kC1 * 2 * kC2 + 2 * kC2];
-      {
-        EpiSplit<kC2> epi{Ud, Rsdd, WMs + kC1 * 2 * kC2};
-        mix_stage<kC1, 0, 2 * kC2, 16, EpiSplit<kC2>, kTcWarps>(R0, nullptr, WMs, epi, warp, lane);
-      }
+      const float dslope1 = WMs[2 * 32 * 32 + 32];
+      small_mix(R0, std::integral_constant<int, kC1>{}, nullptr, WMs);                                  // tensor cores, like encoder layer 2
+      sm_epilogue<true>(spipe, gg, gq, lane, Ud, Rsdd, WMs + 2 * 32 * 32, 0.f);
+      spipe.uses += 1;
       // ---- S15: D2 temporal in place
       boundary();
       acopy(WMs, Pm.dWm[2], mix_blob_floats(32, 4));
@@ -737,10 +742,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       boundary();
       acopy(AB, Pm.dAw[2], kAwFloats);
       cp_async_commit();
-      {
-        EpiStorePrelu<kC3> epi{R0, WMb + 2 * kC2 * kC3, WMb[2 * kC2 * kC3 + kC3]};
-        mix_stage<kC2, kC2, kC3, 16, EpiStorePrelu<kC3>, kTcWarps>(R1 + kNW * kC2 * kCS, R1, WMb, epi, warp, lane);
-      }
+      small_mix(R1 + kNW * kC2 * kCS, std::integral_constant<int, kC2>{}, R1, WMb);                     // tensor cores, like encoder layer 3
+      sm_epilogue<false>(spipe, gg, gq, lane, R0, nullptr, WMb + 2 * 32 * 32, WMb[2 * 32 * 32 + 32]);
+      spipe.uses += 1;
       // ---- S20: D4 (32->2) mix-first: R0 -> U (R1 rows 0..5), Rsd (R1 rows 6..11); GB stays reserved for the next tile's
       //           layer-1 output
       boundary();
