@@ -571,8 +571,10 @@ extern "C" int coskad_train_contract_fwd(coskad_ctx* ctx, const float* X, const 
                                          float* G1, float* G, void* stream_) {
   TRAIN_PRE();
   if (R <= 0) return COSKAD_OK;
-  const int g = static_cast<int>(R < ctx->sm_count * 8 ? R : ctx->sm_count * 8);
-  train_contract_fwd_kernel<<<g, kTrainThreads, 0, st>>>(X, A, T, R, G1, G);
+  const int64_t nblk = (R + kCRows - 1) / kCRows;
+  const int g = static_cast<int>(nblk < ctx->sm_count ? nblk : ctx->sm_count);
+  CK(cudaFuncSetAttribute(train_contract_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
+  train_contract_fwd_kernel<<<g, kCThreads, kCSmemBytes, st>>>(X, A, T, R, G1, G);
   CK_LAUNCH();
   return COSKAD_OK;
 }
@@ -582,8 +584,10 @@ extern "C" int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const
                                          float* dA, float* dT, void* stream_) {
   TRAIN_PRE();
   if (R <= 0) return COSKAD_OK;
-  const int g = static_cast<int>(R < ctx->sm_count * 4 ? R : ctx->sm_count * 4);
-  train_contract_bwd_kernel<<<g, kTrainThreads, 0, st>>>(dG, dXres, X, G1, A, T, R, dX, dA, dT);
+  const int64_t nblk = (R + kCRows - 1) / kCRows;
+  const int g = static_cast<int>(nblk < ctx->sm_count ? nblk : ctx->sm_count);
+  CK(cudaFuncSetAttribute(train_contract_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
+  train_contract_bwd_kernel<<<g, kCThreads, kCSmemBytes, st>>>(dG, dXres, X, G1, A, T, R, dX, dA, dT);
   CK_LAUNCH();
   return COSKAD_OK;
 }

@@ -78,87 +78,160 @@ namespace coskad {
 
 constexpr int kTrainThreads = 256;
 
-// ---- graph contraction forward: G1 = temporal(X), G = spatial(G1); one block iteration per row ----
-__global__ void train_contract_fwd_kernel(const float* __restrict__ X, const float* __restrict__ A,
-                                          const float* __restrict__ T, int64_t R, float* __restrict__ G1,
-                                          float* __restrict__ G) {
-  __shared__ float As[kT * kV * kV], Ts[kV * kT * kT], xs[kP], g1s[kP];
-  for (int i = threadIdx.x; i < kT * kV * kV; i += blockDim.x) As[i] = A[i];
-  for (int i = threadIdx.x; i < kV * kT * kT; i += blockDim.x) Ts[i] = T[i];
-  const int i = threadIdx.x;
-  const int t_ = i / kV, v_ = i % kV;     // (q or t, v or w) of this thread's output
-  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
-    __syncthreads();
-    if (i < kP) xs[i] = X[r * kP + i];
-    __syncthreads();
-    if (i < kP) {                          // G1[q=t_, v=v_] = sum_t X[t, v] T[v, t, q]
-      float s = 0.f;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) s = fmaf(xs[t * kV + v_], Ts[v_ * (kT * kT) + t * kT + t_], s);
-      g1s[i] = s;
-      G1[r * kP + i] = s;
-    }
-    __syncthreads();
-    if (i < kP) {                          // G[t=t_, w=v_] = sum_v G1[t, v] A[t, v, w]
-      float s = 0.f;
-#pragma unroll
-      for (int v = 0; v < kV; ++v) s = fmaf(g1s[t_ * kV + v], As[t_ * (kV * kV) + v * kV + v_], s);
-      G[r * kP + i] = s;
-    }
+// ---- graph contraction forward / backward over rows (row = one (window, channel) plane of 204 positions) ------------
+// Persistent blocks of 384 threads; one iteration = kCRows = 96 consecutive rows held as planes [row][205] in shared
+// memory and pushed through the register-blocked FFMA2 contraction stages of the eval kernel (fused_eval.cuh:
+// temporal_stage_c32 / spatial_stage_c32: lane = row % 32, three 32-row groups per lane, weights broadcast from shared
+// memory).  The backward pass runs the same stages with transposed weights and accumulates dA / dT as per-thread register
+// tiles over the block's rows (one atomicAdd per element per block at the end).
+constexpr int kCRows = kNW * 32;                 // 96
+constexpr int kCThreads = 384;
+constexpr int kCWarps = kCThreads / 32;
+constexpr int kCSmemFloats = 2 * kCRows * kCS + kTwFloats + kAwFloats;
+constexpr int kCSmemBytes = kCSmemFloats * 4;
+static_assert(kCSmemBytes <= 227 * 1024, "contraction kernels: shared memory plan exceeds 227 KB");
+
+__device__ __forceinline__ void contract_load_rows(float* dst, const float* __restrict__ src, int64_t r0, int nr, int tid) {
+  for (int i = tid; i < kCRows * kP; i += kCThreads) {
+    const int row = i / kP, p = i - row * kP;
+    const int rr = row < nr ? row : nr - 1;            // ragged last block: replicate the last row, never stored
+    cp_async4(dst + row * kCS + p, src + (r0 + rr) * kP + p);
   }
 }
 
-// ---- graph contraction backward -----------------------------------------------------------------
+// G1 = einsum('nctv,vtq->ncqv', X, T); G = einsum('nctv,tvw->nctw', G1, A)      (stsgcn.py:154-155)
+__global__ void __launch_bounds__(kCThreads, 1) train_contract_fwd_kernel(const float* __restrict__ X, const float* __restrict__ A,
+                                                                         const float* __restrict__ T, int64_t R,
+                                                                         float* __restrict__ G1, float* __restrict__ G) {
+  extern __shared__ __align__(16) float csm[];
+  float* Xs = csm;
+  float* Gs = Xs + kCRows * kCS;
+  float* Ts = Gs + kCRows * kCS;
+  float* As = Ts + kTwFloats;                      // rows padded 17 -> kAW
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < kTwFloats; i += kCThreads) Ts[i] = T[i];
+  for (int i = tid; i < kAwFloats; i += kCThreads) { const int w = i % kAW, tv = i / kAW; As[i] = (w < kV) ? A[tv * kV + w] : 0.f; }
+  const int64_t nblk = (R + kCRows - 1) / kCRows;
+  if (static_cast<int64_t>(blockIdx.x) < nblk) {
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kCRows;
+    contract_load_rows(Xs, X, r0, static_cast<int>(R - r0 < kCRows ? R - r0 : kCRows), tid);
+  }
+  cp_async_commit();
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t r0 = blk * kCRows;
+    const int nr = static_cast<int>(R - r0 < kCRows ? R - r0 : kCRows);
+    cp_async_wait_all();
+    __syncthreads();
+    temporal_stage_c32<kCWarps>(Xs, Gs, Ts, warp, lane);
+    __syncthreads();
+    {   // Xs is dead: prefetch the next block's rows while this one finishes
+      const int64_t nb = blk + gridDim.x;
+      if (nb < nblk) { const int64_t n0 = nb * kCRows; contract_load_rows(Xs, X, n0, static_cast<int>(R - n0 < kCRows ? R - n0 : kCRows), tid); }
+      cp_async_commit();
+    }
+    for (int i = tid; i < nr * kP; i += kCThreads) { const int row = i / kP, p = i - row * kP; G1[(r0 + row) * kP + p] = Gs[row * kCS + p]; }
+    __syncthreads();
+    spatial_stage_c32<kCWarps>(Gs, As, warp, lane);
+    __syncthreads();
+    for (int i = tid; i < nr * kP; i += kCThreads) { const int row = i / kP, p = i - row * kP; G[(r0 + row) * kP + p] = Gs[row * kCS + p]; }
+  }
+  cp_async_wait_all();
+}
+
 // dG1[t,v] = sum_w dG[t,w] A[t,v,w];  dX[t,v] = dXres[t,v] + sum_q dG1[q,v] T[v,t,q]
 // dA[t,v,w] += G1[t,v] dG[t,w];       dT[v,t,q] += X[t,v] dG1[q,v]      (summed over rows)
-__global__ void train_contract_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ dXres,
-                                          const float* __restrict__ X, const float* __restrict__ G1,
-                                          const float* __restrict__ A, const float* __restrict__ T, int64_t R,
-                                          float* __restrict__ dX, float* dA, float* dT) {
-  __shared__ float As[kT * kV * kV], Ts[kV * kT * kT], dgs[kP], xs[kP], g1s[kP], dg1s[kP];
-  for (int i = threadIdx.x; i < kT * kV * kV; i += blockDim.x) As[i] = A[i];
-  for (int i = threadIdx.x; i < kV * kT * kT; i += blockDim.x) Ts[i] = T[i];
-  constexpr int NA = (kT * kV * kV + kTrainThreads - 1) / kTrainThreads;   // 14
-  constexpr int NT = (kV * kT * kT + kTrainThreads - 1) / kTrainThreads;   // 10
-  float accA[NA], accT[NT];
+__global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
+    const float* __restrict__ dG, const float* __restrict__ dXres, const float* __restrict__ X, const float* __restrict__ G1,
+    const float* __restrict__ A, const float* __restrict__ T, int64_t R, float* __restrict__ dX, float* dA, float* dT) {
+  extern __shared__ __align__(16) float csm[];
+  float* P0 = csm;                                 // dG -> dG1 (in place)
+  float* P1 = P0 + kCRows * kCS;                   // G1, then X, then dX
+  float* Tt = P1 + kCRows * kCS;                   // Tt[v][q][t] = T[v][t][q]
+  float* At = Tt + kTwFloats;                      // At[t][w][v] = A[t][v][w], rows padded 17 -> kAW
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < kTwFloats; i += kCThreads) { const int v = i / (kT * kT), q = (i / kT) % kT, t = i % kT; Tt[i] = T[v * (kT * kT) + t * kT + q]; }
+  for (int i = tid; i < kAwFloats; i += kCThreads) {
+    const int v = i % kAW, tw = i / kAW, t = tw / kV, w = tw % kV;
+    At[i] = (v < kV) ? A[(t * kV + v) * kV + w] : 0.f;
+  }
+  // dA tiles: thread < 300 owns (t, 4 v, 4 w); dT tiles: thread < 306 owns (v, 4 t, 2 q)
+  const bool hasA = tid < kT * 25, hasT = tid < kV * 18;
+  const int at = tid / 25, avg = (tid % 25) / 5, awg = tid % 5;
+  const int tv = tid / 18, ttg = (tid % 18) / 6, tqg = tid % 6;
+  int aiv[4], aiw[4], tit[4], tiq[2];
 #pragma unroll
-  for (int j = 0; j < NA; ++j) accA[j] = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    aiv[i] = at * kV + (4 * avg + i < kV ? 4 * avg + i : kV - 1);
+    aiw[i] = at * kV + (4 * awg + i < kV ? 4 * awg + i : kV - 1);
+    tit[i] = (4 * ttg + i) * kV + tv;
+  }
+  tiq[0] = (2 * tqg) * kV + tv; tiq[1] = (2 * tqg + 1) * kV + tv;
+  float accA[4][4], accT[4][2];
 #pragma unroll
-  for (int j = 0; j < NT; ++j) accT[j] = 0.f;
-  const int i = threadIdx.x;
-  const int t_ = i / kV, v_ = i % kV;
-  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+  for (int i = 0; i < 4; ++i) {
+    accT[i][0] = accT[i][1] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accA[i][j] = 0.f;
+  }
+  const int64_t nblk = (R + kCRows - 1) / kCRows;
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t r0 = blk * kCRows;
+    const int nr = static_cast<int>(R - r0 < kCRows ? R - r0 : kCRows);
     __syncthreads();
-    if (i < kP) { dgs[i] = dG[r * kP + i]; xs[i] = X[r * kP + i]; g1s[i] = G1[r * kP + i]; }
+    contract_load_rows(P0, dG, r0, nr, tid);
+    contract_load_rows(P1, G1, r0, nr, tid);
+    cp_async_commit();
+    cp_async_wait_all();
     __syncthreads();
-    if (i < kP) {
-      float s = 0.f;
+    if (hasA) {
+      for (int r = 0; r < nr; ++r) {
+        float g[4], d[4];
 #pragma unroll
-      for (int w = 0; w < kV; ++w) s = fmaf(dgs[t_ * kV + w], As[t_ * (kV * kV) + v_ * kV + w], s);
-      dg1s[i] = s;
+        for (int i = 0; i < 4; ++i) { g[i] = P1[r * kCS + aiv[i]]; d[i] = P0[r * kCS + aiw[i]]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) accA[i][j] = fmaf(g[i], d[j], accA[i][j]);
+      }
     }
     __syncthreads();
-    if (i < kP) {
-      float s = (dXres != nullptr) ? dXres[r * kP + i] : 0.f;
+    contract_load_rows(P1, X, r0, nr, tid);          // G1 is dead
+    cp_async_commit();
+    spatial_stage_c32<kCWarps>(P0, At, warp, lane);  // dG -> dG1 in place
+    cp_async_wait_all();
+    __syncthreads();
+    if (hasT) {
+      for (int r = 0; r < nr; ++r) {
+        float x[4], d[2];
 #pragma unroll
-      for (int q = 0; q < kT; ++q) s = fmaf(dg1s[q * kV + v_], Ts[v_ * (kT * kT) + t_ * kT + q], s);
-      dX[r * kP + i] = s;
+        for (int i = 0; i < 4; ++i) x[i] = P1[r * kCS + tit[i]];
+        d[0] = P0[r * kCS + tiq[0]]; d[1] = P0[r * kCS + tiq[1]];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { accT[i][0] = fmaf(x[i], d[0], accT[i][0]); accT[i][1] = fmaf(x[i], d[1], accT[i][1]); }
+      }
     }
-#pragma unroll
-    for (int j = 0; j < NA; ++j) {
-      const int e = i + j * kTrainThreads;
-      if (e < kT * kV * kV) { const int t = e / (kV * kV), v = (e / kV) % kV, w = e % kV; accA[j] = fmaf(g1s[t * kV + v], dgs[t * kV + w], accA[j]); }
-    }
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int e = i + j * kTrainThreads;
-      if (e < kV * kT * kT) { const int v = e / (kT * kT), t = (e / kT) % kT, q = e % kT; accT[j] = fmaf(xs[t * kV + v], dg1s[q * kV + v], accT[j]); }
+    __syncthreads();
+    temporal_stage_c32<kCWarps>(P0, P1, Tt, warp, lane);      // dG1 -> temporal^T -> P1 (X is dead)
+    __syncthreads();
+    for (int i = tid; i < nr * kP; i += kCThreads) {
+      const int row = i / kP, p = i - row * kP;
+      const int64_t o = (r0 + row) * kP + p;
+      dX[o] = P1[row * kCS + p] + (dXres != nullptr ? dXres[o] : 0.f);
     }
   }
+  if (hasA) {
 #pragma unroll
-  for (int j = 0; j < NA; ++j) { const int e = i + j * kTrainThreads; if (e < kT * kV * kV) atomicAdd(dA + e, accA[j]); }
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-  for (int j = 0; j < NT; ++j) { const int e = i + j * kTrainThreads; if (e < kV * kT * kT) atomicAdd(dT + e, accT[j]); }
+      for (int j = 0; j < 4; ++j)
+        if (4 * avg + i < kV && 4 * awg + j < kV) atomicAdd(dA + (at * kV + 4 * avg + i) * kV + 4 * awg + j, accA[i][j]);
+  }
+  if (hasT) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) atomicAdd(dT + tv * (kT * kT) + (4 * ttg + i) * kT + 2 * tqg + j, accT[i][j]);
+  }
 }
 
 // ---- 1x1 convolutions forward + BatchNorm partial statistics ----------------------------------------
@@ -372,18 +445,25 @@ __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
   const int64_t E = B * kP;
   for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * kWC; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * kWC) {
     __syncthreads();
-    for (int i = threadIdx.x; i < (CO + CI) * kWC; i += blockDim.x) {
-      const int c = i / kWC, k = i % kWC;
-      const int64_t e = e0 + k;
-      const bool valid = e < E;
-      const int64_t b = valid ? e / kP : 0;
-      const int p = valid ? static_cast<int>(e - b * kP) : 0;
-      if (c < CO) {
-        d1s[c * kWCS + k] = valid ? dy1[(b * CO + c) * kP + p] : 0.f;
-        d2s[c * kWCS + k] = valid ? dy2[(b * CO + c) * kP + p] : 0.f;
-      } else {
-        gs[(c - CO) * kWCS + k] = valid ? G[(b * CI + (c - CO)) * kP + p] : 0.f;
-        xs[(c - CO) * kWCS + k] = valid ? X[(b * CI + (c - CO)) * kP + p] : 0.f;
+    {
+      // element e = e0 + k of channel row c lives at ((b*C + c)*204 + p): one division per chunk, not per element
+      const int64_t b0 = e0 / kP;
+      const int p0 = static_cast<int>(e0 - b0 * kP);
+      const int k = threadIdx.x % kWC;                       // 256 threads: fixed k, rows c = threadIdx.x / kWC + 2 j
+      int p = p0 + k;
+      int64_t b = b0;
+      if (p >= kP) { p -= kP; b += 1; }
+      const bool valid = e0 + k < E;
+      for (int c = threadIdx.x / kWC; c < CO + CI; c += kTrainThreads / kWC) {
+        if (c < CO) {
+          const int64_t o = (b * CO + c) * kP + p;
+          d1s[c * kWCS + k] = valid ? dy1[o] : 0.f;
+          d2s[c * kWCS + k] = valid ? dy2[o] : 0.f;
+        } else {
+          const int64_t o = (b * CI + (c - CO)) * kP + p;
+          gs[(c - CO) * kWCS + k] = valid ? G[o] : 0.f;
+          xs[(c - CO) * kWCS + k] = valid ? X[o] : 0.f;
+        }
       }
     }
     __syncthreads();

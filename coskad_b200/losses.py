@@ -2,24 +2,37 @@
 
 calc_reg_loss mirrors utils/model_utils.py:90-105: 0.5 * sum ||p||^2 over the tensors whose name does
 not contain 'bias', divided by the NUMBER of such tensors (it includes BatchNorm weights, PReLU slopes,
-A and T).  It is a reduction over 240 k parameters per step -- kept in PyTorch (tiny).
+A and T).  The reference walks the ~42 tensors one by one (three tiny kernels each, and as many again in
+the backward); here the value comes from one multi-tensor norm and the gradient (alpha/n * p per tensor)
+from one multi-tensor scale -- same value up to fp32 summation order.
 """
 from __future__ import annotations
+
+from typing import List
 
 import torch
 
 
+class _L2Reg(torch.autograd.Function):
+    """0.5 * sum_i ||p_i||_2^2 / n   (utils/model_utils.py:92-102: first tensor 0.5*sum(p^2), the rest 0.5*||p||_2^2)"""
+
+    @staticmethod
+    def forward(ctx, n_avg: float, *params: torch.Tensor) -> torch.Tensor:
+        ctx.n_avg = n_avg
+        ctx.save_for_backward(*params)
+        norms = torch._foreach_norm([p.detach() for p in params], 2)
+        return 0.5 * torch.stack(norms).square().sum() / n_avg
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        params = ctx.saved_tensors
+        scale = g / ctx.n_avg
+        grads = torch._foreach_mul([p.detach() for p in params], scale)
+        return (None, *grads)
+
+
 def calc_reg_loss(model, reg_type: str = 'l2', avg: bool = True):
-    reg_loss = None
-    parameters = list(param for name, param in model.named_parameters() if 'bias' not in name)
-    num_params = len(parameters)
+    parameters: List[torch.Tensor] = [param for name, param in model.named_parameters() if 'bias' not in name]
     if reg_type.lower() == 'l2':
-        for param in parameters:
-            if reg_loss is None:
-                reg_loss = 0.5 * torch.sum(param ** 2)
-            else:
-                reg_loss = reg_loss + 0.5 * param.norm(2) ** 2
-        if avg:
-            reg_loss /= num_params
-        return reg_loss
+        return _L2Reg.apply(float(len(parameters)) if avg else 1.0, *parameters)
     return torch.tensor(0.0, device=next(model.parameters()).device)

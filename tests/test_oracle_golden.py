@@ -161,3 +161,22 @@ def test_windows_oracle_matches_reference_vectors(golden_dir):
     # identity transform first, x-flip second (utils/dataset_utils.py:304-306)
     assert np.array_equal(g['transformed'][0], w)
     assert np.array_equal(g['transformed'][1][:, 0], -w[:, 0]) and np.array_equal(g['transformed'][1][:, 1], w[:, 1])
+
+
+def test_fused_reg_loss_matches_reference_formula():
+    """coskad_b200.losses.calc_reg_loss (one multi-tensor norm) vs the per-tensor loop of utils/model_utils.py:90-105"""
+    from coskad_b200.losses import calc_reg_loss
+    torch.manual_seed(3)
+    m = torch.nn.Sequential(torch.nn.Conv2d(2, 8, 1), torch.nn.BatchNorm2d(8), torch.nn.PReLU(), torch.nn.Linear(17, 5))
+    params = [p for n, p in m.named_parameters() if 'bias' not in n]
+    ref = None
+    for p in params:
+        ref = 0.5 * torch.sum(p ** 2) if ref is None else ref + 0.5 * p.norm(2) ** 2
+    ref = ref / len(params)
+    got = calc_reg_loss(m)
+    assert abs(float(got.detach()) - float(ref.detach())) <= 1e-6 * abs(float(ref.detach()))
+    g_ref = torch.autograd.grad(ref * 2.5, params)
+    g_got = torch.autograd.grad(got * 2.5, params)
+    for a, b in zip(g_got, g_ref):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+    assert all(p.grad is None for n, p in m.named_parameters() if 'bias' in n)
