@@ -159,6 +159,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL prints its banner ("NCCL version ...") on stdout when NCCL_DEBUG is VERSION/INFO: keep stdout = the JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     model = make_model('stse', 16, seed=0, device=dev)     # random init, randomised BN statistics
