@@ -50,6 +50,7 @@ SIGNATURES = {
     'coskad_frame_aggregate': (C.c_int, [c_ctx_p, c_float_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    'coskad_score_process': (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'coskad_train_contract_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 3 + [C.c_int64] + [c_float_p] * 2 + [C.c_void_p]),
     'coskad_train_contract_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64] + [c_float_p] * 3 + [C.c_void_p]),
     'coskad_train_mix_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64, C.c_int, C.c_int] + [c_float_p] * 3 + [C.c_void_p]),

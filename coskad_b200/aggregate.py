@@ -165,6 +165,67 @@ def score_and_aggregate(score: torch.Tensor, trans, meta, frames, clips: Sequenc
     return res
 
 
+# ---- device post-processing: smoothing + AUC without leaving the GPU -------------------------------
+def gaussian_weights(sigma: float = 30.0, truncate: float = 4.0) -> np.ndarray:
+    """the normalised kernel scipy.ndimage.gaussian_filter1d(order 0) builds (scipy/ndimage/_filters.py _gaussian_kernel1d)"""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum()
+
+
+def score_process_device(curves: torch.Tensor, curve_off: torch.Tensor, sigma: float = 30.0, shift: int = 8 + (8 // 2) - 1
+                         ) -> torch.Tensor:
+    """utils/eval_utils.py:200-207 for all curves at once on the device (float64, scipy's summation order)"""
+    if not curves.is_cuda:
+        raise _lib.CoskadError('curves must be a CUDA tensor (no CPU fallback; use score_process on the host)')
+    dev = curves.device
+    curves = curves.to(torch.float64).contiguous()
+    curve_off = curve_off.to(device=dev, dtype=torch.int64).contiguous()
+    w = torch.from_numpy(gaussian_weights(sigma)).to(dev)
+    out = torch.empty_like(curves)
+    ctx = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    rc = ctx.lib.coskad_score_process(ctx.h, curves.data_ptr(), curve_off.data_ptr(), curve_off.numel() - 1, int(shift),
+                                      w.data_ptr(), (w.numel() - 1) // 2, out.data_ptr(), _lib.stream_ptr(dev))
+    ctx.check(rc, 'coskad_score_process')
+    return out
+
+
+def auc_device(scores: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """sklearn.metrics.roc_auc_score(labels, scores) for binary labels as a 0-dim float64 device tensor: ROC points at the
+    distinct score thresholds (descending), trapezoid rule (sklearn/metrics/_ranking.py _binary_clf_curve + auc)"""
+    s = scores.to(torch.float64).view(-1)
+    y = (labels.to(device=s.device).view(-1) != 0).to(torch.float64)
+    order = torch.argsort(s, descending=True, stable=True)
+    s, y = s[order], y[order]
+    last = torch.ones_like(s, dtype=torch.bool)
+    last[:-1] = s[1:] != s[:-1]
+    idx = torch.nonzero(last).view(-1)
+    tps = torch.cumsum(y, 0)[idx]
+    fps = (idx + 1).to(torch.float64) - tps
+    zero = torch.zeros(1, dtype=torch.float64, device=s.device)
+    tpr = torch.cat([zero, tps]) / tps[-1]
+    fpr = torch.cat([zero, fps]) / fps[-1]
+    return torch.trapezoid(tpr, fpr)
+
+
+def score_auc_device(score: torch.Tensor, trans, meta, frames, clips: Sequence[Tuple[int, int, int]], num_transform: int,
+                     gts: Dict[Tuple[int, int], np.ndarray]) -> Tuple[float, Dict[int, float]]:
+    """eval_COSKAD.py:140-253 without pad_scores / HR masks, entirely on the device: frame aggregation -> shift + Gaussian
+    smoothing -> per-transformation AUC on the concatenated clips and the AUC of the mean curve.  One D2H copy of
+    num_transform + 1 doubles at the end."""
+    gi = GroupIndex(trans, meta, clips, num_transform)
+    _, out = aggregate_curves(score, frames, gi)
+    dev = out.device
+    total = int(gi.clip_off[-1])
+    sm = score_process_device(out[:total], torch.as_tensor(gi.clip_off, dtype=torch.int64))
+    per = total // num_transform                                  # every transformation covers the same clips
+    gt = torch.from_numpy(np.concatenate([np.asarray(gts[(s, c)]).reshape(-1) for (s, c, _f) in clips])).to(dev)
+    st = sm.view(num_transform, per)
+    aucs = torch.stack([auc_device(st[t], gt) for t in range(num_transform)] + [auc_device(st.mean(0), gt)]).cpu()
+    return float(aucs[-1]), {t: float(aucs[t]) for t in range(num_transform)}
+
+
 # ---- reference-named compat surface (utils/eval_utils.py:41-106) ------------------------------------
 def _scatter(loss: torch.Tensor, frames_fig, n_frames: int) -> np.ndarray:
     """pose[n, frames_fig[n]-1] = loss[n] as a float64 [w, n_frames] matrix, one D2H copy instead of w."""

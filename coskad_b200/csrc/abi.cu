@@ -476,6 +476,21 @@ extern "C" int coskad_center_finalize(coskad_ctx* ctx, int flavour, const double
   return COSKAD_OK;
 }
 
+// shift + Gaussian smoothing of n_curves float64 curves (curve_off CSR); weights [2*radius+1] device doubles
+extern "C" int coskad_score_process(coskad_ctx* ctx, const double* curves, const int64_t* curve_off, int64_t n_curves,
+                                    int shift, const double* weights, int radius, double* out, void* stream_) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (n_curves < 0 || shift < 0 || radius < 0) return fail(ctx, COSKAD_ERR_ARG, "negative argument");
+  if (n_curves == 0) return COSKAD_OK;
+  if (!curves || !curve_off || !weights || !out) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  if (curves == out) return fail(ctx, COSKAD_ERR_ARG, "score_process cannot run in place");
+  CK(cudaSetDevice(ctx->device));
+  score_process_kernel<<<static_cast<unsigned>(n_curves), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      curves, curve_off, n_curves, shift, weights, radius, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
 extern "C" int coskad_frame_aggregate(coskad_ctx* ctx, const float* score, const int64_t* frames, int T,
                                       const int64_t* win_idx, const int64_t* person_off, const int32_t* person_clip,
                                       const int64_t* person_out_off, int64_t n_persons, const int64_t* clip_person_off,

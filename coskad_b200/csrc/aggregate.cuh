@@ -74,4 +74,34 @@ __global__ void clip_max_kernel(const double* __restrict__ person_curve, const i
   }
 }
 
+
+// ---- score post-processing: shift by `shift` frames + Gaussian smoothing, per clip curve ----------------------------
+// Reference: utils/eval_utils.py:200-207 score_process: scores_shifted[shift:] = score[:-shift] (shift = 11), then
+// scipy.ndimage.gaussian_filter1d(scores_shifted, 30) = correlate1d with the normalised 241-tap kernel, mode 'reflect'
+// (half-sample symmetric extension: d c b a | a b c d | d c b a).  The accumulation order is the one of scipy's
+// NI_Correlate1D symmetric-kernel branch: tmp = x[l] w[0]; for jj = -r .. -1: tmp += (x[l+jj] + x[l-jj]) * w[jj] --
+// separate multiply and add (no FMA contraction), float64.  weights = the kernel as numpy computes it (host), w[r] = centre.
+__device__ __forceinline__ double shifted_reflect(const double* __restrict__ c, int64_t F, int64_t i, int shift) {
+  const int64_t period = 2 * F;
+  i %= period;
+  if (i < 0) i += period;
+  if (i >= F) i = period - 1 - i;
+  return (i >= shift) ? c[i - shift] : 0.0;
+}
+__global__ void score_process_kernel(const double* __restrict__ curves, const int64_t* __restrict__ curve_off, int64_t n_curves,
+                                     int shift, const double* __restrict__ weights, int radius, double* __restrict__ out) {
+  const int64_t cv = blockIdx.x;
+  if (cv >= n_curves) return;
+  const int64_t o = curve_off[cv], F = curve_off[cv + 1] - o;
+  const double* c = curves + o;
+  for (int64_t l = threadIdx.x; l < F; l += blockDim.x) {
+    double tmp = __dmul_rn(shifted_reflect(c, F, l, shift), weights[radius]);
+    for (int jj = -radius; jj < 0; ++jj) {
+      const double pair = __dadd_rn(shifted_reflect(c, F, l + jj, shift), shifted_reflect(c, F, l - jj, shift));
+      tmp = __dadd_rn(tmp, __dmul_rn(pair, weights[radius + jj]));
+    }
+    out[o + l] = tmp;
+  }
+}
+
 }  // namespace coskad

@@ -20,8 +20,9 @@ from coskad_b200 import aggregate, config as ccfg, tasks      # noqa: E402
 from coskad_b200.trainer import Trainer                       # noqa: E402
 
 
-def evaluate(args, model, dataset_loader, ckpt_path=None, masks=None):
-    """returns (final AUC, per-transformation AUCs, curves)"""
+def evaluate(args, model, dataset_loader, ckpt_path=None, masks=None, device_tail=False):
+    """returns (final AUC, per-transformation AUCs, curves).  device_tail=True (no pad_scores / HR masks): aggregation,
+    smoothing and AUC all run on the GPU (aggregate.score_auc_device) and curves is None."""
     ds, loader = dataset_loader
     trainer = Trainer(device=torch.device('cuda', torch.cuda.current_device()), verbose=False)
     out = trainer.predict(model, dataloaders=loader, ckpt_path=ckpt_path, return_predictions=True)
@@ -34,6 +35,9 @@ def evaluate(args, model, dataset_loader, ckpt_path=None, masks=None):
     else:
         hidden, trans, meta, frames = tasks.light_processing_data(out)
         scores = model.window_scores(hidden, validation=False)
+    if device_tail and pad == -1 and masks is None:
+        auc, per_t = aggregate.score_auc_device(scores, trans, meta, frames, clips, nt, gts)
+        return auc, per_t, None
     curves = aggregate.score_and_aggregate(scores, trans, meta, frames, clips, nt, pad_size=pad, gts=gts, masks=masks)
     auc, per_t = tasks.auc_from_curves(curves, clips, gts, masks)
     return auc, per_t, curves

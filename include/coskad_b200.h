@@ -186,6 +186,14 @@ int coskad_frame_aggregate(coskad_ctx* ctx, const float* score, const int64_t* f
                            int64_t total_person_frames, int64_t max_clip_frames,
                            double* person_out, double* out, void* stream);
 
+/* Score post-processing of per-clip curves on the device: out[f] = gaussian_filter1d(shifted, sigma)[f] with
+ * shifted[shift:] = curve[:-shift]; float64, scipy's 'reflect' boundary and accumulation order.
+ *   curves f64 concatenated, curve_off[n_curves+1] i64 CSR offsets, weights[2*radius+1] f64 = the normalised Gaussian
+ *   kernel exactly as scipy builds it (radius = int(4 sigma + 0.5); the caller computes it with numpy), out != curves.
+ * replaces: utils/eval_utils.py:200-207 score_process (eval_COSKAD.py:217) */
+int coskad_score_process(coskad_ctx* ctx, const double* curves, const int64_t* curve_off, int64_t n_curves, int shift,
+                         const double* weights, int radius, double* out, void* stream);
+
 /* ---- training path (per-layer kernels, train-mode BatchNorm with per-GPU batch statistics) ------
  * Activations are [B, C, 204] float32 in HBM between kernels (the batch statistics of BatchNorm sit
  * between the convolution and the activation).  Gradient buffers that are ACCUMULATED into (dA, dT,
