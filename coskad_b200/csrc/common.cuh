@@ -55,7 +55,7 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 }
 
 // packed FP32 FMA (sm_100a FFMA2): d.{lo,hi} += a.{lo,hi} * b.{lo,hi}; one issue slot for two FMAs (measured 92 % of
-// the scalar FFMA rate in FLOP terms, scratch/ubench/ffma2.cu) -- used where the FP32 stages are issue-bound
+// the scalar FFMA rate in FLOP terms, tools/ubench/ffma2.cu) -- used where the FP32 stages are issue-bound
 __device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }

@@ -1,19 +1,21 @@
-// fused_eval_tc.cuh -- fused eval hot path, v2: the dense channel mixing (65 % of the MACs) runs on the 5th-gen
-// tensor cores (tcgen05.mma kind::tf32, 3xTF32 split accumulate), the graph contractions, the linear head and the
-// geometry stay on the CUDA cores.  Same arithmetic contract as fused_eval.cuh (see there for the reference
-// citations); score parity rtol 1e-4 is kept by the hi/lo operand split (tc.cuh).
-//
-// Per CTA (one per SM, 384 threads = 12 warps, 227 KB smem, all 512 TMEM columns):
-//   * activations live in shared memory as channel planes [row = window*C + c][205] exactly like v1 (the
-//     contraction stages are unchanged);
-//   * a mixing stage = for each of the 6 M-tiles (window n, position half j: 128 positions) the producer warps read
-//     the K <= 32 input channels of their position from the planes, split them into tf32 hi/lo and tcgen05.st them
-//     into one of two 64-column A buffers in TMEM; one elected thread issues 3 MMAs per 8 channels
-//     (A_hi B_hi + A_lo B_hi + A_hi B_lo) with B = BN-folded weights held in shared memory as canonical K-major
-//     images (hi and lo); accumulators D[128 x N] of all 6 tiles stay in TMEM (6 x 64 columns);
-//   * epilogue: tcgen05.ld -> bias + PReLU -> next layer's planes, or (layer 4) straight into the linear head;
-//   * layer 4 is issued in two phases: the residual half (inputs = H3, known before the graph contraction) is
-//     issued first and executes asynchronously while the CUDA cores run the layer-4 contraction.
+// fused_eval_tc.cuh -- fused eval hot path, tensor-core generation: the dense channel mixing (65 % of the MACs) runs on the
+// 5th-gen tensor cores (tcgen05.mma kind::tf32, 3xTF32 split accumulate), the graph contractions, the linear head and
+// the geometry stay on the CUDA cores (packed FFMA2).  Same arithmetic contract as fused_eval.cuh (see there for the
+// reference citations); score parity rtol 1e-4 is kept by the hi/lo operand split (tc.cuh).  DESIGN.md section 4 describes
+// the structure; in short, per CTA (one per SM, 384 threads = 12 warps = 3 groups x 4 TMEM lane quarters, 227 KB smem,
+// all 512 TMEM columns), per tile of kNW = 3 windows:
+//   * activations live in shared memory as channel planes [row = window*C + c][205]; H1 (layer-1 output) and H4
+//     (layer-4 output) never exist in memory: H1 is split straight into the layer-2 TMEM operand, H4 is consumed by
+//     the head from the TMEM accumulators;
+//   * layers 2/3 (N = 32): each warp group owns one window, stages its two M-tiles (128 positions each) into private
+//     TMEM A buffers, issues its own MMAs and runs its own epilogue (SmallPipe);
+//   * layer 4 (N = 64): 384 D columns + two shared 64-column A buffers with mbarrier hand-off (TcPipe); the residual
+//     half is issued before the layer-4 graph contraction and executes behind it; the head starts on the j = 0 tiles
+//     while the j = 1 tiles still execute;
+//   * tile software pipelining: head reduction + score of tile i run in the first stage of tile i+1; the layer-1 graph
+//     contraction of tile i+1 runs on the quarter-3 warps during the head of tile i;
+//   * optional front end: windows gathered from trajectory rows + test-time affine transform in the input stage;
+//   * kDec = true appends the auto-encoder's decoder (folded first layer, layers 1-2 mixing on the tensor cores).
 #pragma once
 #include <type_traits>
 #include "common.cuh"
@@ -173,41 +175,6 @@ __device__ __forceinline__ void tc_wait_done(TcPipe& P) {
   P.n_done += 1;
   tc::fence_after_sync();
 }
-
-// epilogue of layers 1-3: D -> (+bias, PReLU) -> planes dst[(n*COUT + co)][p]; SPLIT: mix-first layout (U | Rsd)
-template <int N, bool SPLIT>
-__device__ __forceinline__ void tc_epilogue_store(const TcPipe& P, float* dst, float* dstR, const float* bias, float slope,
-                                                  int warp, int lane) {
-  const int q = warp & 3, n = warp >> 2;           // group = window
-  constexpr int CO = SPLIT ? N / 2 : N;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int ti = j * kNW + n;
-    const int p = j * 128 + q * 32 + lane;
-    const uint32_t d = P.tbase + (static_cast<uint32_t>(q * 32) << 16) + kTcColD + 64u * ti;
-#pragma unroll
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      uint32_t v[16];
-      tc::tmem_ld16(d + c0, v);
-      tc::wait_ld();
-      if (p < kP) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int co = c0 + u;
-          const float val = __uint_as_float(v[u]) + bias[co];
-          if (SPLIT) {
-            if (co < CO) dst[(n * CO + co) * kCS + p] = val;            // U: bias slot is 0
-            else dstR[(n * CO + co - CO) * kCS + p] = val;              // Rsd + folded bias
-          } else {
-            dst[(n * CO + co) * kCS + p] = prelu(val, slope);
-          }
-        }
-      }
-    }
-  }
-  tc::fence_before_sync();
-}
-
 
 // ---- N = 32 mixing phases (layers 2 and 3): self-contained per warp group ---------------------------------------------
 // Warp group g (4 warps = the 4 TMEM lane quarters) owns window n = g: it stages the two M-tiles (position halves j) of

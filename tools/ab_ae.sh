@@ -1,7 +1,7 @@
 #!/bin/bash
 cp coskad_b200/libcoskad_b200.so /tmp/orig.so
 for rep in 1 2; do for v in "$@"; do
-  cp scratch/variants/$v.so coskad_b200/libcoskad_b200.so
-  echo "== $v"; timeout 200 python scratch/ae_bench.py 2>&1 | tail -3
+  cp tools/variants/$v.so coskad_b200/libcoskad_b200.so
+  echo "== $v"; timeout 200 python tools/ae_bench.py 2>&1 | tail -3
 done; done
 cp /tmp/orig.so coskad_b200/libcoskad_b200.so

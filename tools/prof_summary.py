@@ -1,4 +1,4 @@
-"""usage: python scratch/prof_summary.py gpurun_out/prof.ncu-rep profiles/name.md "title" """
+"""usage: python tools/prof_summary.py gpurun_out/prof.ncu-rep profiles/name.md "title" """
 import csv, subprocess, sys, io, collections
 rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
