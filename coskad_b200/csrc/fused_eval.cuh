@@ -288,7 +288,7 @@ struct EpiHead {
 
 template <bool kDec>
 __global__ void __launch_bounds__(kThreads, 1) fused_eval_kernel(const __grid_constant__ FusedParams P) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* R0 = smem;
   float* R1 = R0 + kRBig;
   float* XB = R1 + kRBig;            // 2 x kRSmall

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(128, 1) tc_mix_test_kernel(const float* __rest
   float* bl = sm + N * K;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int stage = swap_strides >> 4;   // debug bisection: 1 = alloc only, 2 = + st, 3 = + mma, 0 = everything
   swap_strides &= 1;
   for (int i = tid; i < N * K; i += blockDim.x) { bh[i] = Bhi[i]; bl[i] = Blo[i]; }

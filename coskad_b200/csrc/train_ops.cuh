@@ -103,7 +103,7 @@ __device__ __forceinline__ void contract_load_rows(float* dst, const float* __re
 __global__ void __launch_bounds__(kCThreads, 1) train_contract_fwd_kernel(const float* __restrict__ X, const float* __restrict__ A,
                                                                          const float* __restrict__ T, int64_t R,
                                                                          float* __restrict__ G1, float* __restrict__ G) {
-  extern __shared__ __align__(16) float csm[];
+  extern __shared__ __align__(128) float csm[];
   float* Xs = csm;
   float* Gs = Xs + kCRows * kCS;
   float* Ts = Gs + kCRows * kCS;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_fwd_kernel(const 
 __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
     const float* __restrict__ dG, const float* __restrict__ dXres, const float* __restrict__ X, const float* __restrict__ G1,
     const float* __restrict__ A, const float* __restrict__ T, int64_t R, float* __restrict__ dX, float* dA, float* dT) {
-  extern __shared__ __align__(16) float csm[];
+  extern __shared__ __align__(128) float csm[];
   float* P0 = csm;                                 // dG -> dG1 (in place)
   float* P1 = P0 + kCRows * kCS;                   // G1, then X, then dX
   float* Tt = P1 + kCRows * kCS;                   // Tt[v][q][t] = T[v][t][q]
@@ -241,7 +241,7 @@ __global__ void train_mix_fwd_kernel(const float* __restrict__ G, const float* _
                                      const float* __restrict__ W1, const float* __restrict__ b1,
                                      const float* __restrict__ W2, const float* __restrict__ b2, int64_t B, int CO,
                                      float* __restrict__ y1, float* __restrict__ y2, double* stats) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(128) float sm[];
   float* w1s = sm;                 // [CO][CI]
   float* w2s = sm + CO * CI;       // [CO][CI]
   float* red = w2s + CO * CI;      // [4][CO]
@@ -389,7 +389,7 @@ template <int CO>
 __global__ void train_mix_bwd_data_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
                                           const float* __restrict__ W1, const float* __restrict__ W2, int64_t B, int CI,
                                           float* __restrict__ dG, float* __restrict__ dXres) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(128) float sm[];
   float* w1s = sm;                 // [CO][CI]
   float* w2s = sm + CO * CI;
   for (int i = threadIdx.x; i < CO * CI; i += blockDim.x) { w1s[i] = W1[i]; w2s[i] = W2[i]; }
@@ -422,7 +422,7 @@ constexpr int kWCS = kWC + 4;
 __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
     const float* __restrict__ dy1, const float* __restrict__ dy2, const float* __restrict__ G, const float* __restrict__ X,
     int64_t B, int CI, int CO, float* dW1, float* db1, float* dW2, float* db2) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm[];
   float* d1s = sm;                       // [CO][kWCS]
   float* d2s = d1s + CO * kWCS;          // [CO][kWCS]
   float* gs = d2s + CO * kWCS;           // [CI][kWCS]
