@@ -572,13 +572,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const float b = bias[c0 + u];
-            // 4 x LDG.128: the 16 latent rows of feature (c0+u, p), as 8 (d, d+1) pairs
+            // 4 x LDG.128 (streamed once per tile: no L1 allocation): the 16 latent rows of feature (c0+u, p), as 8 (d, d+1) pairs
             const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(Pm.head_w4) + static_cast<size_t>((c0 + u) * (kDP / 4)) * kP + p;
             unsigned long long w2[kDP / 2];
 #pragma unroll
             for (int dq = 0; dq < kDP / 4; ++dq) {
-              const ulonglong2 w = __ldg(wp + dq * kP);
-              w2[2 * dq] = w.x; w2[2 * dq + 1] = w.y;
+              asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
+                           : "=l"(w2[2 * dq]), "=l"(w2[2 * dq + 1]) : "l"(wp + dq * kP));
             }
 #pragma unroll
             for (int n = 0; n < kNW; ++n) {
