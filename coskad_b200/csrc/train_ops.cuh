@@ -454,17 +454,21 @@ __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
       int64_t b = b0;
       if (p >= kP) { p -= kP; b += 1; }
       const bool valid = e0 + k < E;
+      // asynchronous copies: every load of the chunk is in flight at once (a load -> store loop exposed the full memory
+      // latency 96 times per chunk); the zero fill of the ragged tail uses plain stores
       for (int c = threadIdx.x / kWC; c < CO + CI; c += kTrainThreads / kWC) {
         if (c < CO) {
           const int64_t o = (b * CO + c) * kP + p;
-          d1s[c * kWCS + k] = valid ? dy1[o] : 0.f;
-          d2s[c * kWCS + k] = valid ? dy2[o] : 0.f;
+          if (valid) { cp_async4(d1s + c * kWCS + k, dy1 + o); cp_async4(d2s + c * kWCS + k, dy2 + o); }
+          else { d1s[c * kWCS + k] = 0.f; d2s[c * kWCS + k] = 0.f; }
         } else {
           const int64_t o = (b * CI + (c - CO)) * kP + p;
-          gs[(c - CO) * kWCS + k] = valid ? G[o] : 0.f;
-          xs[(c - CO) * kWCS + k] = valid ? X[o] : 0.f;
+          if (valid) { cp_async4(gs + (c - CO) * kWCS + k, G + o); cp_async4(xs + (c - CO) * kWCS + k, X + o); }
+          else { gs[(c - CO) * kWCS + k] = 0.f; xs[(c - CO) * kWCS + k] = 0.f; }
         }
       }
+      cp_async_commit();
+      cp_async_wait_all();
     }
     __syncthreads();
     if (active) {
@@ -514,42 +518,71 @@ __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
 // ---- linear layers over the flattened features ------------------------------------------------------
 // W(d, f) = W[d*sd + f*sf]:  btlnk / fc_* weight [D,F]: sd = F, sf = 1;  rev_btlnk weight [F,D]: sd = 1, sf = D
 // out[b,d] = sum_f A[b,f] W(d,f) + bias[d]           (wide-in: head forward, rev_btlnk input gradient)
+// one block per kLinRows rows b: every weight fetched from L2 feeds kLinRows FMAs (one row per block re-read all of W per row)
+constexpr int kLinRows = 4;
 template <int DMAX>
 __global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __restrict__ W, int64_t sd, int64_t sf,
                                     const float* __restrict__ bias, int64_t B, int F, int D, float* __restrict__ out) {
-  const int64_t b = blockIdx.x;
-  if (b >= B) return;
-  float acc[DMAX];
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kLinRows;
+  if (b0 >= B) return;
+  float acc[kLinRows][DMAX];
 #pragma unroll
-  for (int d = 0; d < DMAX; ++d) acc[d] = 0.f;
+  for (int r = 0; r < kLinRows; ++r)
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) acc[r][d] = 0.f;
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    const float a = A[b * F + f];
+    float a[kLinRows];
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) if (d < D) acc[d] = fmaf(a, W[d * sd + f * sf], acc[d]);
+    for (int r = 0; r < kLinRows; ++r) a[r] = (b0 + r < B) ? A[(b0 + r) * F + f] : 0.f;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) {
+      if (d < D) {
+        const float w = W[d * sd + f * sf];
+#pragma unroll
+        for (int r = 0; r < kLinRows; ++r) acc[r][d] = fmaf(a[r], w, acc[r][d]);
+      }
+    }
   }
-  __shared__ float sh[DMAX][8];
+  __shared__ float sh[kLinRows][DMAX][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int d = 0; d < DMAX; ++d) { const float s = warp_sum(acc[d]); if (lane == 0) sh[d][warp] = s; }
+  for (int r = 0; r < kLinRows; ++r)
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) { const float s = warp_sum(acc[r][d]); if (lane == 0) sh[r][d][warp] = s; }
   __syncthreads();
-  if (threadIdx.x < D) {
-    float s = bias ? bias[threadIdx.x] : 0.f;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
-    out[b * D + threadIdx.x] = s;
+  if (threadIdx.x < kLinRows * DMAX) {
+    const int r = threadIdx.x / DMAX, d = threadIdx.x % DMAX;
+    if (d < D && b0 + r < B) {
+      float s = bias ? bias[d] : 0.f;
+      for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[r][d][w];
+      out[(b0 + r) * D + d] = s;
+    }
   }
 }
 // out[b,f] = sum_d a[b,d] W(d,f) + bias[f]           (wide-out: rev_btlnk forward, head input gradient)
+// grid (ceil(F/256), ceil(B/kExpRows)): a thread keeps the D weights of its feature f in registers for kExpRows rows b
+constexpr int kExpRows = 32;
 template <int DMAX>
 __global__ void lin_expand_f_kernel(const float* __restrict__ a, const float* __restrict__ W, int64_t sd, int64_t sf,
                                     const float* __restrict__ bias, int64_t B, int F, int D, float* __restrict__ out) {
-  const int64_t n = B * F;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t b = e / F;
-    const int f = static_cast<int>(e - b * F);
-    float s = bias ? bias[f] : 0.f;
+  __shared__ float as[kExpRows][DMAX];
+  const int64_t b0 = static_cast<int64_t>(blockIdx.y) * kExpRows;
+  for (int i = threadIdx.x; i < kExpRows * DMAX; i += blockDim.x) {
+    const int r = i / DMAX, d = i % DMAX;
+    as[r][d] = (d < D && b0 + r < B) ? a[(b0 + r) * D + d] : 0.f;
+  }
+  __syncthreads();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float w[DMAX];
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) if (d < D) s = fmaf(a[b * D + d], W[d * sd + f * sf], s);
-    out[e] = s;
+  for (int d = 0; d < DMAX; ++d) w[d] = (d < D) ? W[d * sd + f * sf] : 0.f;
+  const float bf = bias ? bias[f] : 0.f;
+  for (int r = 0; r < kExpRows && b0 + r < B; ++r) {
+    float s = bf;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) s = fmaf(as[r][d], w[d], s);
+    out[(b0 + r) * F + f] = s;
   }
 }
 // dW(d,f) += sum_b a[b,d] A[b,f];  grid (ceil(F/256), NB)
