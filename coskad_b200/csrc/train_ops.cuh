@@ -91,11 +91,35 @@ constexpr int kCSmemFloats = 2 * kCRows * kCS + kTwFloats + kAwFloats;
 constexpr int kCSmemBytes = kCSmemFloats * 4;
 static_assert(kCSmemBytes <= 227 * 1024, "contraction kernels: shared memory plan exceeds 227 KB");
 
+// (row, p) of element i = tid + j * kCThreads of a row block, advanced without a division: 384 = 204 + 180
+struct RowCursor {
+  int row, p;
+  __device__ __forceinline__ explicit RowCursor(int tid) : row(tid / kP), p(tid % kP) {}
+  __device__ __forceinline__ void next() { row += 1; p += kCThreads - kP; if (p >= kP) { p -= kP; row += 1; } }
+};
+static_assert(kCThreads > kP && kCThreads < 2 * kP, "RowCursor step");
+
 __device__ __forceinline__ void contract_load_rows(float* dst, const float* __restrict__ src, int64_t r0, int nr, int tid) {
-  for (int i = tid; i < kCRows * kP; i += kCThreads) {
-    const int row = i / kP, p = i - row * kP;
-    const int rr = row < nr ? row : nr - 1;            // ragged last block: replicate the last row, never stored
-    cp_async4(dst + row * kCS + p, src + (r0 + rr) * kP + p);
+  RowCursor c(tid);
+  for (int i = tid; i < kCRows * kP; i += kCThreads, c.next()) {
+    const int rr = c.row < nr ? c.row : nr - 1;          // ragged last block: replicate the last row, never stored
+    cp_async4(dst + c.row * kCS + c.p, src + (r0 + rr) * kP + c.p);
+  }
+}
+// dst rows [r0, r0+nr) = planes (+ add, nullable); the loads of `add` are batched so that their latency is paid once per batch
+__device__ __forceinline__ void contract_store_rows(float* __restrict__ dst, const float* planes, const float* __restrict__ add,
+                                                    int64_t r0, int nr, int tid) {
+  constexpr int kBatch = 17;                              // kCRows * kP / kCThreads = 51 = 3 x 17
+  static_assert((kCRows * kP) % (kCThreads * kBatch) == 0, "row-block store plan");
+  RowCursor c(tid);
+  for (int b = 0; b < (kCRows * kP) / (kCThreads * kBatch); ++b) {
+    float a[kBatch];
+    RowCursor cl = c;
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j, cl.next()) a[j] = (add != nullptr && cl.row < nr) ? __ldg(add + (r0 + cl.row) * kP + cl.p) : 0.f;
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j, c.next())
+      if (c.row < nr) dst[(r0 + c.row) * kP + c.p] = planes[c.row * kCS + c.p] + a[j];
   }
 }
 
@@ -129,11 +153,11 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_fwd_kernel(const 
       if (nb < nblk) { const int64_t n0 = nb * kCRows; contract_load_rows(Xs, X, n0, static_cast<int>(R - n0 < kCRows ? R - n0 : kCRows), tid); }
       cp_async_commit();
     }
-    for (int i = tid; i < nr * kP; i += kCThreads) { const int row = i / kP, p = i - row * kP; G1[(r0 + row) * kP + p] = Gs[row * kCS + p]; }
+    contract_store_rows(G1, Gs, nullptr, r0, nr, tid);
     __syncthreads();
     spatial_stage_c32<kCWarps>(Gs, As, warp, lane);
     __syncthreads();
-    for (int i = tid; i < nr * kP; i += kCThreads) { const int row = i / kP, p = i - row * kP; G[(r0 + row) * kP + p] = Gs[row * kCS + p]; }
+    contract_store_rows(G, Gs, nullptr, r0, nr, tid);
   }
   cp_async_wait_all();
 }
@@ -213,11 +237,7 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
     __syncthreads();
     temporal_stage_c32<kCWarps>(P0, P1, Tt, warp, lane);      // dG1 -> temporal^T -> P1 (X is dead)
     __syncthreads();
-    for (int i = tid; i < nr * kP; i += kCThreads) {
-      const int row = i / kP, p = i - row * kP;
-      const int64_t o = (r0 + row) * kP + p;
-      dX[o] = P1[row * kCS + p] + (dXres != nullptr ? dXres[o] : 0.f);
-    }
+    contract_store_rows(dX, P1, dXres, r0, nr, tid);
   }
   if (hasA) {
 #pragma unroll
