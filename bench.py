@@ -159,9 +159,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL prints its banner ("NCCL version ...") on stdout when NCCL_DEBUG is VERSION/INFO: keep stdout = the JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its banner ("NCCL version ...") on fd 1 when the communicator is created: point fd 1 at stderr while
+        # the process group and its communicator come up, so that stdout carries nothing but the JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     model = make_model('stse', 16, seed=0, device=dev)     # random init, randomised BN statistics
     W = args.windows_per_step

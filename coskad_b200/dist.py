@@ -44,27 +44,16 @@ class FlatGradBucket:
     def allreduce_(self) -> None:
         if not is_dist() or not self.params:
             return
-        dev = self.params[0].device
-        if self.flat is None or self.flat.device != dev:
-            self.flat = torch.empty(self.numel, dtype=torch.float32, device=dev)
-        off = 0
+        # one concatenation kernel in, one multi-tensor copy out (instead of two tiny copies per parameter)
         for p in self.params:
-            n = p.numel()
             if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.params]
+        self.flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.flat.div_(world())
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = self.flat[off:off + n].view_as(p).clone()
-            else:
-                p.grad.copy_(self.flat[off:off + n].view_as(p))
-            off += n
+        views = [v.view_as(g) for v, g in zip(torch.split(self.flat, [g.numel() for g in grads]), grads)]
+        torch._foreach_copy_(grads, views)
 
 
 def gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:

@@ -5,11 +5,20 @@ import torch
 from coskad_b200 import synth, gmath, _lib
 from coskad_b200.losses import calc_reg_loss
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-dev = torch.device('cuda', 0)
+import torch.distributed as dist
+from coskad_b200 import dist as cdist
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048      # windows per GPU per step (dataset_batch_size of the configs)
+world, rank, local = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+if world > 1:
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    dist.init_process_group('nccl', device_id=dev)
 m = synth.make_model('stse', 16, seed=0, device=dev).train()
+cdist.broadcast_module_(m)
+bucket = cdist.FlatGradBucket(m.parameters())
 opt = torch.optim.Adam(m.parameters(), lr=1e-4)
-g = torch.Generator(device=dev).manual_seed(999)
+g = torch.Generator(device=dev).manual_seed(999 + rank)
 x = torch.empty(B, 2, 12, 17, device=dev)
 synth.synth_windows_(x, g)
 c = torch.zeros(16, device=dev); c[0] = 0.1
@@ -23,17 +32,26 @@ def step():
     loss = dist_c.mean() + 1e-6 * reg
     opt.zero_grad(set_to_none=True)
     loss.backward()
+    bucket.allreduce_()                                   # flat NCCL all-reduce of the gradients (no-op on one GPU)
     opt.step()
     return loss
 
 for _ in range(5): step()
 torch.cuda.synchronize()
+if world > 1: dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 N = 20
 t0 = time.perf_counter(); e0.record()
 for _ in range(N): l = step()
 e1.record(); torch.cuda.synchronize(); t1 = time.perf_counter()
+cdist.allreduce_center_acc(acc)                       # dynamic center: 18 doubles once per epoch
 ms = e0.elapsed_time(e1) / N
+if world > 1:
+    t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    if rank != 0:
+        dist.destroy_process_group(); sys.exit(0)
+    print(f'{world} GPUs x B={B}: {ms:.3f} ms/step (max over ranks) -> {world*B/ms*1e3:.0f} windows/s')
+    dist.destroy_process_group(); sys.exit(0)
 print(f'B={B}: {ms:.3f} ms/step (device), {(t1-t0)/N*1e3:.3f} ms/step (wall) -> {B/ms*1e3:.0f} windows/s, loss {float(l):.4f}')
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
