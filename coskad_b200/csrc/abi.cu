@@ -637,7 +637,7 @@ extern "C" int coskad_train_bn_prelu_fwd(coskad_ctx* ctx, const float* y1, const
                                          const float* slope, int64_t B, int CO, float* out, void* stream_) {
   TRAIN_PRE();
   if (B <= 0) return COSKAD_OK;
-  train_bn_prelu_fwd_kernel<<<ew_grid(ctx, B * CO * kP), kTrainThreads, 0, st>>>(y1, y2, mi, g1, be1, g2, be2, slope, B, CO, out);
+  train_bn_prelu_fwd_kernel<<<ew_grid(ctx, B * CO * 32), kTrainThreads, 0, st>>>(y1, y2, mi, g1, be1, g2, be2, slope, B, CO, out);
   CK_LAUNCH();
   return COSKAD_OK;
 }
@@ -653,7 +653,7 @@ extern "C" int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, con
   if (nb > cap) nb = cap;
   train_bn_prelu_bwd_reduce_kernel<<<dim3(CO, nb), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, B, CO, red);
   CK_LAUNCH();
-  train_bn_prelu_bwd_apply_kernel<<<ew_grid(ctx, B * CO * kP), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2,
+  train_bn_prelu_bwd_apply_kernel<<<ew_grid(ctx, B * CO * 32), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2,
                                                                                     slope, red, B, CO, dy1, dy2);
   CK_LAUNCH();
   return COSKAD_OK;

@@ -327,20 +327,34 @@ __device__ __forceinline__ float bn_pre(float y1, float y2, float m1, float i1, 
 // nn.PReLU: positive branch iff x > 0 (ATen prelu backward uses the same strict comparison)
 __device__ __forceinline__ float prelu_strict(float v, float a) { return v > 0.f ? v : a * v; }
 
-// out = PReLU(BN1(y1) + BN2(y2))
+// out = PReLU(BN1(y1) + BN2(y2)).  One warp per row (b, co) of 204 positions = 51 float4: the per-channel constants are
+// fetched once per row instead of once per element, 16-byte loads and stores.
+constexpr int kRowV4 = kP / 4;                                   // 51
 __global__ void train_bn_prelu_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ y2,
                                           const float* __restrict__ mi, const float* __restrict__ g1,
                                           const float* __restrict__ be1, const float* __restrict__ g2,
                                           const float* __restrict__ be2, const float* __restrict__ slope, int64_t B,
                                           int CO, float* __restrict__ out) {
-  const int64_t n = B * CO * kP;
+  const int64_t rows = B * CO;
   const float a = slope[0];
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int co = static_cast<int>((e / kP) % CO);
-    float h1, h2;
-    const float pre = bn_pre(y1[e], y2[e], mi[co], mi[CO + co], mi[2 * CO + co], mi[3 * CO + co], g1[co], be1[co], g2[co],
-                             be2[co], h1, h2);
-    out[e] = prelu_strict(pre, a);
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows; r += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int co = static_cast<int>(r % CO);
+    const float m1 = mi[co], i1 = mi[CO + co], m2 = mi[2 * CO + co], i2 = mi[3 * CO + co];
+    const float ga1 = g1[co], bb1 = be1[co], ga2 = g2[co], bb2 = be2[co];
+    const float4* a1 = reinterpret_cast<const float4*>(y1 + r * kP);
+    const float4* a2 = reinterpret_cast<const float4*>(y2 + r * kP);
+    float4* o = reinterpret_cast<float4*>(out + r * kP);
+    for (int i = lane; i < kRowV4; i += 32) {
+      const float4 u = a1[i], v = a2[i];
+      float h1, h2;
+      float4 w;
+      w.x = prelu_strict(bn_pre(u.x, v.x, m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2), a);
+      w.y = prelu_strict(bn_pre(u.y, v.y, m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2), a);
+      w.z = prelu_strict(bn_pre(u.z, v.z, m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2), a);
+      w.w = prelu_strict(bn_pre(u.w, v.w, m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2), a);
+      o[i] = w;
+    }
   }
 }
 
@@ -359,13 +373,21 @@ __global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int64_t b = static_cast<int64_t>(blockIdx.y) * nwarp + warp; b < B; b += static_cast<int64_t>(gridDim.y) * nwarp) {
     const int64_t base = (b * CO + co) * kP;
-    for (int p = lane; p < kP; p += 32) {
-      float h1, h2;
-      const float pre = bn_pre(y1[base + p], y2[base + p], m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2);
-      const float d = dout[base + p];
-      const float ds = pre > 0.f ? d : a * d;
-      s0 += ds; s1 = fmaf(ds, h1, s1); s2 = fmaf(ds, h2, s2);
-      if (!(pre > 0.f)) sa = fmaf(d, pre, sa);
+    const float4* a1 = reinterpret_cast<const float4*>(y1 + base);
+    const float4* a2 = reinterpret_cast<const float4*>(y2 + base);
+    const float4* dd = reinterpret_cast<const float4*>(dout + base);
+    for (int i = lane; i < kRowV4; i += 32) {
+      const float4 u = a1[i], v = a2[i], d4 = dd[i];
+      const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float h1, h2;
+        const float pre = bn_pre(uu[k], vv[k], m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2);
+        const float d = dv[k];
+        const float ds = pre > 0.f ? d : a * d;
+        s0 += ds; s1 = fmaf(ds, h1, s1); s2 = fmaf(ds, h2, s2);
+        if (!(pre > 0.f)) sa = fmaf(d, pre, sa);
+      }
     }
   }
   __shared__ float sh[4][8];
@@ -380,27 +402,44 @@ __global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout,
   }
 }
 
-// dy1 = g1*is1*(ds - mean(ds) - yhat1*mean(ds*yhat1)), dy2 likewise (BatchNorm train backward)
+// dy1 = g1*is1*(ds - mean(ds) - yhat1*mean(ds*yhat1)), dy2 likewise (BatchNorm train backward); one warp per row, float4
 __global__ void train_bn_prelu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y1,
                                                 const float* __restrict__ y2, const float* __restrict__ mi,
                                                 const float* __restrict__ g1, const float* __restrict__ be1,
                                                 const float* __restrict__ g2, const float* __restrict__ be2,
                                                 const float* __restrict__ slope, const double* __restrict__ red,
                                                 int64_t B, int CO, float* __restrict__ dy1, float* __restrict__ dy2) {
-  const int64_t n = B * CO * kP;
+  const int64_t rows = B * CO;
   const float a = slope[0];
   const double N = static_cast<double>(B) * kP;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int co = static_cast<int>((e / kP) % CO);
-    float h1, h2;
-    const float pre = bn_pre(y1[e], y2[e], mi[co], mi[CO + co], mi[2 * CO + co], mi[3 * CO + co], g1[co], be1[co], g2[co],
-                             be2[co], h1, h2);
-    const float d = dout[e];
-    const float ds = pre > 0.f ? d : a * d;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows; r += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int co = static_cast<int>(r % CO);
+    const float m1 = mi[co], i1 = mi[CO + co], m2 = mi[2 * CO + co], i2 = mi[3 * CO + co];
+    const float ga1 = g1[co], bb1 = be1[co], ga2 = g2[co], bb2 = be2[co];
     const float mds = static_cast<float>(red[co] / N);
-    const float m1 = static_cast<float>(red[CO + co] / N), m2 = static_cast<float>(red[2 * CO + co] / N);
-    dy1[e] = g1[co] * mi[CO + co] * (ds - mds - h1 * m1);
-    dy2[e] = g2[co] * mi[3 * CO + co] * (ds - mds - h2 * m2);
+    const float mh1 = static_cast<float>(red[CO + co] / N), mh2 = static_cast<float>(red[2 * CO + co] / N);
+    const float sc1 = ga1 * i1, sc2 = ga2 * i2;
+    const float4* a1 = reinterpret_cast<const float4*>(y1 + r * kP);
+    const float4* a2 = reinterpret_cast<const float4*>(y2 + r * kP);
+    const float4* dd = reinterpret_cast<const float4*>(dout + r * kP);
+    float4* o1 = reinterpret_cast<float4*>(dy1 + r * kP);
+    float4* o2 = reinterpret_cast<float4*>(dy2 + r * kP);
+    for (int i = lane; i < kRowV4; i += 32) {
+      const float4 u = a1[i], v = a2[i], d4 = dd[i];
+      const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      float r1[4], r2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float h1, h2;
+        const float pre = bn_pre(uu[k], vv[k], m1, i1, m2, i2, ga1, bb1, ga2, bb2, h1, h2);
+        const float ds = pre > 0.f ? dv[k] : a * dv[k];
+        r1[k] = sc1 * (ds - mds - h1 * mh1);
+        r2[k] = sc2 * (ds - mds - h2 * mh2);
+      }
+      o1[i] = make_float4(r1[0], r1[1], r1[2], r1[3]);
+      o2[i] = make_float4(r2[0], r2[1], r2[2], r2[3]);
+    }
   }
 }
 
