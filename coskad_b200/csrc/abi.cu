@@ -607,18 +607,37 @@ extern "C" int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const
   return COSKAD_OK;
 }
 
+// chan_gemm_kernel launcher: K input channels -> M output channels over B*204 positions
+static int launch_chan_gemm(coskad_ctx* ctx, bool stats_on, const float* in1, const float* in2, const float* Wa, const float* Wb,
+                            int w_is_km, const float* b1, const float* b2, int64_t B, int K, int M, float* out1, float* out2,
+                            double* stats, cudaStream_t st) {
+  const int TM = M < 4 ? M : 4, n_ct = M / TM;
+  const int CE = (n_ct >= kGWarps) ? 128 : 256;          // fewer than 8 output tiles: two 128-position slabs per chunk
+  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(K) * M + 2 * static_cast<size_t>(K) * (CE + 4) + 4 * static_cast<size_t>(M));
+  const int64_t nchunk = (B * kP + CE - 1) / CE;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 2;
+  const int g = static_cast<int>(nchunk < cap ? nchunk : cap);
+  if (stats_on) {
+    CK(cudaFuncSetAttribute(chan_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    chan_gemm_kernel<true><<<g, kGThreads, smem, st>>>(in1, in2, Wa, Wb, w_is_km, b1, b2, B, K, M, CE, out1, out2, stats);
+  } else {
+    CK(cudaFuncSetAttribute(chan_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    chan_gemm_kernel<false><<<g, kGThreads, smem, st>>>(in1, in2, Wa, Wb, w_is_km, b1, b2, B, K, M, CE, out1, out2, stats);
+  }
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
 extern "C" int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1,
                                     const float* W2, const float* b2, int64_t B, int CI, int CO, float* y1, float* y2,
                                     double* stats, void* stream_) {
   TRAIN_PRE();
   if (!chan_ok(CI) || !chan_ok(CO)) return fail(ctx, COSKAD_ERR_ARG, "training kernels support channels {2,16,32,64}, got %d->%d", CI, CO);
   if (B <= 0) return COSKAD_OK;
-  const size_t smem = sizeof(float) * (2 * CO * CI + 4 * CO);
-  const int g = ew_grid(ctx, B * kP);
-#define LAUNCH_MIX(CI_) train_mix_fwd_kernel<CI_><<<g, kTrainThreads, smem, st>>>(G, X, W1, b1, W2, b2, B, CO, y1, y2, stats)
-  switch (CI) { case 2: LAUNCH_MIX(2); break; case 16: LAUNCH_MIX(16); break; case 32: LAUNCH_MIX(32); break; default: LAUNCH_MIX(64); break; }
-#undef LAUNCH_MIX
-  CK_LAUNCH();
+  {
+    const int rc = launch_chan_gemm(ctx, true, G, X, W1, W2, 0, b1, b2, B, CI, CO, y1, y2, stats, st);
+    if (rc) return rc;
+  }
   return COSKAD_OK;
 }
 
@@ -665,12 +684,11 @@ extern "C" int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const flo
   TRAIN_PRE();
   if (!chan_ok(CI) || !chan_ok(CO)) return fail(ctx, COSKAD_ERR_ARG, "training kernels support channels {2,16,32,64}, got %d->%d", CI, CO);
   if (B <= 0) return COSKAD_OK;
-  const size_t smem = sizeof(float) * (2 * CO * CI);
-  const int g = ew_grid(ctx, B * kP);
-#define LAUNCH_BD(CO_) train_mix_bwd_data_kernel<CO_><<<g, kTrainThreads, smem, st>>>(dy1, dy2, W1, W2, B, CI, dG, dXres)
-  switch (CO) { case 2: LAUNCH_BD(2); break; case 16: LAUNCH_BD(16); break; case 32: LAUNCH_BD(32); break; default: LAUNCH_BD(64); break; }
-#undef LAUNCH_BD
-  CK_LAUNCH();
+  {
+    // dG[ci] = sum_co W1[co,ci] dy1[co], dXres[ci] = sum_co W2[co,ci] dy2[co]: K = CO, M = CI, weights already [k][m]
+    const int rc = launch_chan_gemm(ctx, false, dy1, dy2, W1, W2, 1, nullptr, nullptr, B, CO, CI, dG, dXres, nullptr, st);
+    if (rc) return rc;
+  }
   const size_t smem2 = sizeof(float) * 2 * (CO + CI) * kWCS;
   if ((CO >= 4 && CO % 4) || (CI >= 4 && CI % 4) || (CO / (CO < 4 ? CO : 4)) * (CI / (CI < 4 ? CI : 4)) > 128 ||
       (CO / (CO < 4 ? CO : 4)) * (CI / (CI < 4 ? CI : 4)) < 8)

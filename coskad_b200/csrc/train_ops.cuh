@@ -254,50 +254,6 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
   }
 }
 
-// ---- 1x1 convolutions forward + BatchNorm partial statistics ----------------------------------------
-// y1[b,co,p] = sum_ci W1[co,ci] G[b,ci,p] + b1[co];  y2 likewise from X.  stats (double) [4*Co]: sum y1, sum y1^2, sum y2, sum y2^2
-template <int CI>
-__global__ void train_mix_fwd_kernel(const float* __restrict__ G, const float* __restrict__ X,
-                                     const float* __restrict__ W1, const float* __restrict__ b1,
-                                     const float* __restrict__ W2, const float* __restrict__ b2, int64_t B, int CO,
-                                     float* __restrict__ y1, float* __restrict__ y2, double* stats) {
-  extern __shared__ __align__(128) float sm[];
-  float* w1s = sm;                 // [CO][CI]
-  float* w2s = sm + CO * CI;       // [CO][CI]
-  float* red = w2s + CO * CI;      // [4][CO]
-  for (int i = threadIdx.x; i < CO * CI; i += blockDim.x) { w1s[i] = W1[i]; w2s[i] = W2[i]; }
-  for (int i = threadIdx.x; i < 4 * CO; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  const int64_t E = B * kP;
-  const int lane = threadIdx.x & 31;
-  for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * blockDim.x; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t e = e0 + threadIdx.x;
-    const bool valid = e < E;
-    const int64_t b = valid ? e / kP : 0;
-    const int p = valid ? static_cast<int>(e - b * kP) : 0;
-    float g[CI], x[CI];
-#pragma unroll
-    for (int ci = 0; ci < CI; ++ci) {
-      g[ci] = valid ? G[(b * CI + ci) * kP + p] : 0.f;
-      x[ci] = valid ? X[(b * CI + ci) * kP + p] : 0.f;
-    }
-    for (int co = 0; co < CO; ++co) {
-      float a1 = b1 ? b1[co] : 0.f, a2 = b2 ? b2[co] : 0.f;
-#pragma unroll
-      for (int ci = 0; ci < CI; ++ci) { a1 = fmaf(w1s[co * CI + ci], g[ci], a1); a2 = fmaf(w2s[co * CI + ci], x[ci], a2); }
-      if (valid) { y1[(b * CO + co) * kP + p] = a1; y2[(b * CO + co) * kP + p] = a2; }
-      else { a1 = 0.f; a2 = 0.f; }
-      const float s1 = warp_sum(a1), q1 = warp_sum(a1 * a1), s2 = warp_sum(a2), q2 = warp_sum(a2 * a2);
-      if (lane == 0) { atomicAdd(red + co, s1); atomicAdd(red + CO + co, q1); atomicAdd(red + 2 * CO + co, s2); atomicAdd(red + 3 * CO + co, q2); }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 4 * CO; i += blockDim.x) {
-    const int k = i / CO, co = i % CO;
-    atomicAdd(stats + k * CO + co, static_cast<double>(red[i]));
-  }
-}
-
 // mean / invstd from the sums, running-statistics update (momentum 0.1, unbiased variance), nn.BatchNorm2d semantics
 __global__ void train_bn_finalize_kernel(const double* __restrict__ stats, double N, int CO, float eps, float momentum,
                                          float* rm1, float* rv1, float* rm2, float* rv2, float* __restrict__ mi) {
@@ -443,33 +399,6 @@ __global__ void train_bn_prelu_bwd_apply_kernel(const float* __restrict__ dout, 
   }
 }
 
-// dG[b,ci,p] = sum_co W1[co,ci] dy1[b,co,p];  dXres[b,ci,p] = sum_co W2[co,ci] dy2[b,co,p]
-template <int CO>
-__global__ void train_mix_bwd_data_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
-                                          const float* __restrict__ W1, const float* __restrict__ W2, int64_t B, int CI,
-                                          float* __restrict__ dG, float* __restrict__ dXres) {
-  extern __shared__ __align__(128) float sm[];
-  float* w1s = sm;                 // [CO][CI]
-  float* w2s = sm + CO * CI;
-  for (int i = threadIdx.x; i < CO * CI; i += blockDim.x) { w1s[i] = W1[i]; w2s[i] = W2[i]; }
-  __syncthreads();
-  const int64_t E = B * kP;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < E; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t b = e / kP;
-    const int p = static_cast<int>(e - b * kP);
-    float d1[CO], d2[CO];
-#pragma unroll
-    for (int co = 0; co < CO; ++co) { d1[co] = dy1[(b * CO + co) * kP + p]; d2[co] = dy2[(b * CO + co) * kP + p]; }
-    for (int ci = 0; ci < CI; ++ci) {
-      float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-      for (int co = 0; co < CO; ++co) { a1 = fmaf(w1s[co * CI + ci], d1[co], a1); a2 = fmaf(w2s[co * CI + ci], d2[co], a2); }
-      dG[(b * CI + ci) * kP + p] = a1;
-      dXres[(b * CI + ci) * kP + p] = a2;
-    }
-  }
-}
-
 // dW1[co,ci] += sum_e dy1[e,co] G[e,ci]; db1[co] += sum_e dy1[e,co]; same for the residual branch (e = (b,p)).
 // A split-K "GEMM" with tiny M x N (<= 64 x 64) and K = B*204: every block stages chunks of kWC elements e of all channels
 // in shared memory as rows [c][kWC + 4] (row stride = 4 mod 32 banks: LDS.128 of 8 consecutive rows is conflict free),
@@ -571,6 +500,151 @@ __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
       }
       if (cit == 0) { if (db1) atomicAdd(db1 + co, bs1[i]); if (db2) atomicAdd(db2 + co, bs2[i]); }
     }
+  }
+}
+
+// ---- 1x1 convolutions as a register-tiled GEMM over positions ---------------------------------------------------------
+// out1[m, e] = sum_k Wa(m,k) in1[k, e] (+ bias1[m]);  out2 likewise from in2 / Wb / bias2;  e = (b, p) flattened, tensors
+// stored [b][C][204].  Forward: in = (G, X), W = (tcn conv, residual conv) [M = c_out][K = c_in], optional BatchNorm
+// statistics (double) [4*M] += sum out1, sum out1^2, sum out2, sum out2^2.  Backward data: in = (dy1, dy2), W used
+// transposed (dG[ci] = sum_co W1[co,ci] dy1[co]): w_is_km = 1, no bias, no statistics.
+// A block stages the weights once as [k][m] and walks chunks of CE positions: the two input tiles live in shared memory as
+// [k][CE + 4]; a warp owns a slab of 128 positions (lane = 4 consecutive positions) and up to two 4-row output tiles, so
+// that one broadcast LDS.128 of weights and one LDS.128 of inputs feed 16 FMAs (the per-position kernels this replaces
+// paid one shared-memory load per FMA, and 20 shuffles per output channel for the statistics).
+constexpr int kGThreads = 256;
+constexpr int kGWarps = kGThreads / 32;
+template <bool STATS>
+__global__ void __launch_bounds__(kGThreads) chan_gemm_kernel(const float* __restrict__ in1, const float* __restrict__ in2,
+                                                              const float* __restrict__ Wa, const float* __restrict__ Wb,
+                                                              int w_is_km, const float* __restrict__ bias1,
+                                                              const float* __restrict__ bias2, int64_t B, int K, int M, int CE,
+                                                              float* __restrict__ out1, float* __restrict__ out2, double* stats) {
+  extern __shared__ __align__(128) float sm[];
+  const int CES = CE + 4;
+  float* wa = sm;                        // [K][M]
+  float* wb = wa + K * M;
+  float* ia = wb + K * M;                // [K][CES]
+  float* ib = ia + K * CES;
+  float* red = ib + K * CES;             // [4][M]  (STATS)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < K * M; i += kGThreads) {
+    const int k = i / M, m = i % M;
+    wa[i] = w_is_km ? Wa[k * M + m] : Wa[m * K + k];
+    wb[i] = w_is_km ? Wb[k * M + m] : Wb[m * K + k];
+  }
+  if (STATS) for (int i = tid; i < 4 * M; i += kGThreads) red[i] = 0.f;
+  const int TM = M < 4 ? M : 4;
+  const int n_ct = M / TM;               // output-row tiles: 16, 8, 4 or 1
+  const int nslab = CE / 128;            // 1 or 2
+  // warp -> (slab, first tile, number of tiles): n_ct >= 8: slab 0, tiles warp, warp + 8; else one tile, slab = warp / n_ct
+  const int slab = n_ct >= kGWarps ? 0 : warp / n_ct;
+  const int ct0 = n_ct >= kGWarps ? warp : warp % n_ct;
+  const int nct = n_ct >= kGWarps ? n_ct / kGWarps : (slab < nslab ? 1 : 0);
+  const int64_t E = B * kP;
+  const int v4_per_row = CE / 4;
+  for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * CE; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * CE) {
+    __syncthreads();
+    // stage the input tiles with 16-byte loads: 4 consecutive positions never straddle a window (204 = 4 * 51, e0 % 4 == 0)
+    for (int i0 = tid; i0 < K * v4_per_row; i0 += kGThreads * 4) {
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * kGThreads;
+        va[j] = make_float4(0.f, 0.f, 0.f, 0.f); vb[j] = va[j];
+        if (i < K * v4_per_row) {
+          const int k = i / v4_per_row, c4 = i - k * v4_per_row;
+          const int64_t e = e0 + 4 * c4;
+          if (e < E) {
+            const int64_t b = e / kP;
+            const int p = static_cast<int>(e - b * kP);
+            va[j] = __ldg(reinterpret_cast<const float4*>(in1 + (b * K + k) * kP + p));
+            vb[j] = __ldg(reinterpret_cast<const float4*>(in2 + (b * K + k) * kP + p));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * kGThreads;
+        if (i < K * v4_per_row) {
+          const int k = i / v4_per_row, c4 = i - k * v4_per_row;
+          *reinterpret_cast<float4*>(ia + k * CES + 4 * c4) = va[j];
+          *reinterpret_cast<float4*>(ib + k * CES + 4 * c4) = vb[j];
+        }
+      }
+    }
+    __syncthreads();
+    if (nct > 0) {
+      const int el = slab * 128 + lane * 4;                 // this lane's 4 positions inside the chunk
+      float a1[2][4][4], a2[2][4][4];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { a1[c][i][j] = 0.f; a2[c][i][j] = 0.f; }
+      for (int k = 0; k < K; ++k) {
+        const float4 xa = *reinterpret_cast<const float4*>(ia + k * CES + el);
+        const float4 xb = *reinterpret_cast<const float4*>(ib + k * CES + el);
+        const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < nct) {
+            const int m0 = (ct0 + c * kGWarps) * TM;
+            float wav[4], wbv[4];
+            if (TM == 4) {
+              const float4 w1 = *reinterpret_cast<const float4*>(wa + k * M + m0);
+              const float4 w2 = *reinterpret_cast<const float4*>(wb + k * M + m0);
+              wav[0] = w1.x; wav[1] = w1.y; wav[2] = w1.z; wav[3] = w1.w;
+              wbv[0] = w2.x; wbv[1] = w2.y; wbv[2] = w2.z; wbv[3] = w2.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { wav[i] = i < TM ? wa[k * M + m0 + i] : 0.f; wbv[i] = i < TM ? wb[k * M + m0 + i] : 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { a1[c][i][j] = fmaf(wav[i], xav[j], a1[c][i][j]); a2[c][i][j] = fmaf(wbv[i], xbv[j], a2[c][i][j]); }
+          }
+        }
+      }
+      const int64_t e = e0 + el;
+      const bool valid = e < E;                             // E % 4 == 0: the 4 positions are valid together
+      const int64_t b = valid ? e / kP : 0;
+      const int p = valid ? static_cast<int>(e - b * kP) : 0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c < nct) {
+          const int m0 = (ct0 + c * kGWarps) * TM;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < TM) {
+              const int m = m0 + i;
+              const float bb1 = bias1 ? bias1[m] : 0.f, bb2 = bias2 ? bias2[m] : 0.f;
+              const float4 o1 = make_float4(a1[c][i][0] + bb1, a1[c][i][1] + bb1, a1[c][i][2] + bb1, a1[c][i][3] + bb1);
+              const float4 o2 = make_float4(a2[c][i][0] + bb2, a2[c][i][1] + bb2, a2[c][i][2] + bb2, a2[c][i][3] + bb2);
+              if (valid) {
+                *reinterpret_cast<float4*>(out1 + (b * M + m) * kP + p) = o1;
+                *reinterpret_cast<float4*>(out2 + (b * M + m) * kP + p) = o2;
+              }
+              if (STATS) {
+                float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
+                if (valid) {
+                  s1 = (o1.x + o1.y) + (o1.z + o1.w); q1 = fmaf(o1.x, o1.x, fmaf(o1.y, o1.y, fmaf(o1.z, o1.z, o1.w * o1.w)));
+                  s2 = (o2.x + o2.y) + (o2.z + o2.w); q2 = fmaf(o2.x, o2.x, fmaf(o2.y, o2.y, fmaf(o2.z, o2.z, o2.w * o2.w)));
+                }
+                s1 = warp_sum(s1); q1 = warp_sum(q1); s2 = warp_sum(s2); q2 = warp_sum(q2);
+                if (lane == 0) { atomicAdd(red + m, s1); atomicAdd(red + M + m, q1); atomicAdd(red + 2 * M + m, s2); atomicAdd(red + 3 * M + m, q2); }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (STATS) {
+    __syncthreads();
+    for (int i = tid; i < 4 * M; i += kGThreads) atomicAdd(stats + i, static_cast<double>(red[i]));
   }
 }
 
