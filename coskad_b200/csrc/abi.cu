@@ -272,8 +272,8 @@ static int launch_encode_score(coskad_ctx* ctx, int flavour, const float* x, con
                                const float* center, int64_t B, float* z, float* score, void* stream_) {
   if (!ctx->enc_set) return fail(ctx, COSKAD_ERR_STATE, "coskad_set_encoder has not been called");
   if (flavour < COSKAD_SCORE_NONE || flavour > COSKAD_SCORE_POINCARE_HM) return fail(ctx, COSKAD_ERR_ARG, "unknown flavour %d", flavour);
+  if (B == 0) return COSKAD_OK;                      // empty batch: nothing to do (its output pointers may be NULL)
   if (flavour != COSKAD_SCORE_NONE && (!score || !center)) return fail(ctx, COSKAD_ERR_ARG, "score/center is NULL for flavour %d", flavour);
-  if (B == 0) return COSKAD_OK;
   CK(cudaSetDevice(ctx->device));
   int rc = ensure_smem_attr(ctx);
   if (rc) return rc;

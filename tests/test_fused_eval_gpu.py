@@ -172,3 +172,37 @@ def test_full_size_properties():
     _, s2 = m.encode_score(x[100_001:].contiguous(), 1, center=c)
     assert torch.equal(torch.cat([s1, s2]), s)
     assert bool(torch.isfinite(s).all()) and float(s.min()) >= 0
+
+
+def test_empty_batch_and_bad_arguments():
+    """B = 0 is a no-op that returns empty tensors; wrong shapes / missing center fail loudly (no silent fallback)"""
+    from coskad_b200 import _lib
+    m, _ = make_pair('stse', 16, seed=0)
+    z, s = m.encode_score(torch.empty(0, 2, 12, 17, device='cuda'), 1, center=torch.zeros(16, device='cuda'))
+    assert z.shape == (0, 16) and s.shape == (0,)
+    ae, _ = make_pair('stsae', 8, seed=1)
+    z, xh, rs, ls = ae.autoencode_score(torch.empty(0, 2, 12, 17, device='cuda'), center=torch.zeros(8, device='cuda'))
+    assert z.shape == (0, 8) and xh.shape == (0, 2, 12, 17) and rs.shape == (0,) and ls.shape == (0,)
+    zt, st = m.encode_score_traj(torch.zeros(12, 34, device='cuda'), torch.zeros(0, dtype=torch.int64, device='cuda'),
+                                 flavour=1, center=torch.zeros(16, device='cuda'))
+    assert zt.shape == (0, 16) and st.shape == (0,)
+    with pytest.raises((ValueError, _lib.CoskadError)):
+        m.encode_score(torch.zeros(4, 2, 12, 16, device='cuda'))               # 16 joints: the kernels are built for 17
+    with pytest.raises((ValueError, _lib.CoskadError)):
+        m.encode_score(torch.zeros(4, 3, 12, 17, device='cuda'))               # 3 coordinates
+    with pytest.raises((ValueError, _lib.CoskadError, RuntimeError, TypeError)):
+        m.encode_score(torch.zeros(4, 2, 12, 17))                               # host tensor: there is no CPU path
+
+
+def test_scores_invariant_to_launch_geometry():
+    """a window's score does not depend on which tile / CTA / position inside the tile it lands in"""
+    m, _ = make_pair('stse', 16, seed=0)
+    g = torch.Generator(device='cuda').manual_seed(7)
+    x = (torch.randn(1000, 2, 12, 17, device='cuda', generator=g) * 0.4).clamp_(-3, 3)
+    c = torch.full((16,), 0.01, device='cuda')
+    _, s = m.encode_score(x, 1, center=c)
+    for off in (1, 2, 5):
+        _, s2 = m.encode_score(x[off:].contiguous(), 1, center=c)
+        assert torch.equal(s2, s[off:])
+    _, s1 = m.encode_score(x[:1].contiguous(), 1, center=c)
+    assert torch.equal(s1, s[:1])
