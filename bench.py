@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=4096, help='windows per CPU-baseline pass')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-chunk', type=int, default=16384, help='windows per H2D chunk / kernel launch of the e2e leg')
     return ap.parse_args()
 
 
@@ -231,7 +232,7 @@ def run_ours(args):
     e2e = None
     e2e_traj = None
     if not args.no_e2e:
-        hs = HostScorer(model, _lib.SCORE_POINCARE, chunk=131072, device=local)
+        hs = HostScorer(model, _lib.SCORE_POINCARE, chunk=args.e2e_chunk, device=local)
         xh = torch.empty((W, 2, 12, 17), dtype=torch.float32).pin_memory()
         xh.copy_(x[:W])
         oh = torch.empty(W, dtype=torch.float32).pin_memory()

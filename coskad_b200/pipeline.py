@@ -24,9 +24,13 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class HostScorer:
-    """Double-buffered H2D -> fused kernel -> D2H pipeline around ``STSE.encode_score``."""
+    """Double-buffered H2D -> fused kernel -> D2H pipeline around ``STSE.encode_score``.
 
-    def __init__(self, model, flavour: int = _lib.SCORE_POINCARE, chunk: int = 131072, device: Optional[int] = None):
+    ``chunk``: windows per H2D copy / kernel launch.  Only the first chunk's copy is exposed, so small chunks win as long
+    as a launch still fills the 148 persistent CTAs evenly: 16 384 windows = 36.9 tiles per CTA (measured on one B200:
+    12.99 M windows/s end to end vs 12.36 M with 131 072-window chunks, device-resident rate 13.1 M)."""
+
+    def __init__(self, model, flavour: int = _lib.SCORE_POINCARE, chunk: int = 16384, device: Optional[int] = None):
         self.model, self.flavour, self.chunk = model, flavour, int(chunk)
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         shape = (self.chunk, model.input_dim, model.n_frames, model.n_joints)
@@ -68,7 +72,7 @@ class HostScorer:
         return out_host
 
 
-def score_windows_host(model, x_host: torch.Tensor, flavour: int = _lib.SCORE_POINCARE, chunk: int = 131072,
+def score_windows_host(model, x_host: torch.Tensor, flavour: int = _lib.SCORE_POINCARE, chunk: int = 16384,
                        center: Optional[torch.Tensor] = None) -> torch.Tensor:
     return HostScorer(model, flavour, chunk).score(x_host, center=center)
 
