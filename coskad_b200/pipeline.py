@@ -85,9 +85,10 @@ class TrajectoryScorer:
     cross PCIe -- with stride-1 windows and ``num_transform`` = 5 that is ~40x fewer bytes than the window tensor -- and
     the windows are assembled and transformed inside the kernel's input stage (``coskad_encode_score_traj_fwd``)."""
 
-    def __init__(self, model, flavour: int = _lib.SCORE_POINCARE, device: Optional[int] = None):
-        self.model, self.flavour = model, flavour
+    def __init__(self, model, flavour: int = _lib.SCORE_POINCARE, device: Optional[int] = None, chunk: int = 65536):
+        self.model, self.flavour, self.chunk = model, flavour, int(chunk)
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self.copy_stream = torch.cuda.Stream(self.device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -95,22 +96,42 @@ class TrajectoryScorer:
     def score(self, traj_host: torch.Tensor, win_row_host: torch.Tensor, trans_host: Optional[torch.Tensor] = None,
               mats: Optional[torch.Tensor] = None, out_host: Optional[torch.Tensor] = None,
               center: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """traj_host [rows, 2V] f32, win_row_host [N] i64, trans_host [N] i32 (optional, with mats [n,2,3]) -> scores [N]"""
+        """traj_host [rows, 2V] f32, win_row_host [N] i64, trans_host [N] i32 (optional, with mats [n,2,3]) -> scores [N].
+        The trajectory buffer goes over first; the per-window index arrays follow in chunks on a copy stream while the
+        kernel scores the previous chunk."""
         assert not traj_host.is_cuda and traj_host.dtype == torch.float32 and traj_host.is_contiguous()
         N = win_row_host.numel()
         if out_host is None:
             out_host = torch.empty(N, dtype=torch.float32).pin_memory()
         comp = torch.cuda.current_stream(self.device)
         traj = traj_host.to(self.device, non_blocking=True)
-        rows = win_row_host.to(self.device, non_blocking=True)
-        self.h2d_bytes += traj_host.numel() * 4 + N * 8
-        tr = mt = None
+        self.h2d_bytes += traj_host.numel() * 4
+        mt = None
         if trans_host is not None:
-            tr = trans_host.to(torch.int32).to(self.device, non_blocking=True)
+            trans_host = trans_host.to(torch.int32)
             mt = mats.to(self.device, dtype=torch.float32)
-            self.h2d_bytes += N * 4 + mt.numel() * 4
-        _, s = self.model.encode_score_traj(traj, rows, tr, mt, flavour=self.flavour, center=center, want_latent=False)
-        out_host.copy_(s, non_blocking=True)
+            self.h2d_bytes += mt.numel() * 4
+        dscore = torch.empty(N, device=self.device, dtype=torch.float32)
+        rows_d = torch.empty(N, device=self.device, dtype=torch.int64)
+        tr_d = torch.empty(N, device=self.device, dtype=torch.int32) if trans_host is not None else None
+        nchunks = (N + self.chunk - 1) // self.chunk
+        ready = [torch.cuda.Event() for _ in range(nchunks)]
+        self.copy_stream.wait_stream(comp)
+        with torch.cuda.stream(self.copy_stream):
+            for i in range(nchunks):
+                lo, hi = i * self.chunk, min((i + 1) * self.chunk, N)
+                rows_d[lo:hi].copy_(win_row_host[lo:hi], non_blocking=True)
+                if tr_d is not None:
+                    tr_d[lo:hi].copy_(trans_host[lo:hi], non_blocking=True)
+                ready[i].record(self.copy_stream)
+        for i in range(nchunks):
+            lo, hi = i * self.chunk, min((i + 1) * self.chunk, N)
+            comp.wait_event(ready[i])
+            _, s = self.model.encode_score_traj(traj, rows_d[lo:hi], None if tr_d is None else tr_d[lo:hi], mt,
+                                                flavour=self.flavour, center=center, want_latent=False)
+            dscore[lo:hi].copy_(s)
+        self.h2d_bytes += N * 8 + (N * 4 if tr_d is not None else 0)
+        out_host.copy_(dscore, non_blocking=True)
         self.d2h_bytes += N * 4
         comp.synchronize()
         return out_host
