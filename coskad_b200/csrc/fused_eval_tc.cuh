@@ -446,11 +446,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     {
       const int n = gg;
       const bool has1 = gq < 3;                        // tile j = 1 holds positions 128..203: none in quarter 3
-      float h[2][kC1];
+      unsigned long long h2[2][kC1 / 2];             // packed channel pairs (FFMA2)
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-        for (int c = 0; c < kC1; ++c) h[jj][c] = 0.f;
+        for (int c = 0; c < kC1 / 2; ++c) h2[jj][c] = 0ull;
       float in[2][4];
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
@@ -459,26 +459,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
         in[jj][0] = GB[(n * 2 + 0) * kCS + pc]; in[jj][1] = GB[(n * 2 + 1) * kCS + pc];
         in[jj][2] = X0[(n * 2 + 0) * kCS + pc]; in[jj][3] = X0[(n * 2 + 1) * kCS + pc];
       }
-      const float4* w4 = reinterpret_cast<const float4*>(WMs);
+      const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(WMs);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k) {
+        const unsigned long long x0 = dup2(in[0][k]), x1 = dup2(in[1][k]);
 #pragma unroll
         for (int c4 = 0; c4 < kC1 / 4; ++c4) {
-          const float4 w = w4[k * (kC1 / 4) + c4];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            h[jj][4 * c4 + 0] = fmaf(in[jj][k], w.x, h[jj][4 * c4 + 0]);
-            h[jj][4 * c4 + 1] = fmaf(in[jj][k], w.y, h[jj][4 * c4 + 1]);
-            h[jj][4 * c4 + 2] = fmaf(in[jj][k], w.z, h[jj][4 * c4 + 2]);
-            h[jj][4 * c4 + 3] = fmaf(in[jj][k], w.w, h[jj][4 * c4 + 3]);
-          }
+          const ulonglong2 w = w4[k * (kC1 / 4) + c4];
+          ffma2(h2[0][2 * c4], x0, w.x); ffma2(h2[0][2 * c4 + 1], x0, w.y);
+          ffma2(h2[1][2 * c4], x1, w.x); ffma2(h2[1][2 * c4 + 1], x1, w.y);
         }
+      }
       const float slope1 = WMs[4 * kC1 + kC1];
+      float h[2][kC1];
 #pragma unroll
-      for (int c = 0; c < kC1; ++c) {
-        const float b = WMs[4 * kC1 + c];
-        h[0][c] = prelu(h[0][c] + b, slope1);
-        h[1][c] = prelu(h[1][c] + b, slope1);
+      for (int c = 0; c < kC1 / 2; ++c) {
+        const float b0 = WMs[4 * kC1 + 2 * c], b1 = WMs[4 * kC1 + 2 * c + 1];
+        h[0][2 * c] = prelu(lo2(h2[0][c]) + b0, slope1); h[0][2 * c + 1] = prelu(hi2(h2[0][c]) + b1, slope1);
+        h[1][2 * c] = prelu(lo2(h2[1][c]) + b0, slope1); h[1][2 * c + 1] = prelu(hi2(h2[1][c]) + b1, slope1);
       }
       const uint32_t lane_base = spipe.tbase + (static_cast<uint32_t>(gq * 32) << 16);
       sm_store_a(lane_base + sm_col_a(gg, 0), h[0]);
