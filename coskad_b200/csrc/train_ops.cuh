@@ -423,12 +423,14 @@ __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
   const int tile = threadIdx.x % ntile, ks = threadIdx.x / ntile;
   const int cit = tile % NCT, cot = tile / NCT;
   const bool active = ks < nks;
-  float a1[4][4], a2[4][4], bs1[4], bs2[4];
+  // accumulators packed as (sum over even k, sum over odd k): both FFMA2 operands are natural halves of the float4 loads
+  unsigned long long q1[4][4], q2[4][4];
+  float bs1[4], bs2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     bs1[i] = 0.f; bs2[i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { a1[i][j] = 0.f; a2[i][j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { q1[i][j] = 0ull; q2[i][j] = 0ull; }
   }
   const int64_t E = B * kP;
   for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * kWC; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * kWC) {
@@ -461,31 +463,34 @@ __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
     __syncthreads();
     if (active) {
       for (int k = ks * kslice; k < (ks + 1) * kslice; k += 4) {
-        float4 d1[4], d2[4], g[4], x[4];
+        ulonglong2 d1[4], d2[4], g[4], x[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int co = (i < TCO) ? cot + i * NOT : cot;
           const int ci = (i < TCI) ? cit + i * NCT : cit;
-          d1[i] = *reinterpret_cast<const float4*>(d1s + co * kWCS + k);
-          d2[i] = *reinterpret_cast<const float4*>(d2s + co * kWCS + k);
-          g[i] = *reinterpret_cast<const float4*>(gs + ci * kWCS + k);
-          x[i] = *reinterpret_cast<const float4*>(xs + ci * kWCS + k);
+          d1[i] = *reinterpret_cast<const ulonglong2*>(d1s + co * kWCS + k);
+          d2[i] = *reinterpret_cast<const ulonglong2*>(d2s + co * kWCS + k);
+          g[i] = *reinterpret_cast<const ulonglong2*>(gs + ci * kWCS + k);
+          x[i] = *reinterpret_cast<const ulonglong2*>(xs + ci * kWCS + k);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            a1[i][j] = fmaf(d1[i].x, g[j].x, a1[i][j]); a1[i][j] = fmaf(d1[i].y, g[j].y, a1[i][j]);
-            a1[i][j] = fmaf(d1[i].z, g[j].z, a1[i][j]); a1[i][j] = fmaf(d1[i].w, g[j].w, a1[i][j]);
-            a2[i][j] = fmaf(d2[i].x, x[j].x, a2[i][j]); a2[i][j] = fmaf(d2[i].y, x[j].y, a2[i][j]);
-            a2[i][j] = fmaf(d2[i].z, x[j].z, a2[i][j]); a2[i][j] = fmaf(d2[i].w, x[j].w, a2[i][j]);
+            ffma2(q1[i][j], d1[i].x, g[j].x); ffma2(q1[i][j], d1[i].y, g[j].y);
+            ffma2(q2[i][j], d2[i].x, x[j].x); ffma2(q2[i][j], d2[i].y, x[j].y);
           }
-          bs1[i] += (d1[i].x + d1[i].y) + (d1[i].z + d1[i].w);
-          bs2[i] += (d2[i].x + d2[i].y) + (d2[i].z + d2[i].w);
+          bs1[i] += (lo2(d1[i].x) + hi2(d1[i].x)) + (lo2(d1[i].y) + hi2(d1[i].y));
+          bs2[i] += (lo2(d2[i].x) + hi2(d2[i].x)) + (lo2(d2[i].y) + hi2(d2[i].y));
         }
       }
     }
   }
+  float a1[4][4], a2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a1[i][j] = lo2(q1[i][j]) + hi2(q1[i][j]); a2[i][j] = lo2(q2[i][j]) + hi2(q2[i][j]); }
   if (active) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -576,17 +581,15 @@ __global__ void __launch_bounds__(kGThreads) chan_gemm_kernel(const float* __res
     __syncthreads();
     if (nct > 0) {
       const int el = slab * 128 + lane * 4;                 // this lane's 4 positions inside the chunk
-      float a1[2][4][4], a2[2][4][4];
+      // accumulators packed over position pairs (FFMA2: one issue slot per two FMAs; the weight is the broadcast operand)
+      unsigned long long p1[2][4][2], p2[2][4][2];
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { a1[c][i][j] = 0.f; a2[c][i][j] = 0.f; }
+        for (int i = 0; i < 4; ++i) { p1[c][i][0] = p1[c][i][1] = 0ull; p2[c][i][0] = p2[c][i][1] = 0ull; }
       for (int k = 0; k < K; ++k) {
-        const float4 xa = *reinterpret_cast<const float4*>(ia + k * CES + el);
-        const float4 xb = *reinterpret_cast<const float4*>(ib + k * CES + el);
-        const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+        const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(ia + k * CES + el);
+        const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(ib + k * CES + el);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (c < nct) {
@@ -602,12 +605,22 @@ __global__ void __launch_bounds__(kGThreads) chan_gemm_kernel(const float* __res
               for (int i = 0; i < 4; ++i) { wav[i] = i < TM ? wa[k * M + m0 + i] : 0.f; wbv[i] = i < TM ? wb[k * M + m0 + i] : 0.f; }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { a1[c][i][j] = fmaf(wav[i], xav[j], a1[c][i][j]); a2[c][i][j] = fmaf(wbv[i], xbv[j], a2[c][i][j]); }
+            for (int i = 0; i < 4; ++i) {
+              const unsigned long long w1d = dup2(wav[i]), w2d = dup2(wbv[i]);
+              ffma2(p1[c][i][0], w1d, xa.x); ffma2(p1[c][i][1], w1d, xa.y);
+              ffma2(p2[c][i][0], w2d, xb.x); ffma2(p2[c][i][1], w2d, xb.y);
+            }
           }
         }
       }
+      float a1[2][4][4], a2[2][4][4];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a1[c][i][0] = lo2(p1[c][i][0]); a1[c][i][1] = hi2(p1[c][i][0]); a1[c][i][2] = lo2(p1[c][i][1]); a1[c][i][3] = hi2(p1[c][i][1]);
+          a2[c][i][0] = lo2(p2[c][i][0]); a2[c][i][1] = hi2(p2[c][i][0]); a2[c][i][2] = lo2(p2[c][i][1]); a2[c][i][3] = hi2(p2[c][i][1]);
+        }
       const int64_t e = e0 + el;
       const bool valid = e < E;                             // E % 4 == 0: the 4 positions are valid together
       const int64_t b = valid ? e / kP : 0;
