@@ -256,8 +256,11 @@ static int ensure_smem_attr(coskad_ctx* ctx) {
   if (ctx->smem_attr_set) return COSKAD_OK;
   CK(cudaFuncSetAttribute(fused_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   CK(cudaFuncSetAttribute(fused_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  CK(cudaFuncSetAttribute(fused_eval_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   ctx->smem_attr_set = true;
   return COSKAD_OK;
 }
@@ -287,7 +290,13 @@ static int launch_encode_score(coskad_ctx* ctx, int flavour, const float* x, con
     FusedTcParams t = ctx->tp;
     t.x = x; t.center = center; t.z = z; t.score = p.score; t.B = B; t.head_rows = p.head_rows; t.D = p.D; t.flavour = flavour;
     t.traj = traj; t.win_row = win_row; t.traj_rows = traj_rows; t.trans = trans; t.mats = mats; t.n_mats = n_mats;
-    fused_eval_tc_kernel<false><<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
+    // one instantiation per number of 4-row head groups: the head streams and multiplies only the rows it has
+    const int ndq = (t.head_rows + 3) / 4;
+    const dim3 grid(fused_grid(ctx, B));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (ndq <= 2) fused_eval_tc_kernel<false, 2><<<grid, kTcThreads, kTcSmemBytes, st>>>(t);
+    else if (ndq == 3) fused_eval_tc_kernel<false, 3><<<grid, kTcThreads, kTcSmemBytes, st>>>(t);
+    else fused_eval_tc_kernel<false, 4><<<grid, kTcThreads, kTcSmemBytes, st>>>(t);
   } else {
     fused_eval_kernel<false><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
   }
@@ -341,7 +350,8 @@ extern "C" int coskad_autoencode_score_fwd(coskad_ctx* ctx, const float* x, cons
     t.dM = p.dM; t.dm0 = p.dm0; t.d_slope0 = p.d_slope0; t.DL = p.DL;
     for (int i = 0; i < 3; ++i) { t.dTw[i] = p.dTw[i]; t.dAw[i] = p.dAw[i]; t.dWm[i] = p.dWm[i]; }
     t.xhat = xhat; t.rec_score = rec_score;
-    fused_eval_tc_kernel<true><<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
+    if (t.head_rows <= 8) fused_eval_tc_kernel<true, 2><<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
+    else fused_eval_tc_kernel<true, 4><<<fused_grid(ctx, B), kTcThreads, kTcSmemBytes, static_cast<cudaStream_t>(stream_)>>>(t);
   } else {
     fused_eval_kernel<true><<<fused_grid(ctx, B), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream_)>>>(p);
   }

@@ -265,7 +265,7 @@ __device__ __forceinline__ void sm_epilogue(const SmallPipe& P, int g, int q, in
   tc::fence_before_sync();
 }
 
-template <bool kDec>
+template <bool kDec, int NDQ>
 __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __grid_constant__ FusedTcParams Pm) {
   extern __shared__ __align__(128) float smem_tc[];
   float* R0 = smem_tc;
@@ -557,6 +557,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       // 8 units (half j, 16-channel chunk) per lane quarter, split 3/3/2 over the three warp groups
       // (quarter 3 holds no j = 1 positions: its 4 units go 2/2/0, and its warps run the next tile's layer 1 afterwards)
       const int u0 = q < 3 ? sub * 3 : sub * 2, u1 = q < 3 ? ((sub == 2) ? 8 : u0 + 3) : (sub == 2 ? u0 : u0 + 2);
+      // the head only streams the rows it has: the kernel is instantiated per NDQ = ceil(head_rows / 4) groups of 4 rows
+      // (16 rows: 4, the VAE's 8 + 1: 3, latent 8: 2); the weight stream and the FMAs of this stage scale with NDQ
       for (int unit = u0; unit < u1; ++unit) {
         const int j = unit >> 2, c0 = (unit & 3) * 16;
         const int p = j * 128 + q * 32 + lane;
@@ -570,11 +572,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const float b = bias[c0 + u];
-            // 4 x LDG.128 (streamed once per tile: no L1 allocation): the 16 latent rows of feature (c0+u, p), as 8 (d, d+1) pairs
+            // NDQ x LDG.128 (streamed once per tile: no L1 allocation): 4 NDQ latent rows of feature (c0+u, p) as (d, d+1) pairs
             const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(Pm.head_w4) + static_cast<size_t>((c0 + u) * (kDP / 4)) * kP + p;
             unsigned long long w2[kDP / 2];
 #pragma unroll
-            for (int dq = 0; dq < kDP / 4; ++dq) {
+            for (int dq = 0; dq < NDQ; ++dq) {
               asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
                            : "=l"(w2[2 * dq]), "=l"(w2[2 * dq + 1]) : "l"(wp + dq * kP));
             }
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
               const float h = prelu(__uint_as_float(v[n][u]) + b, slope4);
               const unsigned long long hh = dup2(h);
 #pragma unroll
-              for (int dp = 0; dp < kDP / 2; ++dp) ffma2(z2[n][dp], hh, w2[dp]);
+              for (int dp = 0; dp < 2 * NDQ; ++dp) ffma2(z2[n][dp], hh, w2[dp]);
             }
           }
         }
