@@ -548,6 +548,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     {
       const float* bias = WMb + 2 * 32 * 64;
       const float slope4 = bias[kC4];
+      // the head weights are re-read by every tile of every CTA: keep them in L2 ahead of the window stream that flows through it
+      uint64_t l2_keep;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
       const int q = warp & 3, sub = warp >> 2;
       unsigned long long z2[kNW][kDP / 2];           // packed (d, d+1) accumulators for fma.rn.f32x2
 #pragma unroll
@@ -572,13 +575,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const float b = bias[c0 + u];
-            // NDQ x LDG.128 (streamed once per tile: no L1 allocation): 4 NDQ latent rows of feature (c0+u, p) as (d, d+1) pairs
+            // NDQ x LDG.128 (streamed once per tile: no L1 allocation, L2 evict_last): 4 NDQ latent rows of feature (c0+u, p) as (d, d+1) pairs
             const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(Pm.head_w4) + static_cast<size_t>((c0 + u) * (kDP / 4)) * kP + p;
             unsigned long long w2[kDP / 2];
 #pragma unroll
             for (int dq = 0; dq < NDQ; ++dq) {
-              asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
-                           : "=l"(w2[2 * dq]), "=l"(w2[2 * dq + 1]) : "l"(wp + dq * kP));
+              asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                           : "=l"(w2[2 * dq]), "=l"(w2[2 * dq + 1]) : "l"(wp + dq * kP), "l"(l2_keep));
             }
 #pragma unroll
             for (int n = 0; n < kNW; ++n) {
