@@ -206,3 +206,26 @@ def test_scores_invariant_to_launch_geometry():
         assert torch.equal(s2, s[off:])
     _, s1 = m.encode_score(x[:1].contiguous(), 1, center=c)
     assert torch.equal(s1, s[:1])
+
+
+@pytest.mark.parametrize('kind', ['stse16', 'stse8', 'stsae8'])
+def test_repeat_launches_are_bit_identical(kind):
+    """the kernel software-pipelines tiles (deferred score, layer 1 one tile ahead, aliased TMEM buffers, barrier parities that
+    run across tiles): any race or stale buffer shows up as run-to-run differences, so 10 launches must agree bit for bit"""
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = (torch.randn(50_001, 2, 12, 17, device='cuda', generator=g) * 0.4).clamp_(-3, 3)
+    if kind == 'stsae8':
+        m, _ = make_pair('stsae', 8, seed=1)
+        c = torch.full((8,), 0.02, device='cuda')
+        run = lambda: m.autoencode_score(x, center=c)
+    else:
+        d = 16 if kind == 'stse16' else 8
+        m, _ = make_pair('stse', d, seed=0)
+        c = torch.full((d,), 0.01, device='cuda')
+        run = lambda: m.encode_score(x, 1 if d == 16 else 3, center=c)
+    ref = [t.clone() for t in run()]
+    for _ in range(9):
+        out = run()
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)
+    assert all(bool(torch.isfinite(t).all()) for t in ref)
