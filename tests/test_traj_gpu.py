@@ -96,3 +96,26 @@ def test_front_end_argument_errors():
     # out-of-range rows are clamped into the buffer, never read outside it
     z, _ = m.encode_score_traj(traj, torch.tensor([-5, 100, 8], device='cuda'))
     assert bool(torch.isfinite(z).all())
+
+
+@pytest.mark.parametrize('n', [1, 777, 40_001])
+def test_host_scorers_equal_direct_calls(n):
+    """pipeline.HostScorer / TrajectoryScorer (chunked H2D on a copy stream, scores back to pinned host memory) return exactly
+    what one direct device call returns, for sizes that are not multiples of the chunk"""
+    from coskad_b200.pipeline import HostScorer, TrajectoryScorer
+    m, _ = make_pair('stse', 16, seed=0)
+    rng = np.random.default_rng(n)
+    c = torch.full((16,), 0.01, device='cuda')
+    # windows
+    xh = torch.from_numpy((rng.standard_normal((n, 2, 12, 17)) * 0.4).astype(np.float32)).pin_memory()
+    got = HostScorer(m, 1, chunk=4096).score(xh, center=c)
+    _, ref = m.encode_score(xh.cuda(), 1, center=c)
+    assert torch.equal(got, ref.cpu())
+    # trajectories: one long person, n windows at random starts, 5 transforms
+    traj = torch.from_numpy((rng.standard_normal((500, 34)) * 0.4).astype(np.float32)).pin_memory()
+    rows = torch.from_numpy(rng.integers(0, 500 - 12 + 1, size=n)).pin_memory()
+    tr = torch.from_numpy(rng.integers(0, 5, size=n).astype(np.int32)).pin_memory()
+    mats = torch.from_numpy(owin.ae_trans_mats()[:, :2].copy())
+    got = TrajectoryScorer(m, 1, chunk=8192).score(traj, rows, tr, mats, center=c)
+    _, ref = m.encode_score_traj(traj.cuda(), rows.cuda(), tr.cuda(), mats.cuda(), flavour=1, center=c)
+    assert torch.equal(got, ref.cpu())
