@@ -61,6 +61,16 @@ def load_gt_table(args) -> Tuple[List[Tuple[int, int, int]], Dict[Tuple[int, int
     return clips, gts
 
 
+def hr_ubnormal(path_to_boolean_masks: str) -> Dict[Tuple[int, int], np.ndarray]:
+    """utils/model_utils.py:149-161: ``{scene}_{clip}.npy`` boolean frame masks of the UBnormal HR subset, keyed (scene, clip)"""
+    from glob import glob
+    masks = {}
+    for path in glob(path_to_boolean_masks):
+        scene_id, clip_id = map(int, os.path.basename(path).split('.')[0].split('_'))
+        masks[(scene_id, clip_id)] = np.load(path)
+    return masks
+
+
 def auc_from_curves(curves: Dict[int, List[np.ndarray]], clips, gts, masks=None) -> Tuple[float, Dict[int, float]]:
     """eval_COSKAD.py:226-253: per-transformation AUC on the concatenated clips, final AUC on the mean curve"""
     from sklearn.metrics import roc_auc_score

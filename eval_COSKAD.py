@@ -63,7 +63,10 @@ def main(argv=None):
     model = tasks.select_task(args)(args)
     path = os.path.join(args.exp_dir, args.dataset_choice, args.dir_name, args.load_ckpt) if args.load_ckpt else None
     print('Loading model from {}'.format(path))
-    auc, per_t, _ = evaluate(args, model, (ds, loader), ckpt_path=path)
+    # eval_COSKAD.py:92-101: HR subset of UBnormal = boolean frame masks per clip (the reference hard-codes their directory;
+    # here it is the config key hr_masks_path, a glob of {scene}_{clip}.npy files)
+    masks = tasks.hr_ubnormal(args.hr_masks_path) if getattr(args, 'use_hr', False) and getattr(args, 'hr_masks_path', '') else None
+    auc, per_t, _ = evaluate(args, model, (ds, loader), ckpt_path=path, masks=masks)
     for t, a in per_t.items():
         print('auc = {} (transformation {})'.format(a, t + 1))
     print('final AUC score: {}'.format(auc))

@@ -47,3 +47,14 @@ def test_host_postprocessing_equals_oracle():
     fr = np.stack([np.arange(a, a + 12) for a in (0, 1, 5, 30)])
     l = torch.tensor([0.1, 0.0, 0.3, 0.4])
     assert np.array_equal(_scatter(l, fr, 50), oagg.scatter_windows(l.numpy(), fr, 50))
+
+
+def test_hr_mask_loader(tmp_path):
+    """utils/model_utils.py:149-161 restated: {scene}_{clip}.npy boolean masks keyed by (scene, clip)"""
+    from coskad_b200.tasks import hr_ubnormal
+    m = np.array([True, False, True])
+    np.save(tmp_path / '3_17.npy', m)
+    np.save(tmp_path / '12_4.npy', ~m)
+    got = hr_ubnormal(str(tmp_path / '*.npy'))
+    assert sorted(got) == [(3, 17), (12, 4)]
+    assert np.array_equal(got[(3, 17)], m) and np.array_equal(got[(12, 4)], ~m)
