@@ -719,7 +719,12 @@ extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_sma
   if (D < 1 || D > 16) return fail(ctx, COSKAD_ERR_ARG, "linear: D must be in [1,16], got %d", D);
   if (B <= 0) return COSKAD_OK;
   const int64_t sd = w_is_fd ? 1 : F, sf = w_is_fd ? D : 1;
-  if (mode == 0) lin_reduce_f_kernel<16><<<static_cast<unsigned>((B + kLinRows - 1) / kLinRows), kTrainThreads, 0, st>>>(A_wide, W, sd, sf, bias, B, F, D, out);
+  if (mode == 0) {
+    CK(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(B) * D, st));      // the slices add their partial sums
+    const int rows_per_block = (kTrainThreads / 32) * kLinRows;
+    lin_reduce_f_kernel<16><<<dim3(static_cast<unsigned>((B + rows_per_block - 1) / rows_per_block), kLinSlices), kTrainThreads, 0, st>>>(
+        A_wide, W, sd, sf, bias, B, F, D, out);
+  }
   else if (mode == 1) lin_expand_f_kernel<16><<<dim3((F + kTrainThreads - 1) / kTrainThreads, static_cast<unsigned>((B + kExpRows - 1) / kExpRows)), kTrainThreads, 0, st>>>(a_small, W, sd, sf, bias, B, F, D, out);
   else if (mode == 2) {
     int nb = static_cast<int>(B < 32 ? B : 32);

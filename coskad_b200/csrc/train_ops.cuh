@@ -91,35 +91,51 @@ constexpr int kCSmemFloats = 2 * kCRows * kCS + kTwFloats + kAwFloats;
 constexpr int kCSmemBytes = kCSmemFloats * 4;
 static_assert(kCSmemBytes <= 227 * 1024, "contraction kernels: shared memory plan exceeds 227 KB");
 
-// (row, p) of element i = tid + j * kCThreads of a row block, advanced without a division: 384 = 204 + 180
-struct RowCursor {
-  int row, p;
-  __device__ __forceinline__ explicit RowCursor(int tid) : row(tid / kP), p(tid % kP) {}
-  __device__ __forceinline__ void next() { row += 1; p += kCThreads - kP; if (p >= kP) { p -= kP; row += 1; } }
-};
-static_assert(kCThreads > kP && kCThreads < 2 * kP, "RowCursor step");
-
+// Row-block copies, one warp per row (rows warp, warp + 12, ..), lanes = positions p = lane + 32 k: one pointer per row and
+// a few instructions per element (a flat element index cost ~20 integer instructions per 4-byte copy).
+constexpr int kRowIters = (kP + 31) / 32;                         // 7
 __device__ __forceinline__ void contract_load_rows(float* dst, const float* __restrict__ src, int64_t r0, int nr, int tid) {
-  RowCursor c(tid);
-  for (int i = tid; i < kCRows * kP; i += kCThreads, c.next()) {
-    const int rr = c.row < nr ? c.row : nr - 1;          // ragged last block: replicate the last row, never stored
-    cp_async4(dst + c.row * kCS + c.p, src + (r0 + rr) * kP + c.p);
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int row = warp; row < kCRows; row += kCWarps) {
+    const float* s = src + (r0 + (row < nr ? row : nr - 1)) * kP;   // ragged last block: replicate the last row, never stored
+    float* d = dst + row * kCS;
+#pragma unroll
+    for (int k = 0; k < kRowIters; ++k) {
+      const int p = lane + 32 * k;
+      if (p < kP) cp_async4(d + p, s + p);
+    }
   }
 }
-// dst rows [r0, r0+nr) = planes (+ add, nullable); the loads of `add` are batched so that their latency is paid once per batch
+// dst rows [r0, r0+nr) = planes (+ add, nullable); the loads of `add` are batched four rows at a time
 __device__ __forceinline__ void contract_store_rows(float* __restrict__ dst, const float* planes, const float* __restrict__ add,
                                                     int64_t r0, int nr, int tid) {
-  constexpr int kBatch = 17;                              // kCRows * kP / kCThreads = 51 = 3 x 17
-  static_assert((kCRows * kP) % (kCThreads * kBatch) == 0, "row-block store plan");
-  RowCursor c(tid);
-  for (int b = 0; b < (kCRows * kP) / (kCThreads * kBatch); ++b) {
-    float a[kBatch];
-    RowCursor cl = c;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int kRB = 4;
+  static_assert(kCRows % (kCWarps * kRB) == 0, "row-block store plan");
+  for (int rb = warp; rb < kCRows; rb += kCWarps * kRB) {
+    float a[kRB][kRowIters];
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j, cl.next()) a[j] = (add != nullptr && cl.row < nr) ? __ldg(add + (r0 + cl.row) * kP + cl.p) : 0.f;
+    for (int j = 0; j < kRB; ++j) {
+      const int row = rb + j * kCWarps;
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j, c.next())
-      if (c.row < nr) dst[(r0 + c.row) * kP + c.p] = planes[c.row * kCS + c.p] + a[j];
+      for (int k = 0; k < kRowIters; ++k) {
+        const int p = lane + 32 * k;
+        a[j][k] = (add != nullptr && row < nr && p < kP) ? __ldg(add + (r0 + row) * kP + p) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRB; ++j) {
+      const int row = rb + j * kCWarps;
+      if (row < nr) {
+        float* d = dst + (r0 + row) * kP;
+        const float* s = planes + row * kCS;
+#pragma unroll
+        for (int k = 0; k < kRowIters; ++k) {
+          const int p = lane + 32 * k;
+          if (p < kP) d[p] = s[p] + a[j][k];
+        }
+      }
+    }
   }
 }
 
@@ -663,47 +679,53 @@ __global__ void __launch_bounds__(kGThreads) chan_gemm_kernel(const float* __res
 
 // ---- linear layers over the flattened features ------------------------------------------------------
 // W(d, f) = W[d*sd + f*sf]:  btlnk / fc_* weight [D,F]: sd = F, sf = 1;  rev_btlnk weight [F,D]: sd = 1, sf = D
-// out[b,d] = sum_f A[b,f] W(d,f) + bias[d]           (wide-in: head forward, rev_btlnk input gradient)
-// one block per kLinRows rows b: every weight fetched from L2 feeds kLinRows FMAs (one row per block re-read all of W per row)
-constexpr int kLinRows = 4;
+// out[b,d] += sum_{f in slice} A[b,f] W(d,f) (+ bias[d] from slice 0)   (wide-in: head forward, rev_btlnk input gradient)
+// grid (ceil(B / 32), kLinSlices): a block owns 32 rows (4 per warp) and one slice of the features; it stages W chunks of
+// [DMAX][kLinFC] in shared memory once for all its rows (one row per block re-read all 835 KB of W per row from L2) and
+// adds its partial sums to `out` (zeroed by the caller) with atomics.
+constexpr int kLinRows = 4;            // rows per warp
+constexpr int kLinFC = 512;            // features per staged chunk
+constexpr int kLinSlices = 4;
 template <int DMAX>
 __global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __restrict__ W, int64_t sd, int64_t sf,
                                     const float* __restrict__ bias, int64_t B, int F, int D, float* __restrict__ out) {
-  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kLinRows;
-  if (b0 >= B) return;
+  __shared__ float ws[DMAX][kLinFC + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int64_t b0 = (static_cast<int64_t>(blockIdx.x) * nwarp + warp) * kLinRows;
+  const int fslice = (F + kLinSlices - 1) / kLinSlices;
+  const int f_lo = blockIdx.y * fslice, f_hi = min(F, f_lo + fslice);
   float acc[kLinRows][DMAX];
 #pragma unroll
   for (int r = 0; r < kLinRows; ++r)
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) acc[r][d] = 0.f;
-  for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    float a[kLinRows];
+  for (int f0 = f_lo; f0 < f_hi; f0 += kLinFC) {
+    const int nf = min(kLinFC, f_hi - f0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < DMAX * kLinFC; i += blockDim.x) {
+      const int d = i / kLinFC, f = i - d * kLinFC;
+      ws[d][f] = (d < D && f < nf) ? W[d * sd + (f0 + f) * sf] : 0.f;
+    }
+    __syncthreads();
+    for (int f = lane; f < nf; f += 32) {
+      float a[kLinRows];
 #pragma unroll
-    for (int r = 0; r < kLinRows; ++r) a[r] = (b0 + r < B) ? A[(b0 + r) * F + f] : 0.f;
+      for (int r = 0; r < kLinRows; ++r) a[r] = (b0 + r < B) ? A[(b0 + r) * F + f0 + f] : 0.f;
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) {
-      if (d < D) {
-        const float w = W[d * sd + f * sf];
+      for (int d = 0; d < DMAX; ++d) {
+        const float w = ws[d][f];
 #pragma unroll
         for (int r = 0; r < kLinRows; ++r) acc[r][d] = fmaf(a[r], w, acc[r][d]);
       }
     }
   }
-  __shared__ float sh[kLinRows][DMAX][8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < kLinRows; ++r)
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) { const float s = warp_sum(acc[r][d]); if (lane == 0) sh[r][d][warp] = s; }
-  __syncthreads();
-  if (threadIdx.x < kLinRows * DMAX) {
-    const int r = threadIdx.x / DMAX, d = threadIdx.x % DMAX;
-    if (d < D && b0 + r < B) {
-      float s = bias ? bias[d] : 0.f;
-      for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[r][d][w];
-      out[(b0 + r) * D + d] = s;
+    for (int d = 0; d < DMAX; ++d) {
+      const float s = warp_sum(acc[r][d]);
+      if (lane == 0 && d < D && b0 + r < B) atomicAdd(out + (b0 + r) * D + d, s + ((blockIdx.y == 0 && bias) ? bias[d] : 0.f));
     }
-  }
 }
 // out[b,f] = sum_d a[b,d] W(d,f) + bias[f]           (wide-out: rev_btlnk forward, head input gradient)
 // grid (ceil(F/256), ceil(B/kExpRows)): a thread keeps the D weights of its feature f in registers for kExpRows rows b
