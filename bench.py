@@ -97,7 +97,8 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_path(sample: int, passes: int, warm: int = 1):
+def cpu_path(sample: int, passes: int, warm: int = 1, min_seconds: float = 0.0, max_passes: int = 64):
+    # passes: timed passes over the sample; with min_seconds > 0 further passes are added until that much CPU work is timed
     """The reference's CPU implementation of the path (oracle port), all host threads:
     STSE forward (models/sts/ae.py:108-121) + project(expmap0) + dist (eval_COSKAD.py:194-196)."""
     import torch
@@ -111,7 +112,11 @@ def cpu_path(sample: int, passes: int, warm: int = 1):
     c = torch.full((16,), 0.01)
     times = []
     with torch.no_grad():
-        for i in range(warm + passes):
+        i = -1
+        while True:
+            i += 1
+            if i >= warm + passes and (sum(times) >= min_seconds or len(times) >= max_passes):
+                break
             t0 = time.perf_counter()
             for lo in range(0, sample, 2048):                       # dataset_batch_size 2048
                 z = onet.stse_forward(x[lo:lo + 2048], sd)
@@ -343,7 +348,7 @@ def run_ours(args):
                                'rate of the head stage, hence roofline.bound = fp32_fma'}
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        times, ncpu, nthr = cpu_path(args.cpu_sample, 3, 1)
+        times, ncpu, nthr = cpu_path(args.cpu_sample, 3, 1, min_seconds=10.0)      # ~10 s of CPU work, bounded
         cpu_baseline = {'value': args.cpu_sample * len(times) / sum(times), 'unit': 'windows/s', 'cores': nthr,
                         'kind': 'port', 'sample': f'{args.cpu_sample} windows x {len(times)} passes (batches of 2048), '
                                                    f'host cpu_count {ncpu}'}
