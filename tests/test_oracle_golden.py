@@ -180,3 +180,42 @@ def test_fused_reg_loss_matches_reference_formula():
     for a, b in zip(g_got, g_ref):
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
     assert all(p.grad is None for n, p in m.named_parameters() if 'bias' in n)
+
+
+def test_geoopt_restatement_satisfies_the_poincare_ball_identities():
+    """geoopt itself cannot be imported here (parity unpinned, oracle/geoopt_math.py header); what CAN be checked without it is
+    that the restated formulas are the Poincare-ball operations they claim to be: closed forms in float64."""
+    torch.manual_seed(0)
+    k = torch.tensor(-1., dtype=torch.float64)
+    u = torch.randn(256, 16, dtype=torch.float64) * 0.3
+    v = torch.randn(256, 16, dtype=torch.float64) * 0.3
+    x, y = ogm.expmap0(u, k=k), ogm.expmap0(v, k=k)
+    # expmap0 lands inside the unit ball with ||x|| = tanh(||u||); dist0 is its inverse: d(0, x) = 2 ||u||
+    assert bool((x.norm(dim=-1) < 1).all())
+    assert torch.allclose(x.norm(dim=-1), torch.tanh(u.norm(dim=-1)), rtol=1e-12)
+    assert torch.allclose(ogm.dist0(x, k=k), 2 * u.norm(dim=-1), rtol=1e-9)
+    # distance: symmetric, zero on the diagonal, equal to the closed form arcosh(1 + 2|x-y|^2 / ((1-|x|^2)(1-|y|^2)))
+    d = ogm.dist(x, y, k=k)
+    assert torch.allclose(d, ogm.dist(y, x, k=k), rtol=1e-10)
+    assert float(ogm.dist(x, x, k=k).abs().max()) < 1e-6
+    closed = torch.acosh(1 + 2 * (x - y).pow(2).sum(-1) / ((1 - x.pow(2).sum(-1)) * (1 - y.pow(2).sum(-1))))
+    assert torch.allclose(d, closed, rtol=1e-8, atol=1e-10)
+    assert torch.allclose(ogm.dist0(x, k=k), ogm.dist(torch.zeros_like(x), x, k=k), rtol=1e-9)
+    # Moebius addition: left identity, left inverse, and it is an isometry: d(a + x, a + y) = d(x, y)
+    a = ogm.expmap0(torch.randn(256, 16, dtype=torch.float64) * 0.2, k=k)
+    assert torch.allclose(ogm.mobius_add(torch.zeros_like(x), x, k=k), x, atol=1e-14)
+    assert float(ogm.mobius_add(-x, x, k=k).abs().max()) < 1e-12
+    assert torch.allclose(ogm.dist(ogm.mobius_add(a, x, k=k), ogm.mobius_add(a, y, k=k), k=k), d, rtol=1e-7, atol=1e-9)
+    # gyro-midpoint: of one repeated point it is that point; of two points it is equidistant and halves the distance
+    p = x[:1]
+    assert torch.allclose(ogm.weighted_midpoint(p.expand(7, -1), k=k), p[0], atol=1e-12)
+    for i in range(8):
+        m = ogm.weighted_midpoint(torch.stack([x[i], y[i]]), k=k)
+        dx, dy = ogm.dist(m, x[i], k=k), ogm.dist(m, y[i], k=k)
+        assert abs(float(dx - dy)) < 1e-9 and abs(float(dx + dy - d[i])) < 1e-8
+    # project only touches points outside the (1 - eps) ball and puts them on its boundary along the same ray
+    far = x / x.norm(dim=-1, keepdim=True) * 0.9999
+    pr = ogm.project(far.float(), k=torch.tensor(-1.))
+    assert torch.allclose(pr.norm(dim=-1), torch.full((256,), 1 - 4e-3), rtol=1e-6)
+    assert torch.allclose(pr / pr.norm(dim=-1, keepdim=True), (far / far.norm(dim=-1, keepdim=True)).float(), atol=1e-6)
+    assert torch.equal(ogm.project(x.float(), k=torch.tensor(-1.)), x.float())
