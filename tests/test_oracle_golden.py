@@ -219,3 +219,38 @@ def test_geoopt_restatement_satisfies_the_poincare_ball_identities():
     assert torch.allclose(pr.norm(dim=-1), torch.full((256,), 1 - 4e-3), rtol=1e-6)
     assert torch.allclose(pr / pr.norm(dim=-1, keepdim=True), (far / far.norm(dim=-1, keepdim=True)).float(), atol=1e-6)
     assert torch.equal(ogm.project(x.float(), k=torch.tensor(-1.)), x.float())
+
+
+def test_power_spherical_restatement_is_the_distribution_it_claims():
+    """power_spherical cannot be imported (parity unpinned); the restatement is checked against what defines the distribution:
+    density p(x) ~ (1 + mu.x)^kappa on S^{d-1}  =>  marginal of t = mu.x on [-1, 1] ~ (1+t)^(kappa + (d-3)/2) (1-t)^((d-3)/2),
+    i.e. t = 2 Beta(alpha, beta) - 1 with the restated (alpha, beta); entropy / KL against numerical integration."""
+    import math
+    from oracle import power_spherical as ops
+    d = 8
+    for kappa in (0.5, 3.0, 25.0):
+        kap = torch.tensor([kappa], dtype=torch.float64)
+        a, b = ops.ps_alpha_beta(kap, d)
+        assert abs(float(a) - ((d - 1) / 2 + kappa)) < 1e-12 and abs(float(b) - (d - 1) / 2) < 1e-12
+        # numerical entropy of the density on the sphere: p(x) = C (1 + t)^kappa, surface element ~ |S^{d-2}| (1 - t^2)^((d-3)/2) dt
+        t = torch.linspace(-1, 1, 2_000_001, dtype=torch.float64)[1:-1]
+        area = 2 * math.pi ** ((d - 1) / 2) / math.gamma((d - 1) / 2)              # |S^{d-2}|
+        w = area * (1 - t * t) ** ((d - 3) / 2)
+        un = (1 + t) ** kappa
+        Z = torch.trapezoid(un * w, t)
+        p = un / Z
+        H = -torch.trapezoid(p * torch.log(p) * w, t)
+        assert abs(float(H) - float(ops.ps_entropy(kap, d))) < 1e-5 * max(1.0, abs(float(H)))
+        sphere = 2 * math.pi ** (d / 2) / math.gamma(d / 2)                          # |S^{d-1}|
+        assert abs(ops.hu_entropy(d) - math.log(sphere)) < 1e-12
+        assert float(ops.kl_ps_uniform(kap, d)) > 0
+    # sampling transform: unit norm, the t-coordinate is the cosine to the mean direction, t = 1 gives the mean itself
+    g = torch.Generator().manual_seed(0)
+    loc = torch.randn(64, d, generator=g, dtype=torch.float64)
+    loc = loc / loc.norm(dim=-1, keepdim=True)
+    tt, v = ops.draw_noise(torch.full((64,), 4.0, dtype=torch.float64), d, generator=g)
+    z = ops.rsample_from_noise(loc, tt, v)
+    assert torch.allclose(z.norm(dim=-1), torch.ones(64, dtype=torch.float64), atol=1e-4)
+    assert torch.allclose((z * loc).sum(-1), tt.squeeze(-1), atol=1e-4)
+    z1 = ops.rsample_from_noise(loc, torch.ones(64, 1, dtype=torch.float64), v)
+    assert torch.allclose(z1, loc, atol=2e-3)        # sqrt(clamp(1 - t^2, 1e-7)) leaves a 3e-4 tangential component upstream too
