@@ -32,7 +32,8 @@ def step():
     loss = dist_c.mean() + 1e-6 * reg
     opt.zero_grad(set_to_none=True)
     loss.backward()
-    bucket.allreduce_()                                   # flat NCCL all-reduce of the gradients (no-op on one GPU)
+    if not os.environ.get('COSKAD_TB_NOAR'):
+        bucket.allreduce_()                               # flat NCCL all-reduce of the gradients (no-op on one GPU)
     opt.step()
     return loss
 
@@ -50,7 +51,7 @@ if world > 1:
     t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     if rank != 0:
         dist.destroy_process_group(); sys.exit(0)
-    print(f'{world} GPUs x B={B}: {ms:.3f} ms/step (max over ranks) -> {world*B/ms*1e3:.0f} windows/s')
+    print(f'{world} GPUs x B={B}: {ms:.3f} ms/step (max over ranks; wall on rank 0 {(t1-t0)/N*1e3:.3f}) -> {world*B/ms*1e3:.0f} windows/s' + (' [no all-reduce]' if os.environ.get('COSKAD_TB_NOAR') else ''))
     dist.destroy_process_group(); sys.exit(0)
 print(f'B={B}: {ms:.3f} ms/step (device), {(t1-t0)/N*1e3:.3f} ms/step (wall) -> {B/ms*1e3:.0f} windows/s, loss {float(l):.4f}')
 from torch.profiler import profile, ProfilerActivity
