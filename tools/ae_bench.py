@@ -26,3 +26,12 @@ e16 = synth.make_model('stse', 16, seed=0, device=dev)
 c16 = torch.zeros(16, device=dev)
 ms = timeit(lambda: e16.encode_score(x, _lib.SCORE_POINCARE, center=c16, want_latent=False))
 print(f'STSE D=16 poincare score: {ms:.2f} ms -> {B/ms*1e3/1e6:.2f} M windows/s')
+# spherical VAE (use_vae): fc_mean + fc_var as a 9-row head (NDQ = 3), cosine score to the mean direction
+from coskad_b200 import spherical
+torch.manual_seed(0)
+sv = spherical.STSVAE(input_dim=2, layer_channels=[32, 16, 32], hidden_dimension=64, latent_dim=8, n_frames=12, n_joints=17)
+synth.randomize_bn_(sv, 0)
+sv = sv.to(dev).eval()
+mv = torch.nn.functional.normalize(torch.randn(1, 8, device=dev), dim=-1)
+ms = timeit(lambda: sv.cosine_scores(x, mean_vector=mv, sample=False))
+print(f'STSVAE D=8 (9-row head) cosine score on the mean direction: {ms:.2f} ms -> {B/ms*1e3/1e6:.2f} M windows/s')
