@@ -9,7 +9,8 @@
 //     the head from the TMEM accumulators;
 //   * layers 2/3 (N = 32): each warp group owns one window, stages its two M-tiles (128 positions each) into private
 //     TMEM A buffers, issues its own MMAs and runs its own epilogue (SmallPipe);
-//   * layer 4 (N = 64): 384 D columns + two shared 64-column A buffers with mbarrier hand-off (TcPipe); the residual
+//   * layer 4 (N = 64): 384 D columns + two shared 64-column A buffers handed from tile to tile through per-tile mbarriers
+//     (TcPipe), staged by all three warp groups; the residual
 //     half is issued before the layer-4 graph contraction and executes behind it; the head starts on the j = 0 tiles
 //     while the j = 1 tiles still execute;
 //   * tile software pipelining: head reduction + score of tile i run in the first stage of tile i+1; the layer-1 graph
@@ -80,95 +81,90 @@ static_assert((2 * kRBig + 2 * kRSmall + kTcGB) % 4 == 0, "weight staging buffer
 constexpr int kTcSmemFloats = 2 * kRBig + 2 * kRSmall + kTcGB        // R0, R1, XB[2], GB
                               + kTwFloats + kAwFloats + kTcWsFloats + kTcWbFloats
                               + 2 * kTcWarps * kNW * kDP + kNW * kDP + 32   // zpart[2], zfin, center
-                              + 32;                                     // mbarriers (11 x 8 B) + tmem base
+                              + 40;                                     // mbarriers (18 x 8 B) + tmem base + task counter
 constexpr int kTcSmemBytes = kTcSmemFloats * 4;
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory plan exceeds 227 KB");
 
 struct TcPipe {
-  uint64_t* full;     // [2] A buffer b staged (128 arrivals)
-  uint64_t* empty;    // [2] MMAs reading A buffer b complete (1 arrival: tcgen05.commit)
-  uint64_t* done;     // all MMAs of a phase complete
-  uint64_t* half;     // optional: the first kNW tiles (position half j = 0) of the phase complete; nullptr = not signalled
+  uint64_t* tdone;    // [6] MMAs of tile ti complete (1 arrival: tcgen05.commit of the group that issued it)
+  uint64_t* done;     // all MMAs of a phase complete (3 arrivals: one commit per warp group)
+  uint64_t* half;     // optional: the first kNW tiles (position half j = 0) of the phase complete (3 arrivals); nullptr = not signalled
   uint32_t n_half;
   uint32_t tbase;
-  uint32_t n_full[2], n_empty[2], n_done;   // completed-phase counters (identical on every thread)
+  uint32_t n_phase, n_done;   // completed layer-4 phases / done waits (identical on every thread)
 };
 
-// One mixing phase over the 6 M-tiles: D[ti] (+)= [src1 | src2](positions of ti, K channels) * B^T.
-// Warps 0-3 stage tiles 0,2,4 into A buffer 0, warps 4-7 tiles 1,3,5 into buffer 1, lane 0 of warp 8 issues.
+// One layer-4 mixing phase over the 6 M-tiles: D[ti] (+)= [src1 | src2](positions of ti, K channels) * B^T  (N = 64: the
+// 384 D columns leave room for two shared 64-column A buffers).  All 12 warps produce: warp group g (4 warps = the 4 TMEM lane
+// quarters) stages tiles g (j = 0) and g + 3 (j = 1) of its window into A buffer ti & 1, syncs its 4 warps on a named barrier,
+// and its first lane issues the tile's MMAs and commits them to the tile's own mbarrier tdone[ti].  A buffer is handed from
+// tile ti - 2 to tile ti (across groups): the producers of tile ti wait on tdone[ti - 2] of this phase (tiles 0 and 1: on
+// tdone[4] / tdone[5] of the previous phase).  One mbarrier per tile, used once per phase, keeps the parity waits unambiguous
+// whatever the lag between the groups (a shared per-buffer barrier would let a group that skipped a generation pass early).
+// The chains 4 <- 2 <- 0 and 5 <- 3 <- 1 are acyclic: every group issues its first tile before it waits for a later one.
 // K1 + K2 <= 32; Kp = K rounded up to 8 (the extra columns are staged as zeros).
 struct NoFiller { __device__ __forceinline__ void operator()() const {} };
-// `filler` runs on the producer warps after each staged tile: useful work instead of blocking on the A-buffer hand-off
-// (the two A buffers pace the producers at the MMA rate)
+// `filler` runs on every warp between its two tiles: useful work while the other groups' MMAs free the next A buffer
 template <int K1, int K2, int N, class Filler = NoFiller>
 __device__ __forceinline__ void tc_mix_phase(TcPipe& P, const float* src1, const float* src2, const float* Bhi, const float* Blo,
                                              bool accumulate, int warp, int lane, Filler filler = Filler{}) {
   constexpr int K = K1 + K2;
   constexpr int Kp = (K + 7) & ~7;
   static_assert(Kp <= 32 && N % 16 == 0 && N <= 64, "bad mixing phase shape");
-  const int q = warp & 3, sub = warp >> 2;
-  if (sub < 2) {
-    // ---------------- producers
-    const int b = sub;
+  const int q = warp & 3, g = warp >> 2;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int ti = g + kNW * r;                        // = j * kNW + n with n = g, j = r
+    const int b = ti & 1;
+    const int n = g;
+    const int p = r * 128 + q * 32 + lane;
+    const bool valid = p < kP;
+    const int pc = valid ? p : kP - 1;
     const uint32_t abuf = P.tbase + (static_cast<uint32_t>(q * 32) << 16) + kTcColA + 64u * b;
-    for (int it = 0; it < kTcTiles / 2; ++it) {
-      const int ti = b + 2 * it;
-      const int n = ti % kNW, j = ti / kNW;
-      const int p = j * 128 + q * 32 + lane;
-      const bool valid = p < kP;
-      const int pc = valid ? p : kP - 1;
-      tc::mbar_wait(&P.empty[b], (P.n_empty[b] + it) & 1);
-      tc::fence_after_sync();
+    if (ti >= 2) tc::mbar_wait(&P.tdone[ti - 2], P.n_phase & 1);                       // previous user, this phase
+    else if (P.n_phase > 0) tc::mbar_wait(&P.tdone[ti + 4], (P.n_phase - 1) & 1);        // last user of the previous phase
+    tc::fence_after_sync();
 #pragma unroll
-      for (int k0 = 0; k0 < Kp; k0 += 16) {
-        uint32_t hi[16], lo[16];
+    for (int k0 = 0; k0 < Kp; k0 += 16) {
+      uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int k = k0 + u;
-          float a = 0.f;
-          if (k < K1) a = src1[(n * K1 + k) * kCS + pc];
-          else if (k < K) a = src2[(n * K2 + (k - K1)) * kCS + pc];
-          if (!valid) a = 0.f;
-          tc::split_tf32(a, hi[u], lo[u]);
-        }
-        tc::tmem_st16(abuf + k0, hi);
-        tc::tmem_st16(abuf + 32 + k0, lo);
+      for (int u = 0; u < 16; ++u) {
+        const int k = k0 + u;
+        float a = 0.f;
+        if (k < K1) a = src1[(n * K1 + k) * kCS + pc];
+        else if (k < K) a = src2[(n * K2 + (k - K1)) * kCS + pc];
+        if (!valid) a = 0.f;
+        tc::split_tf32(a, hi[u], lo[u]);
       }
-      tc::wait_st();
-      tc::fence_before_sync();
-      tc::mbar_arrive(&P.full[b]);
-      if (it + 1 < kTcTiles / 2) filler();
+      tc::tmem_st16(abuf + k0, hi);
+      tc::tmem_st16(abuf + 32 + k0, lo);
     }
-  } else if (warp == 8) {
-    // ---------------- MMA issuer (one lane)
-    if (lane == 0) {
+    tc::wait_st();
+    tc::fence_before_sync();
+    asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+    if (q == 0 && lane == 0) {
+      tc::fence_after_sync();
       const uint32_t idesc = tc::make_idesc_tf32(128, N);
       constexpr uint32_t lbo = (N / 8) * 128, sbo = 128;
       const uint32_t bh = tc::smem_u32(Bhi), bl = tc::smem_u32(Blo);
-      for (int ti = 0; ti < kTcTiles; ++ti) {
-        const int b = ti & 1, it = ti >> 1;
-        tc::mbar_wait(&P.full[b], (P.n_full[b] + it) & 1);
-        tc::fence_after_sync();
-        const uint32_t d = P.tbase + kTcColD + 64u * ti;
-        const uint32_t a = P.tbase + kTcColA + 64u * b;
+      const uint32_t d = P.tbase + kTcColD + 64u * ti;
+      const uint32_t a = P.tbase + kTcColA + 64u * b;
 #pragma unroll
-        for (int kb = 0; kb < Kp / 8; ++kb) {
-          const uint64_t dh = tc::make_smem_desc(bh + kb * 2 * lbo, lbo, sbo);
-          const uint64_t dl = tc::make_smem_desc(bl + kb * 2 * lbo, lbo, sbo);
-          tc::mma_tf32_ts(d, a + kb * 8, dh, idesc, (accumulate || kb > 0) ? 1u : 0u);
-          tc::mma_tf32_ts(d, a + 32 + kb * 8, dh, idesc, 1u);
-          tc::mma_tf32_ts(d, a + kb * 8, dl, idesc, 1u);
-        }
-        tc::mma_commit(&P.empty[b]);
-        if (ti == kNW - 1 && P.half != nullptr) tc::mma_commit(P.half);   // the j = 0 tiles of all windows are complete
+      for (int kb = 0; kb < Kp / 8; ++kb) {
+        const uint64_t dh = tc::make_smem_desc(bh + kb * 2 * lbo, lbo, sbo);
+        const uint64_t dl = tc::make_smem_desc(bl + kb * 2 * lbo, lbo, sbo);
+        tc::mma_tf32_ts(d, a + kb * 8, dh, idesc, (accumulate || kb > 0) ? 1u : 0u);
+        tc::mma_tf32_ts(d, a + 32 + kb * 8, dh, idesc, 1u);
+        tc::mma_tf32_ts(d, a + kb * 8, dl, idesc, 1u);
       }
-      tc::mma_commit(P.done);
+      tc::mma_commit(&P.tdone[ti]);
+      if (r == 0 && P.half != nullptr) tc::mma_commit(P.half);    // 3 arrivals: the j = 0 tiles of all windows are complete
+      if (r == 1) tc::mma_commit(P.done);                          // 3 arrivals: all MMAs of the phase are complete
     }
     __syncwarp();
+    if (r == 0) filler();
   }
-  // every thread advances the phase counters identically (3 completions per A-buffer barrier, 1 for done)
-  P.n_full[0] += kTcTiles / 2; P.n_full[1] += kTcTiles / 2;
-  P.n_empty[0] += kTcTiles / 2; P.n_empty[1] += kTcTiles / 2;
+  P.n_phase += 1;                                      // identical on every thread
 }
 __device__ __forceinline__ void tc_wait_done(TcPipe& P) {
   tc::mbar_wait(P.done, P.n_done & 1);
@@ -280,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   float* zfin = zpart + 2 * kTcWarps * kNW * kDP;        // decoder variant: latents of the tile
   float* cen = zfin + kNW * kDP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(cen + 32);     // full[2], empty[2], done, small-phase done[6]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);   // bars[11]: layer-4 graph half, j = 0 tiles complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);   // bars[11]: layer-4 graph half, j = 0 tiles complete; bars[12..17]: layer-4 tiles
   int* task_ctr = reinterpret_cast<int*>(tmem_slot + 1);          // dynamic task hand-out of the layer-4 temporal stage
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -340,10 +336,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   if (tid < 32) cen[tid] = (Pm.center != nullptr && tid < Pm.D) ? Pm.center[tid] : 0.f;
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
   if (tid == 32) {
-    tc::mbar_init(&bars[0], 128); tc::mbar_init(&bars[1], 128);
-    tc::mbar_init(&bars[2], 1);   tc::mbar_init(&bars[3], 1);
-    tc::mbar_init(&bars[4], 1);
-    tc::mbar_init(&bars[11], 1);
+    tc::mbar_init(&bars[4], kNW);                                 // bars[0..3]: unused
+    tc::mbar_init(&bars[11], kNW);
+#pragma unroll
+    for (int i = 0; i < kTcTiles; ++i) tc::mbar_init(&bars[12 + i], 1);
 #pragma unroll
     for (int i = 0; i < 6; ++i) tc::mbar_init(&bars[5 + i], 1);
     tc::fence_mbar_init();
@@ -356,13 +352,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   cp_async_commit();
   boundary();
   TcPipe pipe;
-  pipe.full = &bars[0]; pipe.empty = &bars[2]; pipe.done = &bars[4];
+  pipe.tdone = &bars[12]; pipe.done = &bars[4];
   pipe.half = nullptr; pipe.n_half = 0;
   pipe.tbase = *tmem_slot;
-  pipe.n_full[0] = pipe.n_full[1] = 0; pipe.n_done = 0;
-  // both A buffers start out free: one manual arrival completes phase 0 of the empty barriers
-  if (tid == 0) { tc::mbar_arrive(&bars[2]); tc::mbar_arrive(&bars[3]); }
-  pipe.n_empty[0] = pipe.n_empty[1] = 0;
+  pipe.n_phase = 0; pipe.n_done = 0;
   SmallPipe spipe;
   spipe.done = &bars[5]; spipe.tbase = pipe.tbase; spipe.uses = 0;
   const int gq = warp & 3, gg = warp >> 2;          // TMEM lane quarter, warp group (= window in the small phases)
