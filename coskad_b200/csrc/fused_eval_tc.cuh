@@ -305,19 +305,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       }
     }
   };
-  // test-time affine transform of a landed input tile, in place (utils/dataset_utils.py:270-284 apply_pose_transform)
-  auto transform_x = [&](float* buf, int64_t tile, int t0, int nthreads) {
-    if (Pm.trans == nullptr) return;
-    for (int i = t0; i < kNW * kP; i += nthreads) {
-      const int n = i / kP, p = i - n * kP;
-      int64_t w = tile * kNW + n;
-      if (w >= Pm.B) w = Pm.B - 1;
-      int ti = Pm.trans[w];
-      ti = ti < 0 ? 0 : (ti >= Pm.n_mats ? Pm.n_mats - 1 : ti);
-      const float* m = Pm.mats + ti * 6;
-      const float x = buf[(n * 2) * kCS + p], y = buf[(n * 2 + 1) * kCS + p];
-      buf[(n * 2) * kCS + p] = fmaf(__ldg(m + 0), x, fmaf(__ldg(m + 1), y, __ldg(m + 2)));
-      buf[(n * 2 + 1) * kCS + p] = fmaf(__ldg(m + 3), x, fmaf(__ldg(m + 4), y, __ldg(m + 5)));
+  // test-time affine transform of a landed input tile, in place (utils/dataset_utils.py:270-284 apply_pose_transform); run by
+  // 96 threads: 32 lanes per window, so the window's matrix is fetched once per thread
+  auto transform_x = [&](float* buf, int64_t tile, int t96) {
+    if (Pm.trans == nullptr || t96 >= kNW * 32) return;
+    const int n = t96 >> 5, l = t96 & 31;
+    int64_t w = tile * kNW + n;
+    if (w >= Pm.B) w = Pm.B - 1;
+    int ti = Pm.trans[w];
+    ti = ti < 0 ? 0 : (ti >= Pm.n_mats ? Pm.n_mats - 1 : ti);
+    const float* m = Pm.mats + ti * 6;
+    const float m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2), m3 = __ldg(m + 3), m4 = __ldg(m + 4), m5 = __ldg(m + 5);
+    float* bx = buf + (n * 2) * kCS;
+    float* by = bx + kCS;
+    for (int p = l; p < kP; p += 32) {
+      const float x = bx[p], y = by[p];
+      bx[p] = fmaf(m0, x, fmaf(m1, y, m2));
+      by[p] = fmaf(m3, x, fmaf(m4, y, m5));
     }
   };
   auto acopy = [&](float* dst, const float* src, int nfloats) {
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   //      three warps of TMEM lane quarter 3 during the head stage, where they have half the work of the other quarters
   //      (positions 224..255 do not exist): see the end of stage S11.
   boundary();
-  if (Pm.trans != nullptr) { transform_x(XB, blockIdx.x, tid, kTcThreads); __syncthreads(); }
+  if (Pm.trans != nullptr) { transform_x(XB, blockIdx.x, tid); __syncthreads(); }
   temporal_stage_l1<kTcWarps>(XB, GB, TB, warp, lane);
   boundary();
   spatial_stage_l1<kTcWarps>(GB, AB, warp, lane);
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       for (int i = t96 * 4; i < kAwFloats; i += 96 * 4) cp_async16(AB + i, Pm.eAw[0] + i);
       cp_async_commit();
       float* Xn = XB + (cur ^ 1) * kRSmall;
-      if (Pm.trans != nullptr) { transform_x(Xn, next_tile, t96, 96); asm volatile("bar.sync 4, 96;" ::: "memory"); }
+      if (Pm.trans != nullptr) { transform_x(Xn, next_tile, t96); asm volatile("bar.sync 4, 96;" ::: "memory"); }
       temporal_stage_l1<3>(Xn, GB, TB, gg, lane);
       cp_async_wait_all();
       asm volatile("bar.sync 4, 96;" ::: "memory");

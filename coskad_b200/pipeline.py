@@ -127,9 +127,8 @@ class TrajectoryScorer:
         for i in range(nchunks):
             lo, hi = i * self.chunk, min((i + 1) * self.chunk, N)
             comp.wait_event(ready[i])
-            _, s = self.model.encode_score_traj(traj, rows_d[lo:hi], None if tr_d is None else tr_d[lo:hi], mt,
-                                                flavour=self.flavour, center=center, want_latent=False)
-            dscore[lo:hi].copy_(s)
+            self.model.encode_score_traj(traj, rows_d[lo:hi], None if tr_d is None else tr_d[lo:hi], mt, flavour=self.flavour,
+                                         center=center, want_latent=False, score_out=dscore[lo:hi])
         self.h2d_bytes += N * 8 + (N * 4 if tr_d is not None else 0)
         out_host.copy_(dscore, non_blocking=True)
         self.d2h_bytes += N * 4

@@ -253,7 +253,8 @@ class STSE(nn.Module):
     @torch.no_grad()
     def encode_score_traj(self, traj: torch.Tensor, win_row: torch.Tensor, trans: Optional[torch.Tensor] = None,
                           mats: Optional[torch.Tensor] = None, flavour: int = _lib.SCORE_NONE,
-                          center: Optional[torch.Tensor] = None, want_latent: bool = True
+                          center: Optional[torch.Tensor] = None, want_latent: bool = True,
+                          score_out: Optional[torch.Tensor] = None
                           ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         """Fused eval hot path fed from trajectories: window construction (utils/preprocessing.py:58-89) and the
         test-time affine transforms (utils/dataset.py:65-74, utils/dataset_utils.py:255-310) happen inside the kernel.
@@ -284,7 +285,12 @@ class STSE(nn.Module):
         score = cen = None
         if flavour != _lib.SCORE_NONE:
             cen = (self.c if center is None else center).to(device=traj.device, dtype=torch.float32).contiguous().view(-1)
-            score = torch.empty((N,), device=traj.device, dtype=torch.float32)
+            if score_out is not None:
+                assert score_out.is_cuda and score_out.dtype == torch.float32 and score_out.is_contiguous() \
+                    and score_out.numel() == N
+                score = score_out
+            else:
+                score = torch.empty((N,), device=traj.device, dtype=torch.float32)
         rc = ctx.lib.coskad_encode_score_traj_fwd(ctx.h, int(flavour), traj.data_ptr(), traj.shape[0], win_row.data_ptr(),
                                                   _lib._ptr(trans), _lib._ptr(mats), n_mats, _lib._ptr(cen), N,
                                                   _lib._ptr(Z), _lib._ptr(score), _lib.stream_ptr(traj.device))

@@ -35,3 +35,17 @@ sv = sv.to(dev).eval()
 mv = torch.nn.functional.normalize(torch.randn(1, 8, device=dev), dim=-1)
 ms = timeit(lambda: sv.cosine_scores(x, mean_vector=mv, sample=False))
 print(f'STSVAE D=8 (9-row head) cosine score on the mean direction: {ms:.2f} ms -> {B/ms*1e3/1e6:.2f} M windows/s')
+# trajectory front end, device-resident: stride-1 windows of 300-frame persons x 5 transforms
+import math
+from coskad_b200 import _lib as L
+plen, per = 300, 300 - 12 + 1
+persons = B // (5 * per)
+base = torch.arange(per, device=dev).repeat(persons) + torch.arange(persons, device=dev).repeat_interleave(per) * plen
+rows = base.repeat(5).contiguous()
+tr = torch.arange(5, device=dev, dtype=torch.int32).repeat_interleave(base.numel()).contiguous()
+traj = (torch.randn(persons * plen, 34, device=dev) * 0.4).contiguous()
+c45 = math.cos(math.radians(45.0))
+mats = torch.tensor([[[1, 0, 0], [0, 1, 0]], [[-1, 0, 0], [0, 1, 0]], [[0, -1, 0], [1, 0, 0]], [[0, 1, 0], [1, 0, 0]],
+                     [[c45, -c45, 0], [c45, c45, 0]]], dtype=torch.float32, device=dev)
+ms = timeit(lambda: e16.encode_score_traj(traj, rows, tr, mats, flavour=1, center=c16, want_latent=False))
+print(f'STSE D=16 from trajectories ({rows.numel()} windows, 5 transforms, device-resident): {ms:.2f} ms -> {rows.numel()/ms*1e3/1e6:.2f} M windows/s')
