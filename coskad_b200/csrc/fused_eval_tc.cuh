@@ -654,27 +654,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       // ---- S13: folded first decoder layer: H = PReLU(M z + m0) -> R0 (32 ch)
       //      (rev_btlnk models/sts/ae.py:222 + decoder layer 0 linear part, collapsed at set_decoder)
       {
+        // M (32*204 rows x DL) streams from L2 once per tile: all loads of a batch of kFB rows are issued before the first
+        // FMA (as a load -> FMA loop this stage exposed the L2 latency 17 times and took 16 % of the auto-encoder's time)
+        constexpr int kFB = 6;
+        constexpr int kFN = (kC1 * kP) / kTcThreads;            // 17 rows per thread
+        static_assert(kFN * kTcThreads == kC1 * kP, "folded decoder layer: row split");
         const int DL = Pm.DL;
-        for (int i = tid; i < kC1 * kP; i += kTcThreads) {
-          const int co = i / kP, p = i - co * kP;
-          const float m0 = __ldg(Pm.dm0 + i);
-          float o[kNW];
+        float zr[kNW][kDP];                                     // the tile's latents, once per thread
 #pragma unroll
-          for (int n = 0; n < kNW; ++n) o[n] = m0;
-          const float4* m4 = reinterpret_cast<const float4*>(Pm.dM + static_cast<size_t>(i) * DL);
-          for (int d4 = 0; d4 < DL / 4; ++d4) {
-            const float4 m = __ldg(m4 + d4);
+        for (int n = 0; n < kNW; ++n)
 #pragma unroll
-            for (int n = 0; n < kNW; ++n) {
-              const float* zz = zfin + n * kDP + d4 * 4;
-              o[n] = fmaf(m.x, zz[0], o[n]);
-              o[n] = fmaf(m.y, zz[1], o[n]);
-              o[n] = fmaf(m.z, zz[2], o[n]);
-              o[n] = fmaf(m.w, zz[3], o[n]);
-            }
+          for (int d = 0; d < kDP; ++d) zr[n][d] = (d < 8 || DL > 8) ? zfin[n * kDP + d] : 0.f;
+        for (int b0 = 0; b0 < kFN; b0 += kFB) {
+          float m0[kFB];
+          float4 ma[kFB], mb[kFB], mc[kFB], md[kFB];
+#pragma unroll
+          for (int j = 0; j < kFB; ++j) {
+            const int i = tid + (b0 + j < kFN ? b0 + j : kFN - 1) * kTcThreads;
+            m0[j] = __ldg(Pm.dm0 + i);
+            const float4* m4 = reinterpret_cast<const float4*>(Pm.dM + static_cast<size_t>(i) * DL);
+            ma[j] = __ldg(m4); mb[j] = __ldg(m4 + 1);
+            if (DL > 8) { mc[j] = __ldg(m4 + 2); md[j] = __ldg(m4 + 3); }
           }
 #pragma unroll
-          for (int n = 0; n < kNW; ++n) R0[(n * kC1 + co) * kCS + p] = prelu(o[n], Pm.d_slope0);
+          for (int j = 0; j < kFB; ++j) {
+            if (b0 + j < kFN) {
+              const int i = tid + (b0 + j) * kTcThreads;
+              const int co = i / kP, p = i - co * kP;
+#pragma unroll
+              for (int n = 0; n < kNW; ++n) {
+                // two independent partial sums halve the dependent FMA chain
+                float o = m0[j], o2 = 0.f;
+                o = fmaf(ma[j].x, zr[n][0], o); o2 = fmaf(ma[j].y, zr[n][1], o2); o = fmaf(ma[j].z, zr[n][2], o); o2 = fmaf(ma[j].w, zr[n][3], o2);
+                o = fmaf(mb[j].x, zr[n][4], o); o2 = fmaf(mb[j].y, zr[n][5], o2); o = fmaf(mb[j].z, zr[n][6], o); o2 = fmaf(mb[j].w, zr[n][7], o2);
+                if (DL > 8) {
+                  o = fmaf(mc[j].x, zr[n][8], o); o2 = fmaf(mc[j].y, zr[n][9], o2); o = fmaf(mc[j].z, zr[n][10], o); o2 = fmaf(mc[j].w, zr[n][11], o2);
+                  o = fmaf(md[j].x, zr[n][12], o); o2 = fmaf(md[j].y, zr[n][13], o2); o = fmaf(md[j].z, zr[n][14], o); o2 = fmaf(md[j].w, zr[n][15], o2);
+                }
+                R0[(n * kC1 + co) * kCS + p] = prelu(o + o2, Pm.d_slope0);
+              }
+            }
+          }
         }
       }
       // ---- S14: D2 (32->16) mix-first: R0 -> U (R1 rows 0..47), Rsd (rows 48..95)
