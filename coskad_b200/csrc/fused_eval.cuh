@@ -696,22 +696,25 @@ __device__ __forceinline__ void temporal_stage_l1(const float* src, float* dst, 
   constexpr int ROWS = kNW * kC0;                 // 6
   const int row = lane % ROWS, qg = lane / ROWS;  // qg 0..3 -> outputs q = 3 qg .. 3 qg + 2 (lanes >= 24 idle)
   for (int v = warp; v < kV; v += NWARPS) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (qg < 4) {
       const float* s = src + row * kCS + v;
       const float* w = Tw + v * (kT * kT) + 3 * qg;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int t = 0; t < kT; ++t) {
         const float x = s[t * kV];
         a0 = fmaf(x, w[t * kT + 0], a0); a1 = fmaf(x, w[t * kT + 1], a1); a2 = fmaf(x, w[t * kT + 2], a2);
       }
+    }
+    __syncwarp();      // src == dst is allowed: every lane of the row has read the column before anyone overwrites it
+    if (qg < 4) {
       float* d = dst + row * kCS + v;
       d[(3 * qg + 0) * kV] = a0; d[(3 * qg + 1) * kV] = a1; d[(3 * qg + 2) * kV] = a2;
     }
   }
 }
-template <int NWARPS>
-__device__ __forceinline__ void spatial_stage_l1(float* buf, const float* Aw, int warp, int lane) {
+template <int NWARPS, class Epi = EpiIdentity>
+__device__ __forceinline__ void spatial_stage_l1(float* buf, const float* Aw, int warp, int lane, const Epi epi = Epi{}) {
   constexpr int ROWS = kNW * kC0;                 // 6
   const int row = lane % ROWS, wg = lane / ROWS;  // wg 0..4 -> outputs w = 4 wg .. 4 wg + 3 (w < 17; lanes >= 30 idle)
   for (int t = warp; t < kT; t += NWARPS) {
@@ -729,7 +732,7 @@ __device__ __forceinline__ void spatial_stage_l1(float* buf, const float* Aw, in
     __syncwarp();      // every lane of the row has read its 17 inputs before anyone overwrites them (in place)
     if (wg < 5) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (4 * wg + j < kV) s[4 * wg + j] = acc[j];
+      for (int j = 0; j < 4; ++j) if (4 * wg + j < kV) s[4 * wg + j] = epi(acc[j], row, t * kV + 4 * wg + j);
     }
   }
 }

@@ -748,10 +748,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       boundary();
       acopy(WMs, Pm.mixL1, mix_blob_floats(4, 32));
       cp_async_commit();
-      temporal_stage<kNW * kC0, kTcWarps>(U4, U4, TB, warp, lane);
+      temporal_stage_l1<kTcWarps>(U4, U4, TB, warp, lane);
       // ---- S22: D4 spatial + residual + PReLU -> xhat in U4
       boundary();
-      spatial_stage<kNW * kC0, EpiAddResPrelu, kTcWarps>(U4, AB, EpiAddResPrelu{Rsd4, dslope3}, warp, lane);
+      spatial_stage_l1<kTcWarps, EpiAddResPrelu>(U4, AB, warp, lane, EpiAddResPrelu{Rsd4, dslope3});
       // ---- S23: reconstruction score mean_{c,t,v}(x - xhat)^2, optional xhat store
       boundary();
       if (warp < kNW) {
