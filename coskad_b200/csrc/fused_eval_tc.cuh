@@ -337,7 +337,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   };
 
   // ---- prologue ------------------------------------------------------------------------------------
-  if (tid < 32) cen[tid] = (Pm.center != nullptr && tid < Pm.D) ? Pm.center[tid] : 0.f;
+  // cen[0..15]: center (zero padded), cen[16..31]: head bias
+  if (tid < 16) cen[tid] = (Pm.center != nullptr && tid < Pm.D) ? Pm.center[tid] : 0.f;
+  else if (tid < 32) cen[tid] = __ldg(Pm.head_b + (tid - 16));
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
   if (tid == 32) {
     tc::mbar_init(&bars[4], kNW);                                 // bars[0..3]: unused
@@ -367,26 +369,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   // head reduction, geometry and score of a finished tile (its per-warp partial sums are in zpart[buf]): warp 9 + n takes
   // window n.  Deferred into stage S0 of the NEXT tile (whose opening barrier publishes zpart) so that it overlaps the
   // layer-1 contraction instead of costing two barriers of its own.
-  auto finalize = [&](int64_t ftile, int buf) {
+  // phase 0: latents only (-> zfin, what the decoder waits for); phase 1: outputs (z, score) from zfin; phase 2: both
+  auto finalize = [&](int64_t ftile, int buf, int phase) {
     const int n = warp - (kTcWarps - kNW);
     if (n < 0) return;
     const int64_t w = ftile * kNW + n;
-    if (w >= Pm.B) {                                   // ragged last tile: the decoder still runs on a finite dummy latent
-      if (kDec && lane < kDP) zfin[n * kDP + lane] = 0.f;
-      return;
-    }
     float s = 0.f;
-    if (lane < kDP) {
-      s = __ldg(Pm.head_b + lane);
+    if (phase != 1) {
+      if (lane < kDP && w < Pm.B) {
+        s = cen[16 + lane];
 #pragma unroll
-      for (int ww = 0; ww < kTcWarps; ++ww) s += zpart[(buf * kTcWarps + ww) * (kNW * kDP) + n * kDP + lane];
+        for (int ww = 0; ww < kTcWarps; ++ww) s += zpart[(buf * kTcWarps + ww) * (kNW * kDP) + n * kDP + lane];
+      }
+      if (kDec && lane < kDP) zfin[n * kDP + lane] = s;   // ragged last tile: the decoder runs on a finite dummy latent (0)
+      if (phase == 0) return;
+    } else {
+      s = lane < kDP ? zfin[n * kDP + lane] : 0.f;
     }
+    if (w >= Pm.B) return;
     float u[1] = {s};
-    if (kDec && lane < kDP) zfin[n * kDP + lane] = s;
     if (Pm.z != nullptr && lane < Pm.head_rows) Pm.z[w * Pm.head_rows + lane] = u[0];
     if (Pm.score != nullptr) {
       if (lane >= Pm.D) u[0] = 0.f;
-      const float c[1] = {cen[lane]};
+      const float c[1] = {lane < 16 ? cen[lane] : 0.f};
       const float sc = score_from_latent<1>(Pm.flavour, u, c, Pm.D);
       if (lane == 0) Pm.score[w] = sc;
     }
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
     acopy(TB, Pm.eTw[1], kTwFloats);
     if (next_tile < ntiles) load_x(XB + (cur ^ 1) * kRSmall, next_tile);
     cp_async_commit();
-    if (!kDec && last_tile >= 0) finalize(last_tile, cur ^ 1);
+    if (!kDec && last_tile >= 0) finalize(last_tile, cur ^ 1, 2);
     last_tile = tile;
     float* U2 = R1;
     float* Rsd2 = R1 + kNW * kC2 * kCS;
@@ -649,8 +654,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
       acopy(WMs, Pm.tcD2, tc_blob_floats(32, 32));
       acopy(WMb, Pm.tcD3, tc_blob_floats(32, 32));
       cp_async_commit();
-      finalize(tile, cur);
+      finalize(tile, cur, 0);
       __syncthreads();
+      finalize(tile, cur, 1);                          // outputs (z, latent score) off the decoder's critical path
       // ---- S13: folded first decoder layer: H = PReLU(M z + m0) -> R0 (32 ch)
       //      (rev_btlnk models/sts/ae.py:222 + decoder layer 0 linear part, collapsed at set_decoder)
       {
@@ -774,7 +780,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_eval_tc_kernel(const __gr
   cp_async_wait_all();
   tc::fence_before_sync();
   __syncthreads();
-  if (!kDec && last_tile >= 0) finalize(last_tile, cur ^ 1);
+  if (!kDec && last_tile >= 0) finalize(last_tile, cur ^ 1, 2);
   if (warp == 0) tc::tmem_dealloc(pipe.tbase, 512);
 }
 
