@@ -699,14 +699,25 @@ extern "C" int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const flo
     const int rc = launch_chan_gemm(ctx, false, dy1, dy2, W1, W2, 1, nullptr, nullptr, B, CO, CI, dG, dXres, nullptr, st);
     if (rc) return rc;
   }
-  const size_t smem2 = sizeof(float) * 2 * (CO + CI) * kWCS;
-  if ((CO >= 4 && CO % 4) || (CI >= 4 && CI % 4) || (CO / (CO < 4 ? CO : 4)) * (CI / (CI < 4 ? CI : 4)) > 128 ||
-      (CO / (CO < 4 ? CO : 4)) * (CI / (CI < 4 ? CI : 4)) < 8)
+  const int tco = CO < 4 ? CO : 4, tci = CI < 4 ? CI : 4;
+  const int ntile = (CO / tco) * (CI / tci);
+  if ((CO >= 4 && CO % 4) || (CI >= 4 && CI % 4) || ntile > 128 || ntile < 8)
     return fail(ctx, COSKAD_ERR_ARG, "train_mix_bwd: unsupported channel pair %d -> %d", CI, CO);
-  CK(cudaFuncSetAttribute(train_mix_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-  int g2 = static_cast<int>((B * kP + kWC - 1) / kWC);
+  // two staging buffers of [2 (CO + CI)][WC + 4] floats; >= 32 KB for the final reduction over the k-slices
+  const int wc = (CO + CI) > 48 ? 64 : 128;
+  if ((ntile & (ntile - 1)) || (wc * ntile / kTrainThreads) % 4)
+    return fail(ctx, COSKAD_ERR_ARG, "train_mix_bwd: unsupported tile split for %d -> %d", CI, CO);
+  size_t smem2 = sizeof(float) * 2 * 2 * (CO + CI) * (wc + 4);
+  if (smem2 < sizeof(float) * 32 * kTrainThreads) smem2 = sizeof(float) * 32 * kTrainThreads;
+  int g2 = static_cast<int>((B * kP + wc - 1) / wc);
   if (g2 > ctx->sm_count * 2) g2 = ctx->sm_count * 2;
-  train_mix_bwd_weight_kernel<<<g2, kTrainThreads, smem2, st>>>(dy1, dy2, G, X, B, CI, CO, dW1, db1, dW2, db2);
+  if (wc == 64) {
+    CK(cudaFuncSetAttribute(train_mix_bwd_weight_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+    train_mix_bwd_weight_kernel<64><<<g2, kTrainThreads, smem2, st>>>(dy1, dy2, G, X, B, CI, CO, dW1, db1, dW2, db2);
+  } else {
+    CK(cudaFuncSetAttribute(train_mix_bwd_weight_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+    train_mix_bwd_weight_kernel<128><<<g2, kTrainThreads, smem2, st>>>(dy1, dy2, G, X, B, CI, CO, dW1, db1, dW2, db2);
+  }
   CK_LAUNCH();
   return COSKAD_OK;
 }

@@ -416,111 +416,131 @@ __global__ void train_bn_prelu_bwd_apply_kernel(const float* __restrict__ dout, 
 }
 
 // dW1[co,ci] += sum_e dy1[e,co] G[e,ci]; db1[co] += sum_e dy1[e,co]; same for the residual branch (e = (b,p)).
-// A split-K "GEMM" with tiny M x N (<= 64 x 64) and K = B*204: every block stages chunks of kWC elements e of all channels
-// in shared memory as rows [c][kWC + 4] (row stride = 4 mod 32 banks: LDS.128 of 8 consecutive rows is conflict free),
-// every thread owns a 4 x 4 tile of (co, ci) pairs with STRIDED members (co = cot + i*NOT, ci = cit + j*NCT, so that the
-// lanes of a quarter warp read consecutive rows) and, when there are fewer than 256 tiles, one of the k-slices of the
-// chunk; 16 LDS.128 feed 128 FMAs.  One atomicAdd per pair per thread at the end.
-constexpr int kWC = 128;
-constexpr int kWCS = kWC + 4;
+// A split-K "GEMM" with tiny M x N (<= 64 x 64) and K = B*204: every block walks chunks of WC elements e of all channels,
+// staged in shared memory as rows [c][WC + 4] (row stride = 4 mod 32 banks: LDS.128 of 8 consecutive rows is conflict free)
+// with 16-byte asynchronous copies (4 consecutive positions never straddle a window: 204 = 4 * 51) into two buffers, the
+// next chunk in flight while this one is consumed.  Every thread owns a 4 x 4 tile of (co, ci) pairs with STRIDED members
+// (co = cot + i*NOT, ci = cit + j*NCT, so that the lanes of a quarter warp read consecutive rows) and, when there are fewer
+// than 256 tiles, one of the k-slices of the chunk; 16 LDS.128 feed 128 FMAs.  The bias gradients (row sums of dy) are a
+// separate cooperative pass over the staged rows (inside the tile loop every thread of a tile row repeated them: 32 extra
+// FADD per 64 FFMA2).  At the end the k-slices of a block are summed through shared memory and the block issues ONE
+// atomicAdd per weight (with one per thread the 2->32 layer sent 1.2 M atomics to 128 addresses: 178 us, ncu).
+// WC = 128 for <= 96 staged rows, 64 for the 64-channel layers: two buffers of either fit two blocks per SM.
+template <int WC>
 __global__ void __launch_bounds__(kTrainThreads) train_mix_bwd_weight_kernel(
     const float* __restrict__ dy1, const float* __restrict__ dy2, const float* __restrict__ G, const float* __restrict__ X,
     int64_t B, int CI, int CO, float* dW1, float* db1, float* dW2, float* db2) {
   extern __shared__ __align__(128) float sm[];
-  float* d1s = sm;                       // [CO][kWCS]
-  float* d2s = d1s + CO * kWCS;          // [CO][kWCS]
-  float* gs = d2s + CO * kWCS;           // [CI][kWCS]
-  float* xs = gs + CI * kWCS;            // [CI][kWCS]
+  constexpr int WCS = WC + 4;
+  constexpr int kV4 = WC / 4;                              // float4 per staged row
+  const int buf_floats = 2 * (CO + CI) * WCS;              // rows: [dy1 CO | dy2 CO | G CI | X CI]
   const int TCO = CO < 4 ? CO : 4, TCI = CI < 4 ? CI : 4;
   const int NOT = CO / TCO, NCT = CI / TCI;              // tiles along co / ci
-  const int ntile = NOT * NCT;                           // <= 128 for every configured layer
+  const int ntile = NOT * NCT;                           // 8 .. 128 for every configured layer
   const int nks = kTrainThreads / ntile;                 // k-slices (>= 2)
-  const int kslice = kWC / nks;                          // multiple of 4: ntile >= 8
+  const int kslice = WC / nks;                           // multiple of 4 (host-checked)
   const int tile = threadIdx.x % ntile, ks = threadIdx.x / ntile;
   const int cit = tile % NCT, cot = tile / NCT;
-  const bool active = ks < nks;
   // accumulators packed as (sum over even k, sum over odd k): both FFMA2 operands are natural halves of the float4 loads
   unsigned long long q1[4][4], q2[4][4];
-  float bs1[4], bs2[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bs1[i] = 0.f; bs2[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { q1[i][j] = 0ull; q2[i][j] = 0ull; }
-  }
-  const int64_t E = B * kP;
-  for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * kWC; e0 < E; e0 += static_cast<int64_t>(gridDim.x) * kWC) {
-    __syncthreads();
-    {
-      // element e = e0 + k of channel row c lives at ((b*C + c)*204 + p): one division per chunk, not per element
-      const int64_t b0 = e0 / kP;
-      const int p0 = static_cast<int>(e0 - b0 * kP);
-      const int k = threadIdx.x % kWC;                       // 256 threads: fixed k, rows c = threadIdx.x / kWC + 2 j
-      int p = p0 + k;
-      int64_t b = b0;
-      if (p >= kP) { p -= kP; b += 1; }
-      const bool valid = e0 + k < E;
-      // asynchronous copies: every load of the chunk is in flight at once (a load -> store loop exposed the full memory
-      // latency 96 times per chunk); the zero fill of the ragged tail uses plain stores
-      for (int c = threadIdx.x / kWC; c < CO + CI; c += kTrainThreads / kWC) {
-        if (c < CO) {
-          const int64_t o = (b * CO + c) * kP + p;
-          if (valid) { cp_async4(d1s + c * kWCS + k, dy1 + o); cp_async4(d2s + c * kWCS + k, dy2 + o); }
-          else { d1s[c * kWCS + k] = 0.f; d2s[c * kWCS + k] = 0.f; }
-        } else {
-          const int64_t o = (b * CI + (c - CO)) * kP + p;
-          if (valid) { cp_async4(gs + (c - CO) * kWCS + k, G + o); cp_async4(xs + (c - CO) * kWCS + k, X + o); }
-          else { gs[(c - CO) * kWCS + k] = 0.f; xs[(c - CO) * kWCS + k] = 0.f; }
-        }
-      }
-      cp_async_commit();
-      cp_async_wait_all();
-    }
-    __syncthreads();
-    if (active) {
-      for (int k = ks * kslice; k < (ks + 1) * kslice; k += 4) {
-        ulonglong2 d1[4], d2[4], g[4], x[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int co = (i < TCO) ? cot + i * NOT : cot;
-          const int ci = (i < TCI) ? cit + i * NCT : cit;
-          d1[i] = *reinterpret_cast<const ulonglong2*>(d1s + co * kWCS + k);
-          d2[i] = *reinterpret_cast<const ulonglong2*>(d2s + co * kWCS + k);
-          g[i] = *reinterpret_cast<const ulonglong2*>(gs + ci * kWCS + k);
-          x[i] = *reinterpret_cast<const ulonglong2*>(xs + ci * kWCS + k);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ffma2(q1[i][j], d1[i].x, g[j].x); ffma2(q1[i][j], d1[i].y, g[j].y);
-            ffma2(q2[i][j], d2[i].x, x[j].x); ffma2(q2[i][j], d2[i].y, x[j].y);
-          }
-          bs1[i] += (lo2(d1[i].x) + hi2(d1[i].x)) + (lo2(d1[i].y) + hi2(d1[i].y));
-          bs2[i] += (lo2(d2[i].x) + hi2(d2[i].x)) + (lo2(d2[i].y) + hi2(d2[i].y));
-        }
-      }
-    }
-  }
-  float a1[4][4], a2[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { a1[i][j] = lo2(q1[i][j]) + hi2(q1[i][j]); a2[i][j] = lo2(q2[i][j]) + hi2(q2[i][j]); }
-  if (active) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i >= TCO) break;
-      const int co = cot + i * NOT;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j >= TCI) break;
-        const int ci = cit + j * NCT;
-        atomicAdd(dW1 + co * CI + ci, a1[i][j]);
-        atomicAdd(dW2 + co * CI + ci, a2[i][j]);
-      }
-      if (cit == 0) { if (db1) atomicAdd(db1 + co, bs1[i]); if (db2) atomicAdd(db2 + co, bs2[i]); }
+    for (int j = 0; j < 4; ++j) { q1[i][j] = 0ull; q2[i][j] = 0ull; }
+  // bias pass: thread -> (row of [dy1 rows | dy2 rows], every tpr-th float4 of the chunk); 2*CO <= 128 rows
+  const int tpr = kTrainThreads / (2 * CO) < 32 ? kTrainThreads / (2 * CO) : 32;       // power of two
+  const int brow = threadIdx.x / tpr, bk4 = threadIdx.x % tpr;                        // rows >= 2*CO: idle threads
+  const bool want_bias = (db1 != nullptr || db2 != nullptr) && brow < 2 * CO;
+  float bsum = 0.f;
+  const int64_t E = B * kP;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * WC;
+  // elements e = e0 + 4 k4 .. + 3 of channel row c live at ((b*C + c)*204 + p): one division per thread and chunk
+  auto stage = [&](int64_t e0, float* buf) {
+    const int k4 = threadIdx.x % kV4;
+    const int64_t e = e0 + 4 * k4;
+    const int64_t b = e / kP;
+    const int p = static_cast<int>(e - b * kP);
+    const bool valid = e < E;                              // E % 4 == 0: a float4 is entirely in or out
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = threadIdx.x / kV4; c < CO + CI; c += kTrainThreads / kV4) {
+      const bool is_dy = c < CO;
+      const int r = is_dy ? c : c - CO;
+      const int64_t o = (b * (is_dy ? CO : CI) + r) * kP + p;
+      float* s1 = buf + (is_dy ? r : 2 * CO + r) * WCS + 4 * k4;
+      float* s2 = s1 + (is_dy ? CO : CI) * WCS;
+      if (valid) { cp_async16(s1, (is_dy ? dy1 : G) + o); cp_async16(s2, (is_dy ? dy2 : X) + o); }
+      else { *reinterpret_cast<float4*>(s1) = zero4; *reinterpret_cast<float4*>(s2) = zero4; }
     }
+    cp_async_commit();
+  };
+  int64_t e0 = static_cast<int64_t>(blockIdx.x) * WC;
+  if (e0 < E) stage(e0, sm);
+  for (int it = 0; e0 < E; e0 += stride, ++it) {
+    float* buf = sm + (it & 1) * buf_floats;
+    if (e0 + stride < E) {
+      stage(e0 + stride, sm + ((it + 1) & 1) * buf_floats);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      cp_async_wait_all();
+    }
+    __syncthreads();
+    const float* d1s = buf;                      // [CO][WCS]
+    const float* d2s = d1s + CO * WCS;           // [CO][WCS]
+    const float* gs = d2s + CO * WCS;            // [CI][WCS]
+    const float* xs = gs + CI * WCS;             // [CI][WCS]
+    if (want_bias) {
+      const float* row = d1s + brow * WCS;       // d2s follows d1s: rows CO.. are the residual branch
+      for (int q = bk4; q < kV4; q += tpr) {
+        const float4 v = *reinterpret_cast<const float4*>(row + 4 * q);
+        bsum += (v.x + v.y) + (v.z + v.w);
+      }
+    }
+    for (int k = ks * kslice; k < (ks + 1) * kslice; k += 4) {
+      ulonglong2 d1[4], d2[4], g[4], x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = (i < TCO) ? cot + i * NOT : cot;
+        const int ci = (i < TCI) ? cit + i * NCT : cit;
+        d1[i] = *reinterpret_cast<const ulonglong2*>(d1s + co * WCS + k);
+        d2[i] = *reinterpret_cast<const ulonglong2*>(d2s + co * WCS + k);
+        g[i] = *reinterpret_cast<const ulonglong2*>(gs + ci * WCS + k);
+        x[i] = *reinterpret_cast<const ulonglong2*>(xs + ci * WCS + k);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ffma2(q1[i][j], d1[i].x, g[j].x); ffma2(q1[i][j], d1[i].y, g[j].y);
+          ffma2(q2[i][j], d2[i].x, x[j].x); ffma2(q2[i][j], d2[i].y, x[j].y);
+        }
+      }
+    }
+    __syncthreads();                             // this buffer is restaged by the next iteration
+  }
+  // block reduction over the k-slices: red[v][thread], v = (i*4 + j)*2 + branch; then one atomic per weight and block
+  float* red = sm;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[((i * 4 + j) * 2 + 0) * kTrainThreads + threadIdx.x] = lo2(q1[i][j]) + hi2(q1[i][j]);
+      red[((i * 4 + j) * 2 + 1) * kTrainThreads + threadIdx.x] = lo2(q2[i][j]) + hi2(q2[i][j]);
+    }
+  __syncthreads();
+  for (int o = threadIdx.x; o < ntile * 32; o += kTrainThreads) {
+    const int t = o % ntile, v = o / ntile;
+    const int i = v >> 3, j = (v >> 1) & 3, branch = v & 1;
+    if (i >= TCO || j >= TCI) continue;
+    float acc = 0.f;
+    for (int s2 = 0; s2 < nks; ++s2) acc += red[v * kTrainThreads + s2 * ntile + t];
+    const int co = t / NCT + i * NOT, ci = t % NCT + j * NCT;
+    atomicAdd((branch ? dW2 : dW1) + co * CI + ci, acc);
+  }
+  // bias gradients: the tpr threads of a row are neighbouring lanes
+  for (int o = tpr >> 1; o > 0; o >>= 1) bsum += __shfl_down_sync(0xffffffffu, bsum, o, 32);
+  if (bk4 == 0 && brow < 2 * CO) {
+    if (brow < CO) { if (db1) atomicAdd(db1 + brow, bsum); }
+    else if (db2) atomicAdd(db2 + (brow - CO), bsum);
   }
 }
 

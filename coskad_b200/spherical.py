@@ -244,7 +244,7 @@ class LitSphericalVAE(LightningModule):
         return self.post_processing(hidden_out, trans, meta, frames)
 
     def configure_optimizers(self) -> Dict:
-        optimizer = Adam(self.parameters(), lr=self.learning_rate)
+        optimizer = Adam(self.parameters(), lr=self.learning_rate, fused=True)
         if getattr(self.args, 'validation', False):
             sched = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode='max', factor=0.2, patience=2, min_lr=1e-6)
             return {'optimizer': optimizer, 'lr_scheduler': sched, 'monitor': 'validation_auc'}

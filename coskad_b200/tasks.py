@@ -145,8 +145,14 @@ class LitEncoder(LightningModule):
         c = self._finalize_center(acc)
         self.model.c = c
         self.temp = c
-        self.centers.append(c)
+        self.centers.append(c.clone())
         self.model.train()
+
+    graph_safe = True
+
+    def on_train_epoch_start(self) -> None:
+        if self._acc is not None:
+            self._acc.zero_()
 
     # ---------------------------------------------------------------- training (:137-188)
     def training_step(self, batch, batch_idx):
@@ -155,7 +161,7 @@ class LitEncoder(LightningModule):
         loss_reg = calc_reg_loss(self.model)
         self.log('regularization', loss_reg)
         dynamic = not self.args.static_center
-        if dynamic and batch_idx == 0:
+        if dynamic and self._acc is None:          # zeroed per epoch in on_train_epoch_start
             self._acc = gmath.center_accumulator(self.model.latent_dim, data.device)
         self.model.c = self.temp
         if self.hyperbolic:
@@ -181,7 +187,11 @@ class LitEncoder(LightningModule):
         if self.hyperbolic:
             self.log('center/eucl', torch.norm(c, dim=-1))
             self.log('center/hyp', gmath.dist0(c.view(1, -1), k=-1.0)[0])
-        self.temp = c
+        # in place: a captured training step (Trainer(cuda_graph=True)) keeps reading this tensor
+        if self.temp is not None and self.temp.shape == c.shape:
+            self.temp.copy_(c)
+        else:
+            self.temp = c
         self.centers.append(c)
 
     def validation_step(self, batch, batch_idx):
@@ -192,7 +202,7 @@ class LitEncoder(LightningModule):
         return self.post_processing(hidden_out, trans, meta, frames)
 
     def configure_optimizers(self) -> Dict:
-        optimizer = Adam(self.parameters(), lr=self.learning_rate)          # no weight decay upstream (:199)
+        optimizer = Adam(self.parameters(), lr=self.learning_rate, fused=True)          # no weight decay upstream (:199)
         if getattr(self.args, 'validation', False):
             sched = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode='max', factor=0.2, patience=100, min_lr=1e-6)
             return {'optimizer': optimizer, 'lr_scheduler': sched, 'monitor': 'validation_auc'}
@@ -237,6 +247,8 @@ class LitAutoEncoder(LightningModule):
         self.temp = None
         self._acc = None
 
+    graph_safe = True          # static center, no per-epoch training state
+
     def forward(self, x):
         """(out, hidden, gt_data, trans, meta, frames): the 6-tuple consumed by light_processing_data"""
         z, xhat = self.model(x[0])
@@ -277,7 +289,7 @@ class LitAutoEncoder(LightningModule):
         return self.post_processing(out, hidden_out, gt_data, trans, meta, frames)
 
     def configure_optimizers(self) -> Dict:
-        optimizer = Adam(self.parameters(), lr=self.learning_rate)
+        optimizer = Adam(self.parameters(), lr=self.learning_rate, fused=True)
         sched = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=self.args.ae_epochs, eta_min=self.args.opt_lr)
         return {'optimizer': optimizer, 'lr_scheduler': sched}
 

@@ -79,7 +79,15 @@ class _LayerFn(torch.autograd.Function):
         c = _ctx(X)
         st = _lib.stream_ptr(X.device)
         lib = c.lib
-        red = torch.zeros(3 * CO + 1, device=X.device, dtype=torch.float64)
+        # every accumulator of this layer's backward (float64 BN/PReLU sums, weight / bias / graph-operator gradients)
+        # lives in one zeroed buffer: one memset per layer instead of seven
+        sizes = (2 * (3 * CO + 1), W1.numel(), W2.numel(), CO, CO, A.numel(), T.numel())
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)
+        zbuf = torch.zeros(offs[-1], device=X.device, dtype=torch.float32)
+        seg = [zbuf[offs[i]:offs[i] + n] for i, n in enumerate(sizes)]
+        red = seg[0].view(torch.float64)
         dy1 = torch.empty_like(y1)
         dy2 = torch.empty_like(y2)
         c.check(lib.coskad_train_bn_prelu_bwd(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
@@ -88,16 +96,12 @@ class _LayerFn(torch.autograd.Function):
                 'coskad_train_bn_prelu_bwd')
         dG = torch.empty_like(X)
         dXres = torch.empty_like(X)
-        dW1 = torch.zeros_like(W1)
-        dW2 = torch.zeros_like(W2)
-        db1 = torch.zeros(CO, device=X.device, dtype=torch.float32)
-        db2 = torch.zeros(CO, device=X.device, dtype=torch.float32)
+        dW1, dW2, db1, db2 = seg[1].view_as(W1), seg[2].view_as(W2), seg[3], seg[4]
         c.check(lib.coskad_train_mix_bwd(c.h, dy1.data_ptr(), dy2.data_ptr(), G.data_ptr(), X.data_ptr(), W1.data_ptr(),
                                          W2.data_ptr(), B, CI, CO, dG.data_ptr(), dXres.data_ptr(), dW1.data_ptr(),
                                          db1.data_ptr(), dW2.data_ptr(), db2.data_ptr(), st), 'coskad_train_mix_bwd')
         dX = torch.empty_like(X)
-        dA = torch.zeros_like(A)
-        dT = torch.zeros_like(T)
+        dA, dT = seg[5].view_as(A), seg[6].view_as(T)
         c.check(lib.coskad_train_contract_bwd(c.h, dG.data_ptr(), dXres.data_ptr(), X.data_ptr(), G1.data_ptr(),
                                               A.data_ptr(), T.data_ptr(), B * CI, dX.data_ptr(), dA.data_ptr(),
                                               dT.data_ptr(), st), 'coskad_train_contract_bwd')

@@ -25,14 +25,24 @@ class LightningModule(nn.Module):
     def __init__(self) -> None:
         super().__init__()
         self.trainer: Optional['Trainer'] = None
-        self._logged: Dict[str, float] = {}
+        self._log_raw: Dict[str, Any] = {}
+
+    #: True when training_step has no Python-side effects beyond in-place updates of device tensors that exist after the
+    #: first step (so that Trainer(cuda_graph=True) may replay it); per-epoch state is reset in on_train_epoch_start
+    graph_safe = False
 
     # -- Lightning API used by the reference modules
     def save_hyperparameters(self, *a, **k) -> None:
         pass
 
     def log(self, name: str, value, *a, **k) -> None:
-        self._logged[name] = float(value.detach()) if torch.is_tensor(value) else float(value)
+        # kept as a device scalar: converting here would be one device synchronisation per logged value and step
+        self._log_raw[name] = value.detach() if torch.is_tensor(value) else float(value)
+
+    @property
+    def _logged(self) -> Dict[str, float]:
+        """last logged values as floats (read at epoch granularity; synchronises)"""
+        return {k: float(v) for k, v in self._log_raw.items()}
 
     @property
     def device(self) -> torch.device:
@@ -49,6 +59,29 @@ class LightningModule(nn.Module):
     def validation_step(self, batch, batch_idx): ...
     def validation_epoch_end(self, outputs): ...
     def configure_optimizers(self): raise NotImplementedError
+
+
+_GRAPH_WARMUP = 3
+
+
+def _flat_tensors(batch) -> bool:
+    return isinstance(batch, (list, tuple)) and len(batch) > 0 and all(torch.is_tensor(b) for b in batch)
+
+
+def _same_layout(batch, static) -> bool:
+    return _flat_tensors(batch) and len(batch) == len(static) and \
+        all(b.shape == s.shape and b.dtype == s.dtype for b, s in zip(batch, static))
+
+
+def _make_capturable(opt: torch.optim.Optimizer, device: torch.device) -> None:
+    """the optimizer step inside a CUDA graph: step counters on the device, and the learning rate a device scalar the
+    schedulers update in place (a Python float would be frozen into the captured kernels' arguments)"""
+    for g in opt.param_groups:
+        g['capturable'] = True
+        if not torch.is_tensor(g['lr']):
+            g['lr'] = torch.tensor(float(g['lr']), dtype=torch.float32, device=device)
+        if 'initial_lr' in g and torch.is_tensor(g['initial_lr']):
+            g['initial_lr'] = float(g['initial_lr'])
 
 
 def _to_device(batch, device):
@@ -71,10 +104,15 @@ class _DataConnector:
 class Trainer:
     def __init__(self, max_epochs: int = 1, device: Optional[torch.device] = None, ckpt_dir: Optional[str] = None,
                  monitor: Optional[str] = None, mode: str = 'max', save_top_k: int = 2, verbose: bool = True,
-                 check_val_every_n_epoch: int = 1, **_ignored) -> None:
+                 check_val_every_n_epoch: int = 1, cuda_graph: bool = False, **_ignored) -> None:
         self.max_epochs, self.ckpt_dir, self.monitor, self.mode = max_epochs, ckpt_dir, monitor, mode
         self.save_top_k, self.verbose, self.check_val_every_n_epoch = save_top_k, verbose, check_val_every_n_epoch
         self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        # cuda_graph: after _GRAPH_WARMUP eager steps the whole training step (training_step + backward + gradient
+        # all-reduce + optimizer) of every full-size batch is one CUDA graph replay (~100 launches and as many tiny
+        # allocator / autograd operations per step otherwise bound the step on the host); modules opt in with graph_safe
+        self.cuda_graph = cuda_graph
+        self.graph_replays = 0
         self.current_epoch = 0
         self.history: List[Dict[str, float]] = []
         self._best: List = []          # heap of (score, path)
@@ -96,6 +134,13 @@ class Trainer:
         sched = cfg.get('lr_scheduler') if isinstance(cfg, dict) else None
         monitor = (cfg.get('monitor') if isinstance(cfg, dict) else None) or self.monitor
         bucket = cdist.FlatGradBucket(model.parameters())
+        use_graph = self.cuda_graph and bool(getattr(model, 'graph_safe', False))
+        if self.cuda_graph and not use_graph and self.verbose and cdist.rank() == 0:
+            print(f'cuda_graph: {type(model).__name__} is not graph_safe, training eagerly')
+        if use_graph:
+            _make_capturable(opt, self.device)
+        gstate: Optional[Dict[str, Any]] = None
+        n_eager = 0
         for epoch in range(self.max_epochs):
             self.current_epoch = epoch
             t0 = time.time()
@@ -104,13 +149,19 @@ class Trainer:
             outputs, nwin = [], 0
             for batch_idx, batch in enumerate(train_loader):
                 batch = _to_device(batch, self.device)
-                loss = model.training_step(batch, batch_idx)
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                bucket.allreduce_()
-                opt.step()
-                outputs.append(loss.detach())
                 nwin += int(batch[0].shape[0])
+                if use_graph and gstate is None and n_eager >= _GRAPH_WARMUP and _flat_tensors(batch) \
+                        and int(batch[0].shape[0]) == getattr(train_loader, 'batch_size', int(batch[0].shape[0])):
+                    gstate = self._capture(model, opt, bucket, batch, batch_idx)
+                if gstate is not None and _same_layout(batch, gstate['batch']):
+                    for dst, src in zip(gstate['batch'], batch):
+                        dst.copy_(src, non_blocking=True)
+                    gstate['graph'].replay()
+                    self.graph_replays += 1
+                    outputs.append(gstate['loss'].detach().clone())
+                    continue
+                outputs.append(self._eager_step(model, opt, bucket, batch, batch_idx))
+                n_eager += 1
             model.training_epoch_end(outputs)
             model.on_train_epoch_end()
             logs = dict(model._logged)
@@ -137,6 +188,31 @@ class Trainer:
                 print('epoch', epoch, {k: (round(v, 6) if isinstance(v, float) else v) for k, v in logs.items()})
             self._checkpoint(model, logs, monitor)
         return self
+
+    @staticmethod
+    def _eager_step(model, opt, bucket, batch, batch_idx) -> torch.Tensor:
+        # a function of its own: no reference to the autograd graph (the loss) survives the step, so a later capture
+        # builds fresh AccumulateGrad nodes on the capture stream
+        loss = model.training_step(batch, batch_idx)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        bucket.allreduce_()
+        opt.step()
+        return loss.detach()
+
+    def _capture(self, model, opt, bucket, batch, batch_idx) -> Dict[str, Any]:
+        """record one full training step on static copies of ``batch`` (nothing executes during the capture)"""
+        static = [b.clone() for b in batch]
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = model.training_step(static, batch_idx)
+            loss.backward()
+            bucket.allreduce_()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        return {'graph': graph, 'batch': static, 'loss': loss.detach()}     # no reference to the autograd graph is kept
 
     def _checkpoint(self, model, logs, monitor) -> None:
         """ModelCheckpoint(save_top_k=2, monitor='validation_auc' | 'loss') of train_COSKAD.py:70-73"""

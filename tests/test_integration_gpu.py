@@ -110,3 +110,54 @@ def test_autoencoder_task_runs(tmp_path):
     tr = Trainer(max_epochs=2, verbose=False).fit(model, train_loader, test_loader)
     assert all(np.isfinite(e['train_loss_mean']) for e in tr.history)
     assert 0.0 <= tr.history[-1]['validation_auc'] <= 1.0
+
+
+@pytest.mark.parametrize('use_decoder', [False, True])
+def test_cuda_graph_training_matches_eager(tmp_path, use_decoder):
+    """Trainer(cuda_graph=True): the replayed step (training_step + backward + Adam, dynamic center, LR schedule) follows
+    the eager trajectory (float atomics in the gradient kernels: not bit-identical, hence the tolerance)"""
+    from coskad_b200 import tasks
+    from coskad_b200.data import get_dataset_and_loader
+    from coskad_b200.trainer import Trainer
+    res = []
+    for graph in (False, True):
+        torch.manual_seed(3)
+        kw = dict(hyperbolic=False, use_decoder=True, latent_dim=8) if use_decoder else {}
+        args, ae_args, *_ = _args(tmp_path, ae_epochs=3, validation=False, dataset_batch_size=48, **kw)
+        _, loader = get_dataset_and_loader(ae_args, 'train')
+        model = tasks.select_task(args)(args)
+        tr = Trainer(max_epochs=3, verbose=False, cuda_graph=graph).fit(model, loader)
+        sizes = [int(b[0].shape[0]) for b in loader]
+        expected = n_eager = 0
+        captured = False
+        for _ in range(3):                       # every full-size batch after 3 eager warm-up steps is a replay
+            for sz in sizes:
+                captured = captured or (n_eager >= 3 and sz == loader.batch_size)
+                if captured and sz == loader.batch_size:
+                    expected += 1
+                else:
+                    n_eager += 1
+        assert expected >= 6 and sizes[-1] != loader.batch_size, sizes      # the ragged last batch stays eager
+        assert tr.graph_replays == (expected if graph else 0), (tr.graph_replays, expected, sizes)
+        res.append((model, [e['train_loss_mean'] for e in tr.history], [e['loss'] for e in tr.history]))
+    (m0, mean0, last0), (m1, mean1, last1) = res
+    np.testing.assert_allclose(mean1, mean0, rtol=2e-3)
+    np.testing.assert_allclose(last1, last0, rtol=2e-3)
+    assert torch.allclose(m1.model.c, m0.model.c, rtol=1e-3, atol=1e-5)
+    if not use_decoder:
+        assert len(m1.centers) == len(m0.centers) == 4
+        for a, b in zip(m1.centers, m0.centers):
+            assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+    # parameters: compared through the function they define (a conv bias in front of train-mode BatchNorm has an exactly
+    # zero gradient, so Adam normalises rounding noise and bias / running_mean drift together without changing the output)
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m0.state_dict().items()):
+        if not a.dtype.is_floating_point:
+            assert torch.equal(a, b), k                             # num_batches_tracked
+    x = next(iter(loader))[0].cuda()
+    with torch.no_grad():
+        from coskad_b200 import _lib
+        (z1, s1), (z0, s0) = (m.model.eval().encode_score(x, _lib.SCORE_EUCLID) for m in (m1, m0))
+    # eval mode sees (bias - running_mean), whose noise-driven drift the running average follows with a lag: the train-mode
+    # loss trajectories above are the tight check, this one catches gross divergence only
+    assert torch.allclose(z1, z0, rtol=5e-2, atol=3e-2), float((z1 - z0).abs().max())
+    assert torch.allclose(s1, s0, rtol=5e-2, atol=3e-2), float((s1 - s0).abs().max())

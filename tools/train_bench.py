@@ -17,7 +17,8 @@ if world > 1:
 m = synth.make_model('stse', 16, seed=0, device=dev).train()
 cdist.broadcast_module_(m)
 bucket = cdist.FlatGradBucket(m.parameters())
-opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+GRAPH = bool(os.environ.get('COSKAD_TB_GRAPH'))          # whole step (fwd + bwd + all-reduce + Adam) as one CUDA graph
+opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=GRAPH, fused=not os.environ.get('COSKAD_TB_FOREACH'))   # the tasks use fused=True
 g = torch.Generator(device=dev).manual_seed(999 + rank)
 x = torch.empty(B, 2, 12, 17, device=dev)
 synth.synth_windows_(x, g)
@@ -37,6 +38,20 @@ def step():
     opt.step()
     return loss
 
+if GRAPH:
+    eager_step = step
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3): eager_step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_loss = eager_step()
+    def step():
+        graph.replay()
+        return static_loss
 for _ in range(5): step()
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
@@ -53,7 +68,8 @@ if world > 1:
         dist.destroy_process_group(); sys.exit(0)
     print(f'{world} GPUs x B={B}: {ms:.3f} ms/step (max over ranks; wall on rank 0 {(t1-t0)/N*1e3:.3f}) -> {world*B/ms*1e3:.0f} windows/s' + (' [no all-reduce]' if os.environ.get('COSKAD_TB_NOAR') else ''))
     dist.destroy_process_group(); sys.exit(0)
-print(f'B={B}: {ms:.3f} ms/step (device), {(t1-t0)/N*1e3:.3f} ms/step (wall) -> {B/ms*1e3:.0f} windows/s, loss {float(l):.4f}')
+print(('[CUDA graph] ' if GRAPH else '') + f'B={B}: {ms:.3f} ms/step (device), {(t1-t0)/N*1e3:.3f} ms/step (wall) -> {B/ms*1e3:.0f} windows/s, loss {float(l):.4f}')
+if GRAPH: sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3): step()

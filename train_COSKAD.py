@@ -42,6 +42,8 @@ def main(argv=None):
     parser.add_argument('-c', '--config', type=str, required=True)
     parser.add_argument('--synthetic', action='store_true', help='use the synthetic stand-in dataset')
     parser.add_argument('--epochs', type=int, default=None)
+    parser.add_argument('--cuda_graph', action='store_true',
+                        help='replay the training step as one CUDA graph (also: cuda_graph: true in the YAML)')
     cli = parser.parse_args(argv)
     args = ccfg.load_config(cli.config)
     if cli.synthetic:
@@ -59,7 +61,8 @@ def main(argv=None):
     loader, val = get_loaders(args, ae_args)
     monitor = 'validation_auc' if getattr(args, 'validation', False) else 'loss'
     trainer = Trainer(max_epochs=args.ae_epochs, device=torch.device('cuda', local), ckpt_dir=args.ckpt_dir,
-                      monitor=monitor, mode='max' if monitor == 'validation_auc' else 'min', save_top_k=2)
+                      monitor=monitor, mode='max' if monitor == 'validation_auc' else 'min', save_top_k=2,
+                      cuda_graph=cli.cuda_graph or bool(getattr(args, 'cuda_graph', False)))
     trainer.fit(model, loader, val)
     if world > 1:
         torch.distributed.destroy_process_group()
