@@ -728,6 +728,7 @@ extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_sma
                                    int w_is_fd, const float* bias, int64_t B, int F, int D, float* out, void* stream_) {
   TRAIN_PRE();
   if (D < 1 || D > 16) return fail(ctx, COSKAD_ERR_ARG, "linear: D must be in [1,16], got %d", D);
+  if (F % 4) return fail(ctx, COSKAD_ERR_ARG, "linear: F must be a multiple of 4 (16-byte loads), got %d", F);
   if (B <= 0) return COSKAD_OK;
   const int64_t sd = w_is_fd ? 1 : F, sf = w_is_fd ? D : 1;
   if (mode == 0) {
@@ -738,8 +739,8 @@ extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_sma
   }
   else if (mode == 1) lin_expand_f_kernel<16><<<dim3((F + kTrainThreads - 1) / kTrainThreads, static_cast<unsigned>((B + kExpRows - 1) / kExpRows)), kTrainThreads, 0, st>>>(a_small, W, sd, sf, bias, B, F, D, out);
   else if (mode == 2) {
-    int nb = static_cast<int>(B < 32 ? B : 32);
-    lin_wgrad_kernel<16><<<dim3((F + kTrainThreads - 1) / kTrainThreads, nb), kTrainThreads, 0, st>>>(a_small, A_wide, sd, sf, B, F, D, out);
+    const int nb = B >= 512 ? 4 : 1;                  // row slices: >= 16 rows per warp
+    lin_wgrad_kernel<16><<<dim3((F + kWgF - 1) / kWgF, nb), kTrainThreads, 0, st>>>(a_small, A_wide, sd, sf, B, F, D, out);
   } else return fail(ctx, COSKAD_ERR_ARG, "linear: unknown mode %d", mode);
   CK_LAUNCH();
   return COSKAD_OK;
@@ -748,7 +749,8 @@ extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_sma
 extern "C" int coskad_train_col_sum(coskad_ctx* ctx, const float* a, int64_t B, int N, float* out, void* stream_) {
   TRAIN_PRE();
   if (B <= 0 || N <= 0) return COSKAD_OK;
-  col_sum_kernel<<<(N + 31) / 32, kTrainThreads, 0, st>>>(a, B, N, out);
+  const int64_t slices = (B + 63) / 64;               // >= 8 rows per thread
+  col_sum_kernel<<<dim3((N + 31) / 32, static_cast<unsigned>(slices < 32 ? slices : 32)), kTrainThreads, 0, st>>>(a, B, N, out);
   CK_LAUNCH();
   return COSKAD_OK;
 }

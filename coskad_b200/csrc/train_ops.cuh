@@ -702,17 +702,18 @@ __global__ void __launch_bounds__(kGThreads) chan_gemm_kernel(const float* __res
 // out[b,d] += sum_{f in slice} A[b,f] W(d,f) (+ bias[d] from slice 0)   (wide-in: head forward, rev_btlnk input gradient)
 // grid (ceil(B / 32), kLinSlices): a block owns 32 rows (4 per warp) and one slice of the features; it stages W chunks of
 // [DMAX][kLinFC] in shared memory once for all its rows (one row per block re-read all 835 KB of W per row from L2) and
-// adds its partial sums to `out` (zeroed by the caller) with atomics.
+// adds its partial sums to `out` (zeroed by the caller) with atomics.  A lane takes 4 consecutive features: 16-byte loads
+// of the activations (4 in flight per lane) and of the staged weights; F % 4 == 0 (host-checked).
 constexpr int kLinRows = 4;            // rows per warp
 constexpr int kLinFC = 512;            // features per staged chunk
-constexpr int kLinSlices = 4;
+constexpr int kLinSlices = 8;
 template <int DMAX>
 __global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __restrict__ W, int64_t sd, int64_t sf,
                                     const float* __restrict__ bias, int64_t B, int F, int D, float* __restrict__ out) {
-  __shared__ float ws[DMAX][kLinFC + 1];
+  __shared__ __align__(16) float ws[DMAX][kLinFC + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int64_t b0 = (static_cast<int64_t>(blockIdx.x) * nwarp + warp) * kLinRows;
-  const int fslice = (F + kLinSlices - 1) / kLinSlices;
+  const int fslice = ((F + kLinSlices - 1) / kLinSlices + 3) / 4 * 4;
   const int f_lo = blockIdx.y * fslice, f_hi = min(F, f_lo + fslice);
   float acc[kLinRows][DMAX];
 #pragma unroll
@@ -722,20 +723,34 @@ __global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __
   for (int f0 = f_lo; f0 < f_hi; f0 += kLinFC) {
     const int nf = min(kLinFC, f_hi - f0);
     __syncthreads();
-    for (int i = threadIdx.x; i < DMAX * kLinFC; i += blockDim.x) {
-      const int d = i / kLinFC, f = i - d * kLinFC;
-      ws[d][f] = (d < D && f < nf) ? W[d * sd + (f0 + f) * sf] : 0.f;
+    if (sf == 1 && sd % 4 == 0) {
+      // rows of W are contiguous: 16-byte asynchronous copies, all in flight at once (as a load -> store loop the staging
+      // exposed the L2 latency 8 times per chunk and was most of the kernel's time); nf % 4 == 0
+      for (int i = threadIdx.x; i < DMAX * (kLinFC / 4); i += blockDim.x) {
+        const int d = i / (kLinFC / 4), f = 4 * (i - d * (kLinFC / 4));
+        if (d < D && f < nf) cp_async16(&ws[d][f], W + d * sd + f0 + f);
+        else *reinterpret_cast<float4*>(&ws[d][f]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+    } else {
+      for (int i = threadIdx.x; i < DMAX * kLinFC; i += blockDim.x) {
+        const int d = i / kLinFC, f = i - d * kLinFC;
+        ws[d][f] = (d < D && f < nf) ? W[d * sd + (f0 + f) * sf] : 0.f;
+      }
     }
     __syncthreads();
-    for (int f = lane; f < nf; f += 32) {
-      float a[kLinRows];
+    for (int f = 4 * lane; f < nf; f += 128) {
+      float4 a[kLinRows];
 #pragma unroll
-      for (int r = 0; r < kLinRows; ++r) a[r] = (b0 + r < B) ? A[(b0 + r) * F + f0 + f] : 0.f;
+      for (int r = 0; r < kLinRows; ++r)
+        a[r] = (b0 + r < B) ? __ldg(reinterpret_cast<const float4*>(A + (b0 + r) * F + f0 + f)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int d = 0; d < DMAX; ++d) {
-        const float w = ws[d][f];
+        const float4 w = *reinterpret_cast<const float4*>(&ws[d][f]);
 #pragma unroll
-        for (int r = 0; r < kLinRows; ++r) acc[r][d] = fmaf(a[r], w, acc[r][d]);
+        for (int r = 0; r < kLinRows; ++r)
+          acc[r][d] = fmaf(a[r].w, w.w, fmaf(a[r].z, w.z, fmaf(a[r].y, w.y, fmaf(a[r].x, w.x, acc[r][d]))));
       }
     }
   }
@@ -749,11 +764,12 @@ __global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __
 }
 // out[b,f] = sum_d a[b,d] W(d,f) + bias[f]           (wide-out: rev_btlnk forward, head input gradient)
 // grid (ceil(F/256), ceil(B/kExpRows)): a thread keeps the D weights of its feature f in registers for kExpRows rows b
-constexpr int kExpRows = 32;
+constexpr int kExpRows = 128;
 template <int DMAX>
 __global__ void lin_expand_f_kernel(const float* __restrict__ a, const float* __restrict__ W, int64_t sd, int64_t sf,
                                     const float* __restrict__ bias, int64_t B, int F, int D, float* __restrict__ out) {
-  __shared__ float as[kExpRows][DMAX];
+  static_assert(DMAX % 4 == 0, "rows of the staged latents are read as float4");
+  __shared__ __align__(16) float as[kExpRows][DMAX];
   const int64_t b0 = static_cast<int64_t>(blockIdx.y) * kExpRows;
   for (int i = threadIdx.x; i < kExpRows * DMAX; i += blockDim.x) {
     const int r = i / DMAX, d = i % DMAX;
@@ -769,38 +785,104 @@ __global__ void lin_expand_f_kernel(const float* __restrict__ a, const float* __
   for (int r = 0; r < kExpRows && b0 + r < B; ++r) {
     float s = bf;
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) s = fmaf(as[r][d], w[d], s);
+    for (int d4 = 0; d4 < DMAX / 4; ++d4) {        // broadcast LDS.128: one shared-memory load per 4 FMAs
+      const float4 v = *reinterpret_cast<const float4*>(&as[r][4 * d4]);
+      s = fmaf(v.w, w[4 * d4 + 3], fmaf(v.z, w[4 * d4 + 2], fmaf(v.y, w[4 * d4 + 1], fmaf(v.x, w[4 * d4], s))));
+    }
     out[(b0 + r) * F + f] = s;
   }
 }
-// dW(d,f) += sum_b a[b,d] A[b,f];  grid (ceil(F/256), NB)
+// dW(d,f) += sum_b a[b,d] A[b,f].  grid (ceil(F/128), NB): the 8 warps of a block share 128 features (a lane owns 4
+// consecutive ones, 16-byte loads) and split the block's rows; their partial sums meet in shared memory, so the block
+// issues one atomicAdd per weight (one per thread and row slice was 6.7 M atomics for the 16 x 13056 bottleneck).
+constexpr int kWgF = 128;
 template <int DMAX>
-__global__ void lin_wgrad_kernel(const float* __restrict__ a, const float* __restrict__ A, int64_t sd, int64_t sf,
-                                 int64_t B, int F, int D, float* dW) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  float acc[DMAX];
+__global__ void __launch_bounds__(kTrainThreads) lin_wgrad_kernel(const float* __restrict__ a, const float* __restrict__ A,
+                                                                  int64_t sd, int64_t sf, int64_t B, int F, int D, float* dW) {
+  static_assert(DMAX % 4 == 0, "latent rows are read as float4");
+  constexpr int kHalf = kTrainThreads / 64;              // the warps meet in two rounds: 33 KB of static shared memory
+  __shared__ float red[kHalf][DMAX][kWgF + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = kTrainThreads / 32;
+  const int f = blockIdx.x * kWgF + 4 * lane;
+  float acc[DMAX][4];
 #pragma unroll
-  for (int d = 0; d < DMAX; ++d) acc[d] = 0.f;
+  for (int d = 0; d < DMAX; ++d) acc[d][0] = acc[d][1] = acc[d][2] = acc[d][3] = 0.f;
   if (f < F) {
-    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
-      const float v = A[b * F + f];
+    const bool a_vec = (D == DMAX);                      // rows of `a` are 16-byte aligned only for the full width
+    const int64_t bstep = static_cast<int64_t>(gridDim.y) * nwarp;
+    for (int64_t bb = static_cast<int64_t>(blockIdx.y) * nwarp + warp; bb < B; bb += 4 * bstep) {
+     // the wide rows of 4 steps are requested together (the latent rows that follow are L1 hits)
+     float4 vq[4];
 #pragma unroll
-      for (int d = 0; d < DMAX; ++d) if (d < D) acc[d] = fmaf(a[b * D + d], v, acc[d]);
+     for (int u = 0; u < 4; ++u)
+       vq[u] = (bb + u * bstep < B) ? __ldg(reinterpret_cast<const float4*>(A + (bb + u * bstep) * F + f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+     for (int u = 0; u < 4; ++u) {
+      const int64_t b = bb + u * bstep;
+      if (b >= B) break;
+      const float4 v = vq[u];
+      float ar[DMAX];
+      if (a_vec) {
+#pragma unroll
+        for (int d4 = 0; d4 < DMAX / 4; ++d4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(a + b * D) + d4);
+          ar[4 * d4] = t.x; ar[4 * d4 + 1] = t.y; ar[4 * d4 + 2] = t.z; ar[4 * d4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d) ar[d] = (d < D) ? __ldg(a + b * D + d) : 0.f;
+      }
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) {
+        acc[d][0] = fmaf(ar[d], v.x, acc[d][0]); acc[d][1] = fmaf(ar[d], v.y, acc[d][1]);
+        acc[d][2] = fmaf(ar[d], v.z, acc[d][2]); acc[d][3] = fmaf(ar[d], v.w, acc[d][3]);
+      }
+     }
     }
+  }
+  if (warp >= kHalf) {
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) if (d < D) atomicAdd(dW + d * sd + f * sf, acc[d]);
+    for (int d = 0; d < DMAX; ++d)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red[warp - kHalf][d][4 * lane + q] = acc[d][q];
+  }
+  __syncthreads();
+  if (warp < kHalf) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[d][q] += red[warp][d][4 * lane + q];
+  }
+  __syncthreads();
+  if (warp < kHalf) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red[warp][d][4 * lane + q] = acc[d][q];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D * kWgF; i += kTrainThreads) {
+    const int d = i / kWgF, fl = i - d * kWgF;
+    const int fo = blockIdx.x * kWgF + fl;
+    if (fo >= F) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kHalf; ++w) s += red[w][d][fl];
+    atomicAdd(dW + d * sd + fo * sf, s);
   }
 }
-// column sums: out[j] += sum_b a[b, j]   (bias gradients), one block per 32 columns
+// column sums: out[j] += sum_b a[b, j]   (bias gradients); grid (ceil(N/32), row slices): a block owns 32 columns and
+// every gridDim.y-th group of 8 rows
 __global__ void col_sum_kernel(const float* __restrict__ a, int64_t B, int N, float* out) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int row0 = threadIdx.x >> 5, nrow = blockDim.x >> 5;
+  const int nrow = blockDim.x >> 5;
+  const int row0 = blockIdx.y * nrow + (threadIdx.x >> 5);
   float s = 0.f;
-  if (j < N) for (int64_t b = row0; b < B; b += nrow) s += a[b * N + j];
+  if (j < N) for (int64_t b = row0; b < B; b += static_cast<int64_t>(nrow) * gridDim.y) s += a[b * N + j];
   __shared__ float sh[8][33];
-  sh[row0][threadIdx.x & 31] = s;
+  sh[threadIdx.x >> 5][threadIdx.x & 31] = s;
   __syncthreads();
-  if (row0 == 0 && j < N) {
+  if ((threadIdx.x >> 5) == 0 && j < N) {
     float t = 0.f;
     for (int r = 0; r < nrow; ++r) t += sh[r][threadIdx.x & 31];
     atomicAdd(out + j, t);
