@@ -134,9 +134,12 @@ class Trainer:
         sched = cfg.get('lr_scheduler') if isinstance(cfg, dict) else None
         monitor = (cfg.get('monitor') if isinstance(cfg, dict) else None) or self.monitor
         bucket = cdist.FlatGradBucket(model.parameters())
-        use_graph = self.cuda_graph and bool(getattr(model, 'graph_safe', False))
+        # one process only: with the NCCL gradient all-reduce inside the capture the 2-GPU replay hung on the test box
+        # (torch 2.11 / NCCL 2.28), so data-parallel runs stay eager until the step is split around the collective
+        use_graph = self.cuda_graph and bool(getattr(model, 'graph_safe', False)) and cdist.world() == 1
         if self.cuda_graph and not use_graph and self.verbose and cdist.rank() == 0:
-            print(f'cuda_graph: {type(model).__name__} is not graph_safe, training eagerly')
+            why = 'data-parallel run' if cdist.world() > 1 else f'{type(model).__name__} is not graph_safe'
+            print(f'cuda_graph: {why}, training eagerly')
         if use_graph:
             _make_capturable(opt, self.device)
         gstate: Optional[Dict[str, Any]] = None
