@@ -318,8 +318,8 @@ def run_ours(args):
     ach_tf = FLOP_PER_WINDOW * W / (k_ms * 1e-3) / 1e12
     ach_gb = BYTES_PER_WINDOW * W / (k_ms * 1e-3) / 1e9
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    # ncu dram__bytes_read+write of one launch (profiles/r01_v8_fused_eval_tc.md: 215.48 + 7.08 MB for 131 072 windows)
-    traffic_per_window = 222.57e6 / 131072
+    # ncu dram__bytes_read+write of one launch (profiles/r01_v9_fused_eval_tc.md: 1726.73 + 10.98 MB for 1 048 576 windows)
+    traffic_per_window = 1737.71e6 / 1048576
     roofline = {'bound': 'fp32_fma', 'achieved': ach_tf, 'peak': fp32_peak_measured, 'unit': 'TFLOP/s',
                 'frac': ach_tf / fp32_peak_measured if fp32_peak_measured else None,
                 'traffic': traffic_per_window * W, 'traffic_unit': 'bytes per launch (ncu dram read+write, scaled from the profiled launch)',
@@ -344,7 +344,7 @@ def run_ours(args):
                        'note': 'the tensor view of the same launch: algorithmic FLOPs over the dense BF16 peak. Only the 1x1 channel '
                                'mixing (65 % of the MACs) is GEMM-shaped; it needs 3 TF32 passes per product to keep the 1e-4 score '
                                'tolerance (TF32 = half the BF16 rate) and occupies the tensor pipe 11 % of the time '
-                               '(profiles/r01_v8_fused_eval_tc.md); the binding resources are the FP32 pipe and the per-SM L2 fetch '
+                               '(profiles/r01_v9_fused_eval_tc.md); the binding resources are the FP32 pipe and the per-SM L2 fetch '
                                'rate of the head stage, hence roofline.bound = fp32_fma'}
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
