@@ -228,7 +228,8 @@ int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const float* dy2, co
                          float* dW1, float* db1, float* dW2, float* db2, void* stream);
 /* linear layers over the F = C*204 flattened features (btlnk / fc_mean / fc_var / rev_btlnk, models/sts/ae.py:155,206):
  * mode 0: out[B,D] = A_wide[B,F] W^T + bias; mode 1: out[B,F] = a_small[B,D] W + bias[F]; mode 2: out(=dW) += a_small^T A_wide.
- * w_is_fd = 0: W is [D,F] (btlnk); 1: W is [F,D] (rev_btlnk). */
+ * w_is_fd = 0: W is [D,F] (btlnk); 1: W is [F,D] (rev_btlnk).  D <= 16, F % 4 == 0 (rows are read with 16-byte loads:
+ * every COSKAD layout has F = C*T*V with T*V a multiple of 4); mode 2 accumulates into a zeroed / running dW. */
 int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_small, const float* A_wide, const float* W, int w_is_fd,
                         const float* bias, int64_t B, int F, int D, float* out, void* stream);
 /* out[N] += column sums of a[B,N] (bias gradients) */
