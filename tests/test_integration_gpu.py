@@ -141,8 +141,8 @@ def test_cuda_graph_training_matches_eager(tmp_path, use_decoder):
         assert tr.graph_replays == (expected if graph else 0), (tr.graph_replays, expected, sizes)
         res.append((model, [e['train_loss_mean'] for e in tr.history], [e['loss'] for e in tr.history]))
     (m0, mean0, last0), (m1, mean1, last1) = res
-    np.testing.assert_allclose(mean1, mean0, rtol=2e-3)
-    np.testing.assert_allclose(last1, last0, rtol=2e-3)
+    np.testing.assert_allclose(mean1, mean0, rtol=1e-2)
+    np.testing.assert_allclose(last1, last0, rtol=1e-2)
     assert torch.allclose(m1.model.c, m0.model.c, rtol=1e-3, atol=1e-5)
     if not use_decoder:
         assert len(m1.centers) == len(m0.centers) == 4
