@@ -143,11 +143,11 @@ def test_cuda_graph_training_matches_eager(tmp_path, use_decoder):
     (m0, mean0, last0), (m1, mean1, last1) = res
     np.testing.assert_allclose(mean1, mean0, rtol=1e-2)
     np.testing.assert_allclose(last1, last0, rtol=1e-2)
-    assert torch.allclose(m1.model.c, m0.model.c, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(m1.model.c, m0.model.c, rtol=1e-2, atol=1e-4)
     if not use_decoder:
         assert len(m1.centers) == len(m0.centers) == 4
         for a, b in zip(m1.centers, m0.centers):
-            assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+            assert torch.allclose(a, b, rtol=1e-2, atol=1e-4)
     # parameters: compared through the function they define (a conv bias in front of train-mode BatchNorm has an exactly
     # zero gradient, so Adam normalises rounding noise and bias / running_mean drift together without changing the output)
     for (k, a), (_, b) in zip(m1.state_dict().items(), m0.state_dict().items()):
