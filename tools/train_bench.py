@@ -1,4 +1,10 @@
-"""training-step timing on one GPU: hyperbolic dynamic-center step (fwd + bwd + Adam), batch 2048 (BASELINE configs[4])"""
+"""training-step timing: hyperbolic dynamic-center step (fwd + bwd + Adam), batch 2048 per GPU (BASELINE configs[4])
+
+    python tools/train_bench.py [B]                              one GPU, eager step + torch-profiler kernel table
+    COSKAD_TB_GRAPH=1 python tools/train_bench.py                the step as one CUDA-graph replay (what Trainer(cuda_graph=True) does)
+    torchrun --nproc-per-node N tools/train_bench.py             data parallel: flat NCCL gradient all-reduce per step, max over ranks
+    COSKAD_TB_NOAR=1 / COSKAD_TB_FOREACH=1                       A/B switches: skip the all-reduce / for-each instead of fused Adam
+"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
