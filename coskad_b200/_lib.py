@@ -42,6 +42,9 @@ SIGNATURES = {
     'coskad_autoencode_score_fwd': (C.c_int, [c_ctx_p, c_float_p, c_float_p, C.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, C.c_void_p]),
     'coskad_geom_map': (C.c_int, [c_ctx_p, C.c_int, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_dist': (C.c_int, [c_ctx_p, C.c_int, c_float_p, c_float_p, C.c_int, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
+    'coskad_geom_map_bwd': (C.c_int, [c_ctx_p, C.c_int, c_float_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
+    'coskad_dist_bwd': (C.c_int, [c_ctx_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int64, C.c_int, c_float_p,
+                                  c_float_p, C.c_void_p]),
     'coskad_dist0': (C.c_int, [c_ctx_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_ps_sample': (C.c_int, [c_ctx_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_poincare_score_bwd': (C.c_int, [c_ctx_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_int, C.c_int, c_float_p, C.c_void_p]),

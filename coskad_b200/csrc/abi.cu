@@ -428,6 +428,35 @@ extern "C" int coskad_dist(coskad_ctx* ctx, int flavour, const float* a, const f
   return COSKAD_OK;
 }
 
+extern "C" int coskad_geom_map_bwd(coskad_ctx* ctx, int op, const float* in, const float* gout, int64_t B, int D, float* gin,
+                                   void* stream_) {
+  CHECK_BD();
+  if (op != COSKAD_MAP_EXPMAP0 && op != COSKAD_MAP_PROJECT && op != COSKAD_MAP_EXPMAP0_PROJECT && op != COSKAD_MAP_L2NORMALIZE)
+    return fail(ctx, COSKAD_ERR_ARG, "geom_map_bwd: op %d has no backward (geoopt flavour and L2 normalise only)", op);
+  if (D > 128) return fail(ctx, COSKAD_ERR_ARG, "geom_map_bwd supports D <= 128");
+  if (!in || !gout || !gin) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (D <= 32) geom_map_bwd_kernel<1><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(op, in, gout, B, D, gin);
+  else geom_map_bwd_kernel<4><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(op, in, gout, B, D, gin);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_dist_bwd(coskad_ctx* ctx, int flavour, const float* a, const float* b, int b_bcast, const float* gs,
+                               int64_t B, int D, float* ga, float* gb, void* stream_) {
+  CHECK_BD();
+  if (flavour != COSKAD_SCORE_POINCARE && flavour != COSKAD_SCORE_POINCARE_NOPROJ && flavour != COSKAD_SCORE_EUCLID &&
+      flavour != COSKAD_SCORE_COSINE)
+    return fail(ctx, COSKAD_ERR_ARG, "dist_bwd: flavour %d has no backward", flavour);
+  if (D > 128) return fail(ctx, COSKAD_ERR_ARG, "dist_bwd supports D <= 128");
+  if (!a || !b || !gs || (!ga && !gb)) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (D <= 32) dist_bwd_kernel<1><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(flavour, a, b, b_bcast, gs, B, D, ga, gb);
+  else dist_bwd_kernel<4><<<row_grid(ctx, B), kRowWarps * 32, 0, st>>>(flavour, a, b, b_bcast, gs, B, D, ga, gb);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
 extern "C" int coskad_dist0(coskad_ctx* ctx, const float* x, int64_t B, int D, float* out, void* stream_) {
   CHECK_BD();
   if (!x || !out) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");

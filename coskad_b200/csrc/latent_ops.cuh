@@ -79,6 +79,129 @@ __global__ void dist0_kernel(const float* __restrict__ x, int64_t B, int D, floa
   }
 }
 
+// ---- backward of the element-wise gmath ops ----------------------------------------------------------------------
+// The reference's own training_step differentiates through gmath.expmap0 / gmath.project / gmath.dist one call at a
+// time (models/hyperbolic_encoder.py:147,157); these kernels are the analytic vector-Jacobian products of exactly the
+// forward expressions above (clamps pass zero gradient outside their range, like autograd).
+template <int E>
+__device__ __forceinline__ void expmap0_vjp(const float (&u)[E], float (&g)[E]) {      // g: in = dL/dy, out = dL/du
+  const float nraw = sqrtf(vec_sumsq(u));
+  const float n = fmaxf(nraw, 1e-15f);
+  const bool live = nraw > 1e-15f;
+  const float t = clamped_tanh(n);
+  const float f = t / n;
+  const float tp = (n < 15.f) ? 1.f - t * t : 0.f;
+  const float fp = live ? (tp * n - t) / (n * n) : 0.f;
+  const float dot = vec_dot(g, u);
+#pragma unroll
+  for (int e = 0; e < E; ++e) g[e] = f * g[e] + (live ? fp * (u[e] / n) * dot : 0.f);
+}
+// y = x / n * R with n = max(|x|, floor); radial part of the gradient removed
+template <int E>
+__device__ __forceinline__ void rescale_vjp(const float (&x)[E], float (&g)[E], float R, float floor_) {
+  const float nraw = sqrtf(vec_sumsq(x));
+  const float n = fmaxf(nraw, floor_);
+  const float dot = (nraw > floor_) ? vec_dot(g, x) : 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) g[e] = R * (g[e] / n - x[e] * dot / (n * n * n));
+}
+template <int E>
+__device__ __forceinline__ void project_vjp(const float (&x)[E], float (&g)[E]) {
+  const float n = fmaxf(sqrtf(vec_sumsq(x)), 1e-15f);
+  const float maxnorm = 1.f - 4e-3f;
+  if (n > maxnorm) rescale_vjp(x, g, maxnorm, 1e-15f);
+}
+
+template <int E>
+__global__ void geom_map_bwd_kernel(int op, const float* __restrict__ in, const float* __restrict__ gout, int64_t B, int D,
+                                    float* __restrict__ gin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    float x[E], g[E];
+    load_row<E>(in + r * D, D, lane, x);
+    load_row<E>(gout + r * D, D, lane, g);
+    switch (op) {
+      case COSKAD_MAP_EXPMAP0: expmap0_vjp(x, g); break;
+      case COSKAD_MAP_PROJECT: project_vjp(x, g); break;
+      case COSKAD_MAP_EXPMAP0_PROJECT: {
+        float e_[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) e_[e] = x[e];
+        expmap0(e_, geo_geoopt(), false);
+        project_vjp(e_, g);
+        expmap0_vjp(x, g);
+      } break;
+      case COSKAD_MAP_L2NORMALIZE: rescale_vjp(x, g, 1.f, 0.f); break;
+      default: break;
+    }
+    store_row<E>(gin + r * D, D, lane, g);
+  }
+}
+
+// ga[B,D] (nullable) = gs * d f(a,b)/da, gb[B,D] (nullable) = gs * d f(a,b)/db per row (a broadcast b gets per-row rows too)
+template <int E>
+__global__ void dist_bwd_kernel(int flavour, const float* __restrict__ a, const float* __restrict__ b, int b_bcast,
+                                const float* __restrict__ gs, int64_t B, int D, float* __restrict__ ga,
+                                float* __restrict__ gb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    float x[E], y[E], dx[E], dy[E];
+    load_row<E>(a + r * D, D, lane, x);
+    load_row<E>(b_bcast ? b : b + r * D, D, lane, y);
+    const float g = gs[r];
+    if (flavour == COSKAD_SCORE_POINCARE || flavour == COSKAD_SCORE_POINCARE_NOPROJ) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) x[e] = -x[e];                   // mobius_add(-a, b)
+      const float x2 = vec_sumsq(x), y2 = vec_sumsq(y), xy = vec_dot(x, y);
+      const float ca = 1.f + 2.f * xy + y2, cb = 1.f - x2;
+      const float den_raw = 1.f + 2.f * xy + x2 * y2;
+      const float den = fmaxf(den_raw, 1e-15f);
+      float rr[E], dnum[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) rr[e] = (ca * x[e] + cb * y[e]) / den;
+      const float rn = sqrtf(vec_sumsq(rr));
+      const float hi = 1.f - 1e-7f;
+      const float d_rn = (rn < hi && rn > -hi) ? g * 2.f / (1.f - rn * rn) : 0.f;
+      float s_rr = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float d_r = (rn > 0.f) ? d_rn * rr[e] / rn : 0.f;
+        dnum[e] = d_r / den;
+        s_rr = fmaf(d_r, rr[e], s_rr);
+      }
+      const float d_den = (den_raw > 1e-15f) ? -warp_sum(s_rr) / den : 0.f;
+      const float d_ca = vec_dot(dnum, x), d_cb = vec_dot(dnum, y);
+      const float d_xy = 2.f * d_ca + 2.f * d_den;
+      const float d_y2 = d_ca + x2 * d_den;
+      const float d_x2 = -d_cb + y2 * d_den;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        dx[e] = -(ca * dnum[e] + d_xy * y[e] + 2.f * d_x2 * x[e]);   // d/da = -d/dx
+        dy[e] = cb * dnum[e] + d_xy * x[e] + 2.f * d_y2 * y[e];
+      }
+    } else if (flavour == COSKAD_SCORE_EUCLID) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) { const float d = 2.f * (y[e] - x[e]) / static_cast<float>(D) * g; dx[e] = -d; dy[e] = d; }
+    } else {   // COSINE: 1 - <b/|b|, a/|a|>, norms clamped at 1e-8
+      const float nar = sqrtf(vec_sumsq(x)), nbr = sqrtf(vec_sumsq(y));
+      const float na = fmaxf(nar, 1e-8f), nb = fmaxf(nbr, 1e-8f);
+      float ah[E], bh[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) { ah[e] = x[e] / na; bh[e] = y[e] / nb; }
+      const float c = vec_dot(ah, bh);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        dx[e] = -g * (bh[e] - (nar > 1e-8f ? c * ah[e] : 0.f)) / na;
+        dy[e] = -g * (ah[e] - (nbr > 1e-8f ? c * bh[e] : 0.f)) / nb;
+      }
+    }
+    if (ga) store_row<E>(ga + r * D, D, lane, dx);
+    if (gb) store_row<E>(gb + r * D, D, lane, dy);
+  }
+}
+
 // PowerSpherical reparameterised sample from explicit noise (models/sts/vae.py:110,129; power_spherical's
 // _TTransform + _HouseholderRotationTransform): y = [t, sqrt(clamp(1-t^2,1e-7)) v]; u = (e1 - mu)/(|e1 - mu| + 1e-5);
 // z = y - 2 <y,u> u.   mu [B,d], t [B], v [B,d-1] (unit vectors), d <= 32, one warp per row.

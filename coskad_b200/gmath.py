@@ -4,7 +4,9 @@ Mirrors the functions COSKAD calls on ``geoopt.manifolds.stereographic.math`` wi
 (models/hyperbolic_encoder.py:110,122,147,157,179,181,266; utils/eval_utils.py:67;
 eval_COSKAD.py:195): ``expmap0, project, dist, dist0, weighted_midpoint``; plus the
 ``utils/hyper_math.py`` flavour (``hm_*``), the sharded center update and the fused, differentiable
-training score ``poincare_score``.  Tensors must live on a CUDA device; there is no CPU path.
+training score ``poincare_score``.  The element-wise ops are differentiable (analytic
+vector-Jacobian kernels), so the reference's own ``training_step`` runs on them unchanged.  Tensors must live on a CUDA
+device; there is no CPU path.
 """
 from __future__ import annotations
 
@@ -28,25 +30,61 @@ def _prep(x: torch.Tensor, what: str, dim: int = -1):
         raise _lib.CoskadError(f'{what} is not on a CUDA device: coskad_b200.gmath has no CPU fallback')
     if dim not in (-1, x.dim() - 1):
         raise NotImplementedError('only dim=-1 is implemented')
-    if x.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError('the element-wise gmath ops are forward-only; the differentiable training path is '
-                                  'coskad_b200.gmath.poincare_score (fused expmap0 -> project -> dist)')
     x2 = x.detach().to(torch.float32).contiguous()
     D = x2.shape[-1]
     return x2.view(-1, D), D
+
+
+def _needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in ts)
 
 
 def _ctx(x: torch.Tensor) -> _lib.Context:
     return _lib.context(x.device.index if x.device.index is not None else torch.cuda.current_device())
 
 
-def _map(x: torch.Tensor, op: int, what: str, dim: int = -1) -> torch.Tensor:
+def _map_fwd(x: torch.Tensor, op: int, what: str, dim: int = -1) -> torch.Tensor:
     x2, D = _prep(x, what, dim)
     out = torch.empty_like(x2)
     ctx = _ctx(x2)
     ctx.check(ctx.lib.coskad_geom_map(ctx.h, op, x2.data_ptr(), x2.shape[0], D, out.data_ptr(), _lib.stream_ptr(x2.device)),
               'coskad_geom_map')
     return out.view(x.shape)
+
+
+_MAP_HAS_BWD = (_lib.MAP_EXPMAP0, _lib.MAP_PROJECT, _lib.MAP_EXPMAP0_PROJECT, _lib.MAP_L2NORMALIZE)
+
+
+class _MapFn(torch.autograd.Function):
+    """an element-wise gmath map with its analytic vector-Jacobian product (coskad_geom_map_bwd): what autograd does through
+    geoopt at models/hyperbolic_encoder.py:147"""
+
+    @staticmethod
+    def forward(ctx, x, op, what):
+        ctx.save_for_backward(x.detach())
+        ctx.op = op
+        return _map_fwd(x, op, what)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        x2, D = _prep(x, 'x')
+        g2 = gout.detach().to(torch.float32).contiguous().view(-1, D)
+        gin = torch.empty_like(x2)
+        c = _ctx(x2)
+        c.check(c.lib.coskad_geom_map_bwd(c.h, ctx.op, x2.data_ptr(), g2.data_ptr(), x2.shape[0], D, gin.data_ptr(),
+                                          _lib.stream_ptr(x2.device)), 'coskad_geom_map_bwd')
+        return gin.view(x.shape), None, None
+
+
+def _map(x: torch.Tensor, op: int, what: str, dim: int = -1) -> torch.Tensor:
+    if _needs_grad(x):
+        if op not in _MAP_HAS_BWD:
+            raise NotImplementedError('the utils/hyper_math.py flavour is forward-only (a pinned cross-check, not a training path)')
+        if dim not in (-1, x.dim() - 1):
+            raise NotImplementedError('only dim=-1 is implemented')
+        return _MapFn.apply(x, op, what)
+    return _map_fwd(x, op, what, dim)
 
 
 def expmap0(u: torch.Tensor, *, k=-1.0, dim: int = -1) -> torch.Tensor:
@@ -81,7 +119,7 @@ def l2_normalize(z: torch.Tensor) -> torch.Tensor:                   # models/st
     return _map(z, _lib.MAP_L2NORMALIZE, 'z')
 
 
-def _pair(flavour: int, a: torch.Tensor, b: torch.Tensor, keepdim: bool = False) -> torch.Tensor:
+def _pair_fwd(flavour: int, a: torch.Tensor, b: torch.Tensor, keepdim: bool = False) -> torch.Tensor:
     # broadcast the 1-D operand like torch does; the kernel computes f(a_row, b_row)
     if a.dim() == 1 and b.dim() > 1:
         a = a.expand_as(b)
@@ -103,11 +141,57 @@ def _pair(flavour: int, a: torch.Tensor, b: torch.Tensor, keepdim: bool = False)
     return out.unsqueeze(-1) if keepdim else out
 
 
+_PAIR_HAS_BWD = (_lib.SCORE_POINCARE, _lib.SCORE_POINCARE_NOPROJ, _lib.SCORE_EUCLID, _lib.SCORE_COSINE)
+
+
+class _PairFn(torch.autograd.Function):
+    """f(a, b) per row with gradients to both operands (coskad_dist_bwd); a [D] operand is broadcast and its gradient is the
+    sum of the per-row gradients.  What autograd does through gmath.dist at models/hyperbolic_encoder.py:157."""
+
+    @staticmethod
+    def forward(ctx, a, b, flavour, keepdim):
+        ctx.save_for_backward(a.detach(), b.detach())
+        ctx.flavour, ctx.keepdim = flavour, keepdim
+        return _pair_fwd(flavour, a, b, keepdim)
+
+    @staticmethod
+    def backward(ctx, gs):
+        a, b = ctx.saved_tensors
+        rows = b if a.dim() == 1 and b.dim() > 1 else a
+        D = rows.shape[-1]
+        a2 = a.to(device=rows.device, dtype=torch.float32).expand_as(rows).contiguous().view(-1, D)
+        bc = int(b.dim() == 1 or b.numel() == D) if rows is a else 0
+        b2 = b.to(device=rows.device, dtype=torch.float32).contiguous().view(-1) if bc else \
+            b.to(torch.float32).contiguous().view(-1, D)
+        g2 = gs.detach().to(torch.float32).contiguous().view(-1)
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ga = torch.empty_like(a2) if need_a else None
+        gb = torch.empty_like(a2) if need_b else None
+        c = _ctx(a2)
+        c.check(c.lib.coskad_dist_bwd(c.h, ctx.flavour, a2.data_ptr(), b2.data_ptr(), bc, g2.data_ptr(), a2.shape[0], D,
+                                      _lib._ptr(ga), _lib._ptr(gb), _lib.stream_ptr(a2.device)), 'coskad_dist_bwd')
+
+        def shape_like(g, t):
+            if g is None:
+                return None
+            g = g.view(rows.shape)
+            return g.reshape(-1, D).sum(0).view(t.shape) if t.numel() == D and rows.numel() != D else g.view(t.shape)
+        return shape_like(ga, a), shape_like(gb, b), None, None
+
+
+def _pair(flavour: int, a: torch.Tensor, b: torch.Tensor, keepdim: bool = False) -> torch.Tensor:
+    if _needs_grad(a, b):
+        if flavour not in _PAIR_HAS_BWD:
+            raise NotImplementedError('the utils/hyper_math.py flavour is forward-only (a pinned cross-check, not a training path)')
+        return _PairFn.apply(a, b.to(a.device) if b.device != a.device else b, flavour, keepdim)
+    return _pair_fwd(flavour, a, b, keepdim)
+
+
 def dist(x: torch.Tensor, y: torch.Tensor, *, k=-1.0, keepdim: bool = False, dim: int = -1) -> torch.Tensor:
     """2 artanh(|(-x) (+) y|); either operand may be a single point [D] (the center)."""
     _k_is_minus_one(k)
-    if x.dim() == 1 and y.dim() > 1:
-        x = x.to(y.device).expand_as(y).contiguous()
+    if x.dim() == 1 and y.dim() > 1 and x.device != y.device:
+        x = x.to(y.device)
     return _pair(_lib.SCORE_POINCARE, x, y, keepdim)
 
 

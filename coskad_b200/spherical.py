@@ -29,12 +29,15 @@ from .sts import STSAE, _check_x
 from .trainer import LightningModule
 
 
-class PowerSphericalQ:
+class PowerSphericalQ(torch.distributions.Distribution):
     """the subset of power_spherical.PowerSpherical used by COSKAD: rsample(), entropy(), loc, scale"""
+    arg_constraints = {}
+    has_rsample = True
 
-    def __init__(self, loc: torch.Tensor, scale: torch.Tensor):
+    def __init__(self, loc: torch.Tensor, scale: torch.Tensor, validate_args=None):
         self.loc, self.scale = loc, scale
         self.d = loc.shape[-1]
+        super().__init__(batch_shape=loc.shape[:-1], event_shape=loc.shape[-1:], validate_args=False)
 
     def _alpha_beta(self):
         return (self.d - 1) / 2 + self.scale, torch.full_like(self.scale, (self.d - 1) / 2)
@@ -45,7 +48,11 @@ class PowerSphericalQ:
         g = torch.randn(self.loc.shape[:-1] + (self.d - 1,), device=self.loc.device, dtype=self.loc.dtype)
         return t, g / g.norm(dim=-1, keepdim=True)
 
-    def rsample(self, noise=None) -> torch.Tensor:
+    def rsample(self, sample_shape=torch.Size(), noise=None) -> torch.Tensor:
+        if isinstance(sample_shape, (tuple, list)) and len(sample_shape) == 2 and torch.is_tensor(sample_shape[0]):
+            noise, sample_shape = sample_shape, torch.Size()          # rsample((t, v)): explicit noise, positional
+        if len(tuple(sample_shape)) != 0:
+            raise NotImplementedError('COSKAD draws one sample per window (models/sts/vae.py:129)')
         t, v = self.draw_noise() if noise is None else noise
         if not (torch.is_grad_enabled() and (self.loc.requires_grad or t.requires_grad)):
             return ps_sample(self.loc, t, v)                               # CUDA kernel
@@ -62,17 +69,22 @@ class PowerSphericalQ:
         return -(log_norm + self.scale * (math.log(2) + torch.digamma(a) - torch.digamma(a + b)))
 
 
-class HypersphericalUniformP:
-    def __init__(self, dim: int, device=None):
+class HypersphericalUniformP(torch.distributions.Distribution):
+    arg_constraints = {}
+
+    def __init__(self, dim: int, device=None, dtype=None, validate_args=None):
         self.dim = dim
+        super().__init__(batch_shape=torch.Size(), event_shape=torch.Size([dim + 1]), validate_args=False)
 
     def entropy(self) -> float:
         d = self.dim + 1
         return math.log(2) + (d / 2) * math.log(math.pi) - math.lgamma(d / 2)
 
 
+@torch.distributions.kl.register_kl(PowerSphericalQ, HypersphericalUniformP)
 def kl_divergence(q: PowerSphericalQ, p: HypersphericalUniformP) -> torch.Tensor:
-    """KL(PS || U) = -H(PS) + H(U)   (power_spherical's registered KL, used at models/spherical_vae.py:92)"""
+    """KL(PS || U) = -H(PS) + H(U)   (power_spherical's registered KL, used at models/spherical_vae.py:92 through
+    torch.distributions.kl.kl_divergence)"""
     return -q.entropy() + p.entropy()
 
 
@@ -152,7 +164,7 @@ class STSVAE(STSAE):
     def forward(self, X: torch.Tensor, noise=None):
         Z_mean, Z_var = self.encode(X)
         q_Z, p_Z = self.reparameterize(Z_mean, Z_var)
-        Z = q_Z.rsample(noise)
+        Z = q_Z.rsample(noise=noise)
         Xh = train.decode_forward(self, Z, self.training)
         return Z, Xh, (q_Z, p_Z, Z_var)
 
@@ -164,7 +176,7 @@ class STSVAE(STSAE):
             _, s = self.encode_score(X, _lib.SCORE_COSINE, center=mv, want_latent=False)
             return s
         Z_mean, Z_var = self.encode(X)
-        Z = self.reparameterize(Z_mean, Z_var)[0].rsample(noise)
+        Z = self.reparameterize(Z_mean, Z_var)[0].rsample(noise=noise)
         return gmath.cosine_score(Z, mv.to(Z.device))
 
 

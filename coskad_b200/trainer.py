@@ -104,7 +104,11 @@ class _DataConnector:
 class Trainer:
     def __init__(self, max_epochs: int = 1, device: Optional[torch.device] = None, ckpt_dir: Optional[str] = None,
                  monitor: Optional[str] = None, mode: str = 'max', save_top_k: int = 2, verbose: bool = True,
-                 check_val_every_n_epoch: int = 1, cuda_graph: bool = False, **_ignored) -> None:
+                 check_val_every_n_epoch: int = 1, cuda_graph: bool = False, callbacks=None, **_ignored) -> None:
+        for cb in callbacks or ():          # pytorch_lightning.callbacks.ModelCheckpoint of train_COSKAD.py:70-73
+            if hasattr(cb, 'dirpath') and hasattr(cb, 'save_top_k'):
+                ckpt_dir = cb.dirpath if cb.dirpath is not None else ckpt_dir
+                monitor, mode, save_top_k = cb.monitor or monitor, cb.mode, cb.save_top_k
         self.max_epochs, self.ckpt_dir, self.monitor, self.mode = max_epochs, ckpt_dir, monitor, mode
         self.save_top_k, self.verbose, self.check_val_every_n_epoch = save_top_k, verbose, check_val_every_n_epoch
         self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
@@ -118,6 +122,13 @@ class Trainer:
         self._best: List = []          # heap of (score, path)
         self._data_connector = None
         self.train_dataloader = None
+
+    @classmethod
+    def from_argparse_args(cls, args, **kw) -> 'Trainer':
+        """pl.Trainer.from_argparse_args(args, default_root_dir=..., max_epochs=..., callbacks=[...]) of train_COSKAD.py:75-78"""
+        kw.setdefault('max_epochs', getattr(args, 'ae_epochs', getattr(args, 'max_epochs', 1)))
+        kw.setdefault('ckpt_dir', kw.pop('default_root_dir', None))
+        return cls(**kw)
 
     # ------------------------------------------------------------------ fit
     def fit(self, model: LightningModule, train_loader=None, val_loader=None, train_dataloaders=None, val_dataloaders=None):

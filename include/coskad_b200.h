@@ -141,6 +141,13 @@ int coskad_geom_map(coskad_ctx* ctx, int op, const float* in, int64_t B, int D, 
  * COSINE: 1 - cos(b, a).  replaces: geoopt stereographic math dist / utils/eval_utils.py:61-67 */
 int coskad_dist(coskad_ctx* ctx, int flavour, const float* a, const float* b, int b_is_broadcast,
                 int64_t B, int D, float* out, void* stream);
+/* Vector-Jacobian products of the two calls above, so that the reference's own training_step can differentiate
+ * through gmath.expmap0 / project / dist one call at a time.  gin[B,D] = (d map(in)/d in)^T gout; ops EXPMAP0, PROJECT,
+ * EXPMAP0_PROJECT, L2NORMALIZE.  ga / gb [B,D] (either nullable) = gs[B] * d f(a,b)/d a, d b per row; flavours POINCARE,
+ * EUCLID, COSINE.   replaces: autograd through geoopt at models/hyperbolic_encoder.py:147,157 */
+int coskad_geom_map_bwd(coskad_ctx* ctx, int op, const float* in, const float* gout, int64_t B, int D, float* gin, void* stream);
+int coskad_dist_bwd(coskad_ctx* ctx, int flavour, const float* a, const float* b, int b_is_broadcast, const float* gs,
+                    int64_t B, int D, float* ga, float* gb, void* stream);
 /* dist0(x) = 2 artanh(||x||).   replaces: models/hyperbolic_encoder.py:181 */
 int coskad_dist0(coskad_ctx* ctx, const float* x, int64_t B, int D, float* out, void* stream);
 /* PowerSpherical reparameterised sample from explicit noise: z = Householder_{e1->mu}([t, sqrt(1-t^2) v]);
