@@ -64,6 +64,7 @@ SIGNATURES = {
     'coskad_train_linear': (C.c_int, [c_ctx_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int64, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     'coskad_train_col_sum': (C.c_int, [c_ctx_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_measure_fp32_peak': (C.c_int, [c_ctx_p, C.POINTER(C.c_double), C.c_void_p]),
+    'coskad_measure_tf32_peak': (C.c_int, [c_ctx_p, C.POINTER(C.c_double), C.c_void_p]),
     'coskad_launch_count': (C.c_int64, [c_ctx_p]),
     'coskad_debug_fused_stage': (C.c_int, [c_ctx_p, C.c_int, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_debug_fused_floats': (C.c_int, []),

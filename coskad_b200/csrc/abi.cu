@@ -609,6 +609,36 @@ extern "C" int coskad_measure_fp32_peak(coskad_ctx* ctx, double* tflops, void* s
   return COSKAD_OK;
 }
 
+extern "C" int coskad_measure_tf32_peak(coskad_ctx* ctx, double* tflops, void* stream_) {
+  if (!ctx || !tflops) return COSKAD_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  float* d = nullptr;
+  CK(cudaMalloc(&d, 16));
+  const int blocks = ctx->sm_count, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  tf32_peak_kernel<<<blocks, 128, 0, st>>>(256, d);   // warm-up
+  CK_LAUNCH();
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0, st));
+    tf32_peak_kernel<<<blocks, 128, 0, st>>>(iters, d);
+    CK_LAUNCH();
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 128.0 * 256.0 * 8.0 * iters * static_cast<double>(blocks);
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return COSKAD_OK;
+}
+
 // ---- training path --------------------------------------------------------------------------------
 #define TRAIN_PRE()                                    \
   if (!ctx) return COSKAD_ERR_ARG;                     \

@@ -70,4 +70,46 @@ __global__ void __launch_bounds__(128, 1) tc_mix_test_kernel(const float* __rest
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+// Sustained tcgen05 kind::tf32 rate of the device: every SM issues `iters` back-to-back M128 x N256 x K8 MMAs (A from TMEM,
+// B from shared memory -- the operand form of the channel-mixing stages) onto one accumulator.  This is the measured
+// denominator of the tensor-pipe roofline ("measure it the same way before quoting a tensor fraction").
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, float* __restrict__ sink) {
+  __shared__ __align__(128) float bsm[256 * 8];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 256 * 8; i += blockDim.x) bsm[i] = __uint_as_float(__float_as_uint(1e-3f * static_cast<float>((i * 37) % 101 - 50)) & 0xFFFFE000u);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_base = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+  uint32_t a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = __float_as_uint(1e-3f * static_cast<float>((tid + 3 * j) % 17 - 8)) & 0xFFFFE000u;
+  tc::tmem_st8(lane_base + 256, a);
+  tc::wait_st();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::make_idesc_tf32(128, 256);
+    const uint64_t bd = tc::make_smem_desc(tc::smem_u32(bsm), (256 / 8) * 128, 128);
+    for (int i = 0; i < iters; ++i) tc::mma_tf32_ts(tbase, tbase + 256, bd, idesc, i > 0 ? 1u : 0u);
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  uint32_t v[16];
+  tc::tmem_ld16(lane_base, v);
+  tc::wait_ld();
+  if (__uint_as_float(v[0]) == 12345.678f) sink[0] = __uint_as_float(v[1]);     // never true; keeps the result live
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace coskad

@@ -34,26 +34,90 @@ def allreduce_center_acc(acc: torch.Tensor) -> torch.Tensor:
 
 class FlatGradBucket:
     """One flat float32 bucket holding every parameter gradient: a single all-reduce (0.96 MB for the STSE
-    encoder) enqueued right behind the last backward kernel, then averaged like DDP."""
+    encoder) enqueued right behind the last backward kernel, then averaged like DDP.
+
+    ``attach()`` makes every ``p.grad`` a VIEW of the flat buffer (DDP's ``gradient_as_bucket_view``): autograd accumulates
+    straight into the bucket, the all-reduce runs in place, and the optimizer reads the averaged gradients from the same
+    memory -- no gather / scatter copies, and the addresses are stable, which is what lets the training step be replayed
+    as CUDA graphs around the collective (trainer.TrainStep).  Without ``attach()`` the bucket gathers the gradients into
+    a temporary flat tensor and scatters the average back."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
         self.flat: Optional[torch.Tensor] = None
+        self.views: List[torch.Tensor] = []
+
+    def attached(self) -> bool:
+        return self.flat is not None and all(p.grad is v for p, v in zip(self.params, self.views))
+
+    def attach(self) -> 'FlatGradBucket':
+        if not self.params:
+            return self
+        if self.flat is None or self.flat.device != self.params[0].device:
+            self.flat = torch.zeros(self.numel, device=self.params[0].device, dtype=torch.float32)
+            self.views, off = [], 0
+            for p in self.params:
+                self.views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+        return self
+
+    def zero_(self) -> None:
+        """replaces optimizer.zero_grad(set_to_none=True), which would detach the views"""
+        self.attach()
+        if self.flat is not None:
+            self.flat.zero_()
 
     def allreduce_(self) -> None:
         if not is_dist() or not self.params:
+            return
+        if self.attached():
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(world())
             return
         # one concatenation kernel in, one multi-tensor copy out (instead of two tiny copies per parameter)
         for p in self.params:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         grads = [p.grad for p in self.params]
-        self.flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.div_(world())
-        views = [v.view_as(g) for v, g in zip(torch.split(self.flat, [g.numel() for g in grads]), grads)]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world())
+        views = [v.view_as(g) for v, g in zip(torch.split(flat, [g.numel() for g in grads]), grads)]
         torch._foreach_copy_(grads, views)
+
+
+class ShardedLoader:
+    """every rank takes the batches ``i % world == rank`` of the wrapped loader and all ranks take the same number of them
+    (the collectives of a data-parallel step must pair up): what Lightning's DDP strategy gets from a DistributedSampler
+    (train_COSKAD.py:75-85).  ``set_epoch`` is forwarded to a sampler that has it."""
+
+    def __init__(self, loader, rank_: Optional[int] = None, world_: Optional[int] = None):
+        self.loader = loader
+        self.rank = rank() if rank_ is None else rank_
+        self.world = world() if world_ is None else world_
+        self.batch_size = getattr(loader, 'batch_size', None)
+
+    def set_epoch(self, epoch: int) -> None:
+        sampler = getattr(self.loader, 'sampler', None)
+        if hasattr(sampler, 'set_epoch'):
+            sampler.set_epoch(epoch)
+
+    def __len__(self) -> int:
+        return len(self.loader) // self.world
+
+    def __iter__(self):
+        usable = (len(self.loader) // self.world) * self.world
+        for i, batch in enumerate(self.loader):
+            if i >= usable:
+                break
+            if i % self.world == self.rank:
+                yield batch
 
 
 def gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:

@@ -43,8 +43,10 @@ class HostScorer:
 
     @torch.no_grad()
     def score(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
-              center: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x_host [N,C,T,V] float32 (pinned for full overlap) -> scores [N] float32 on the host"""
+              center: Optional[torch.Tensor] = None, on_device_scores=None) -> torch.Tensor:
+        """x_host [N,C,T,V] float32 (pinned for full overlap) -> scores [N] float32 on the host.
+        ``on_device_scores(dscore)`` (optional) runs stream-ordered between the last kernel and the D2H copy -- the hook of
+        the multi-GPU score all-gather."""
         assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
         N = x_host.shape[0]
         if out_host is None:
@@ -66,6 +68,8 @@ class HostScorer:
                                     score_out=dscore[lo:hi])
             self.free[b].record(comp)
             self.h2d_bytes += (hi - lo) * x_host[0].numel() * 4
+        if on_device_scores is not None:
+            on_device_scores(dscore)
         out_host.copy_(dscore, non_blocking=True)
         self.d2h_bytes += N * 4
         comp.synchronize()
@@ -95,13 +99,13 @@ class TrajectoryScorer:
     @torch.no_grad()
     def score(self, traj_host: torch.Tensor, win_row_host: torch.Tensor, trans_host: Optional[torch.Tensor] = None,
               mats: Optional[torch.Tensor] = None, out_host: Optional[torch.Tensor] = None,
-              center: Optional[torch.Tensor] = None) -> torch.Tensor:
+              center: Optional[torch.Tensor] = None, keep_on_device: bool = False) -> torch.Tensor:
         """traj_host [rows, 2V] f32, win_row_host [N] i64, trans_host [N] i32 (optional, with mats [n,2,3]) -> scores [N].
         The trajectory buffer goes over first; the per-window index arrays follow in chunks on a copy stream while the
         kernel scores the previous chunk."""
         assert not traj_host.is_cuda and traj_host.dtype == torch.float32 and traj_host.is_contiguous()
         N = win_row_host.numel()
-        if out_host is None:
+        if out_host is None and not keep_on_device:
             out_host = torch.empty(N, dtype=torch.float32).pin_memory()
         comp = torch.cuda.current_stream(self.device)
         traj = traj_host.to(self.device, non_blocking=True)
@@ -130,6 +134,8 @@ class TrajectoryScorer:
             self.model.encode_score_traj(traj, rows_d[lo:hi], None if tr_d is None else tr_d[lo:hi], mt, flavour=self.flavour,
                                          center=center, want_latent=False, score_out=dscore[lo:hi])
         self.h2d_bytes += N * 8 + (N * 4 if tr_d is not None else 0)
+        if keep_on_device:           # the aggregation / AUC tail consumes the scores where they are (stream-ordered)
+            return dscore
         out_host.copy_(dscore, non_blocking=True)
         self.d2h_bytes += N * 4
         comp.synchronize()

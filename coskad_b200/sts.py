@@ -174,6 +174,13 @@ class STSE(nn.Module):
         else:
             raise ValueError(f'Projector type {self.projector} not supported.')
 
+    def train(self, mode: bool = True):
+        """every train/eval switch drops the folded-weight cache: a CUDA-graph replay of the training step updates the
+        parameters and the BatchNorm statistics on the device without bumping any ``tensor._version``, so the version key
+        of ``_sync_encoder`` alone would let an eval pass score with the weights of the previous fold"""
+        self._enc_key = self._dec_key = None
+        return super().train(mode)
+
     # -- C-ABI plumbing
     def _context(self, X: torch.Tensor) -> _lib.Context:
         dev = X.device.index if X.device.index is not None else torch.cuda.current_device()

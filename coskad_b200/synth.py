@@ -44,7 +44,10 @@ def make_model(kind: str = 'stse', latent_dim: int = 16, seed: int = 0, device='
     """random-init network of the reference architecture (config/UBnormal/*.yaml shapes)"""
     from . import sts
     torch.manual_seed(seed)
-    cls = {'stse': sts.STSE, 'stsae': sts.STSAE}[kind]
+    if kind == 'stsvae':
+        from .spherical import STSVAE as cls
+    else:
+        cls = {'stse': sts.STSE, 'stsae': sts.STSAE}[kind]
     m = cls(input_dim=2, layer_channels=[32, 16, 32], hidden_dimension=64, latent_dim=latent_dim, n_frames=12,
             n_joints=17, encoder_type='sts_gcn', projector='linear', distance='euclidean', dropout=0.0)
     randomize_bn_(m, seed)

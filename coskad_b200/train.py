@@ -111,11 +111,23 @@ class _LayerFn(torch.autograd.Function):
                 dW2, db2 if ctx.has_b[1] else None, redf[2 * CO:3 * CO], dbeta.clone(), redf[3 * CO:3 * CO + 1], None, None)
 
 
+def _check_params(*tensors) -> None:
+    """the kernels read raw device pointers: a half / double / CPU / non-contiguous parameter would be read as garbage"""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.CoskadError('training kernels need contiguous float32 CUDA parameters, got '
+                                   f'{tuple(t.shape)} {t.dtype} on {t.device} (contiguous={t.is_contiguous()})')
+
+
 def layer_forward(layer, X: torch.Tensor, training: bool) -> torch.Tensor:
     if isinstance(layer.residual, torch.nn.Identity):
         raise NotImplementedError('identity residual (c_in == c_out) does not occur in any COSKAD config; not implemented '
                                   'in the training kernels')
     conv1, bn1, conv2, bn2 = layer.tcn[0], layer.tcn[1], layer.residual[0], layer.residual[1]
+    _check_params(layer.gcn.A, layer.gcn.T, conv1.weight, conv1.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
+                  conv2.weight, conv2.bias, bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var, layer.prelu.weight)
     return _LayerFn.apply(X, layer.gcn.A, layer.gcn.T, conv1.weight, conv1.bias, bn1.weight, bn1.bias,
                           conv2.weight, conv2.bias, bn2.weight, bn2.bias, layer.prelu.weight, layer, training)
 
@@ -195,10 +207,12 @@ class _LinearExpandFn(torch.autograd.Function):
 
 
 def linear_reduce(H, W, bias):
+    _check_params(W, bias)
     return _LinearReduceFn.apply(H, W, bias)
 
 
 def linear_expand(z, W, bias):
+    _check_params(W, bias)
     return _LinearExpandFn.apply(z, W, bias)
 
 

@@ -101,6 +101,71 @@ class _DataConnector:
     def __init__(self, loader): self._train_dataloader_source = _LoaderSource(loader)
 
 
+class TrainStep:
+    """One optimisation step: ``training_step`` + backward + flat gradient all-reduce + optimizer.
+
+    Gradients live in one flat bucket (``dist.FlatGradBucket.attach``), so the step has three device phases with stable
+    addresses: (A) zero the bucket, forward, backward -- the gradients accumulate into the bucket; (N) one in-place NCCL
+    all-reduce of the bucket + the division by the world size; (B) the optimizer.  ``capture`` records A and B as CUDA
+    graphs (one graph holding A and B when there is a single rank); ``replay`` enqueues graph A, the collective and graph
+    B on the current stream -- three host calls per step and no host synchronisation, so data-parallel runs replay
+    exactly like single-GPU ones (the collective itself is not captured: capturing NCCL inside the step graph hung a
+    2-GPU replay with torch 2.11 / NCCL 2.28)."""
+
+    def __init__(self, model: 'LightningModule', opt: torch.optim.Optimizer, bucket: 'cdist.FlatGradBucket',
+                 device: torch.device) -> None:
+        self.model, self.opt, self.bucket, self.device = model, opt, bucket, device
+        self.graph_a: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_b: Optional[torch.cuda.CUDAGraph] = None
+        self.static: Optional[List[torch.Tensor]] = None
+        self.loss: Optional[torch.Tensor] = None
+
+    def eager(self, batch, batch_idx: int) -> torch.Tensor:
+        # a function of its own: no reference to the autograd graph (the loss) survives the step, so a later capture
+        # builds fresh AccumulateGrad nodes on the capture stream
+        self.bucket.zero_()
+        loss = self.model.training_step(batch, batch_idx)
+        loss.backward()
+        self.bucket.allreduce_()
+        self.opt.step()
+        return loss.detach()
+
+    @property
+    def captured(self) -> bool:
+        return self.graph_a is not None
+
+    def capture(self, batch, batch_idx: int) -> None:
+        """record the step on static copies of ``batch`` (nothing executes during the capture)"""
+        self.static = [b.clone() for b in batch]
+        self.bucket.attach()
+        torch.cuda.synchronize(self.device)
+        split = cdist.world() > 1
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self.bucket.flat.zero_()
+            loss = self.model.training_step(self.static, batch_idx)
+            loss.backward()
+            if not split:
+                self.opt.step()
+        self.loss = loss.detach()                  # no reference to the autograd graph is kept
+        if split:
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+                self.opt.step()
+
+    def matches(self, batch) -> bool:
+        return self.static is not None and _same_layout(batch, self.static)
+
+    def replay(self, batch) -> torch.Tensor:
+        for dst, src in zip(self.static, batch):
+            dst.copy_(src, non_blocking=True)
+        self.graph_a.replay()
+        if self.graph_b is not None:
+            self.bucket.allreduce_()               # in place on the bucket the two graphs read and write
+            self.graph_b.replay()
+        return self.loss
+
+
 class Trainer:
     def __init__(self, max_epochs: int = 1, device: Optional[torch.device] = None, ckpt_dir: Optional[str] = None,
                  monitor: Optional[str] = None, mode: str = 'max', save_top_k: int = 2, verbose: bool = True,
@@ -135,6 +200,11 @@ class Trainer:
         train_loader = train_loader if train_loader is not None else train_dataloaders
         val_loader = val_loader if val_loader is not None else val_dataloaders
         model.trainer = self
+        if cdist.world() > 1 and not isinstance(train_loader, cdist.ShardedLoader):
+            # one process per GPU: every rank trains on its own batches (Lightning's DDP strategy installs a
+            # DistributedSampler, train_COSKAD.py:75-85); the center initialisation in setup() walks the same shard and
+            # all-reduces its partial sums
+            train_loader = cdist.ShardedLoader(train_loader)
         self.train_dataloader = train_loader
         self._data_connector = _DataConnector(train_loader)
         model.to(self.device)
@@ -144,37 +214,34 @@ class Trainer:
         opt = cfg['optimizer'] if isinstance(cfg, dict) else cfg
         sched = cfg.get('lr_scheduler') if isinstance(cfg, dict) else None
         monitor = (cfg.get('monitor') if isinstance(cfg, dict) else None) or self.monitor
-        bucket = cdist.FlatGradBucket(model.parameters())
-        # one process only: with the NCCL gradient all-reduce inside the capture the 2-GPU replay hung on the test box
-        # (torch 2.11 / NCCL 2.28), so data-parallel runs stay eager until the step is split around the collective
-        use_graph = self.cuda_graph and bool(getattr(model, 'graph_safe', False)) and cdist.world() == 1
+        bucket = cdist.FlatGradBucket(model.parameters()).attach()
+        use_graph = self.cuda_graph and bool(getattr(model, 'graph_safe', False))
         if self.cuda_graph and not use_graph and self.verbose and cdist.rank() == 0:
-            why = 'data-parallel run' if cdist.world() > 1 else f'{type(model).__name__} is not graph_safe'
-            print(f'cuda_graph: {why}, training eagerly')
+            print(f'cuda_graph: {type(model).__name__} is not graph_safe, training eagerly')
         if use_graph:
             _make_capturable(opt, self.device)
-        gstate: Optional[Dict[str, Any]] = None
+        step = TrainStep(model, opt, bucket, self.device)
+        self.train_step = step
         n_eager = 0
         for epoch in range(self.max_epochs):
             self.current_epoch = epoch
             t0 = time.time()
             model.train()
             model.on_train_epoch_start()
+            if hasattr(train_loader, 'set_epoch'):
+                train_loader.set_epoch(epoch)
             outputs, nwin = [], 0
             for batch_idx, batch in enumerate(train_loader):
                 batch = _to_device(batch, self.device)
                 nwin += int(batch[0].shape[0])
-                if use_graph and gstate is None and n_eager >= _GRAPH_WARMUP and _flat_tensors(batch) \
+                if use_graph and not step.captured and n_eager >= _GRAPH_WARMUP and _flat_tensors(batch) \
                         and int(batch[0].shape[0]) == getattr(train_loader, 'batch_size', int(batch[0].shape[0])):
-                    gstate = self._capture(model, opt, bucket, batch, batch_idx)
-                if gstate is not None and _same_layout(batch, gstate['batch']):
-                    for dst, src in zip(gstate['batch'], batch):
-                        dst.copy_(src, non_blocking=True)
-                    gstate['graph'].replay()
+                    step.capture(batch, batch_idx)
+                if step.captured and step.matches(batch):
+                    outputs.append(step.replay(batch).clone())
                     self.graph_replays += 1
-                    outputs.append(gstate['loss'].detach().clone())
                     continue
-                outputs.append(self._eager_step(model, opt, bucket, batch, batch_idx))
+                outputs.append(step.eager(batch, batch_idx))
                 n_eager += 1
             model.training_epoch_end(outputs)
             model.on_train_epoch_end()
@@ -202,31 +269,6 @@ class Trainer:
                 print('epoch', epoch, {k: (round(v, 6) if isinstance(v, float) else v) for k, v in logs.items()})
             self._checkpoint(model, logs, monitor)
         return self
-
-    @staticmethod
-    def _eager_step(model, opt, bucket, batch, batch_idx) -> torch.Tensor:
-        # a function of its own: no reference to the autograd graph (the loss) survives the step, so a later capture
-        # builds fresh AccumulateGrad nodes on the capture stream
-        loss = model.training_step(batch, batch_idx)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        bucket.allreduce_()
-        opt.step()
-        return loss.detach()
-
-    def _capture(self, model, opt, bucket, batch, batch_idx) -> Dict[str, Any]:
-        """record one full training step on static copies of ``batch`` (nothing executes during the capture)"""
-        static = [b.clone() for b in batch]
-        opt.zero_grad(set_to_none=True)
-        torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss = model.training_step(static, batch_idx)
-            loss.backward()
-            bucket.allreduce_()
-            opt.step()
-            opt.zero_grad(set_to_none=True)
-        return {'graph': graph, 'batch': static, 'loss': loss.detach()}     # no reference to the autograd graph is kept
 
     def _checkpoint(self, model, logs, monitor) -> None:
         """ModelCheckpoint(save_top_k=2, monitor='validation_auc' | 'loss') of train_COSKAD.py:70-73"""
@@ -273,8 +315,10 @@ class Trainer:
         return [o for _, o in local]
 
 
-def load_checkpoint(model: nn.Module, path: str, strict: bool = True) -> Dict[str, Any]:
-    ck = torch.load(path, map_location='cpu', weights_only=False)
+def load_checkpoint(model: nn.Module, path: str, strict: bool = True, trust_pickle: bool = False) -> Dict[str, Any]:
+    """checkpoints written here hold tensors, ints and floats only, so they load with ``weights_only=True``;
+    ``trust_pickle=True`` opts into unpickling arbitrary objects (a legacy Lightning .ckpt from a trusted source)"""
+    ck = torch.load(path, map_location='cpu', weights_only=not trust_pickle)
     sd = ck['state_dict'] if isinstance(ck, dict) and 'state_dict' in ck else ck
     own = model.state_dict()
     # buffers assigned at run time upstream (model.c) may change shape/device; copy what matches by name

@@ -246,6 +246,9 @@ int coskad_train_col_sum(coskad_ctx* ctx, const float* a, int64_t B, int N, floa
 /* Sustained FP32-FMA rate of the device (TFLOP/s) from a register-resident FFMA loop; used by
  * bench.py as the measured denominator of the FP32 roofline. */
 int coskad_measure_fp32_peak(coskad_ctx* ctx, double* tflops, void* stream);
+/* Sustained tcgen05 kind::tf32 rate (TFLOP/s, one product per MAC -- a 3xTF32 product costs three) from back-to-back
+ * M128 N256 K8 MMAs with A in TMEM and B in shared memory on every SM; the measured denominator of roofline_tensor. */
+int coskad_measure_tf32_peak(coskad_ctx* ctx, double* tflops, void* stream);
 /* test aid: run tile 0 of the fused kernel up to `stage` (S0..S23 of fused_eval.cuh) and dump the
  * CTA's shared-memory activations; coskad_debug_fused_floats() floats are written to dbg_out. */
 int coskad_debug_fused_stage(coskad_ctx* ctx, int with_decoder, const float* x, int64_t B, int stage,

@@ -16,7 +16,10 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['metric'] == 'pose windows/sec scored' and d['unit'] == 'windows/s'
     assert d['higher_is_better'] is True and d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 1
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    # the unmodified reference network from baseline/_ref when that copy exists (oracle/install_ref.py), else the oracle port
+    have_ref = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'models', 'sts'))
+    assert d['cpu_baseline']['kind'] == ('reference' if have_ref else 'port'), d['cpu_baseline']
+    assert d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'windows/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['gpu_launches'] == 0 and d['vs_baseline'] is None
 

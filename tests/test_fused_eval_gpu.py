@@ -65,8 +65,9 @@ def test_config0_4096_windows(shape, impl):
         c = ogm.weighted_midpoint(xr, k=K)
         sr = ogm.dist(xr, c, k=K)
     z, s = m.encode_score(x.cuda(), 1, center=c.cuda())
-    _assert_close(z, zr, 'latent')
-    _assert_close(s, sr, 'poincare score')
+    _assert_close(z, zr, 'latent')                      # signed components cross zero: 1e-4 relative + 1e-5 of the largest
+    # the north-star gate: per-window SCORES within 1e-4 RELATIVE, no absolute slack (scores are bounded away from zero)
+    _assert_close(s, sr, 'poincare score', atol_scale=0.0)
     # the score recomputed by the oracle FROM THE KERNEL'S latent isolates the geometry arithmetic
     with torch.no_grad():
         s2 = ogm.dist(ogm.project(ogm.expmap0(z.cpu(), k=K), k=K), c, k=K)
