@@ -61,6 +61,9 @@ SIGNATURES = {
     'coskad_train_bn_prelu_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 8 + [C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_train_bn_prelu_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 9 + [C.c_int64, C.c_int, C.c_void_p, c_float_p, c_float_p, C.c_void_p]),
     'coskad_train_mix_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64, C.c_int, C.c_int] + [c_float_p] * 6 + [C.c_void_p]),
+    'coskad_train_mix_bwd_tc': (C.c_int, [c_ctx_p] + [c_float_p] * 9 + [C.c_void_p] + [c_float_p] * 4 + [C.c_int64, C.c_int, C.c_int]
+                                + [c_float_p] * 8 + [C.c_void_p]),
+    'coskad_set_train_impl': (C.c_int, [c_ctx_p, C.c_int]),
     'coskad_train_linear': (C.c_int, [c_ctx_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int64, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     'coskad_train_col_sum': (C.c_int, [c_ctx_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_measure_fp32_peak': (C.c_int, [c_ctx_p, C.POINTER(C.c_double), C.c_void_p]),

@@ -13,6 +13,7 @@
 #include "fused_eval_tc.cuh"
 #include "latent_ops.cuh"
 #include "train_ops.cuh"
+#include "train_tc.cuh"
 #include "tc_test.cuh"
 
 using namespace coskad;
@@ -34,6 +35,10 @@ struct coskad_ctx {
   int32_t* cnt_scratch = nullptr;
   size_t cnt_scratch_elems = 0;
   bool smem_attr_set = false;
+  // training: per-CTA partial sums of the cross-CTA reductions (second stage: partial_sum_kernel), stream-ordered reuse
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  int train_impl = 1;      // 1 = 1x1 convolutions / weight gradients on tcgen05 (3xTF32), 0 = the FP32 CUDA-core kernels (A/B)
 };
 
 static thread_local std::string g_create_err;
@@ -62,6 +67,19 @@ static int fail(coskad_ctx* ctx, int code, const char* fmt, ...) {
   } while (0)
 
 static inline size_t align4(size_t n) { return (n + 3) & ~static_cast<size_t>(3); }
+
+// the partial-sum workspace: one allocation, grown on demand (never inside a stream capture: the eager warm-up steps of a
+// graph-captured training loop size it first)
+static int ensure_ws(coskad_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return COSKAD_OK;
+  const size_t want = bytes < (static_cast<size_t>(32) << 20) ? (static_cast<size_t>(32) << 20) : bytes;
+  cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  CK(cudaMalloc(&ctx->ws, want));
+  ctx->ws_bytes = want;
+  return COSKAD_OK;
+}
 
 extern "C" int coskad_abi_version(void) { return COSKAD_ABI_VERSION; }
 
@@ -100,6 +118,7 @@ extern "C" int coskad_destroy(coskad_ctx* ctx) {
   cudaFree(ctx->enc_pack);
   cudaFree(ctx->dec_pack);
   cudaFree(ctx->cnt_scratch);
+  cudaFree(ctx->ws);
   delete ctx;
   return COSKAD_OK;
 }
@@ -497,8 +516,13 @@ extern "C" int coskad_center_partial(coskad_ctx* ctx, int flavour, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   int g = row_grid(ctx, B);
   if (g > ctx->sm_count * 2) g = ctx->sm_count * 2;
-  if (D <= 32) center_partial_kernel<1><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, acc);
-  else center_partial_kernel<4><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, acc);
+  // per-CTA float64 partials, added to acc in a fixed order (no atomics: the center is bit-reproducible)
+  { const int rc = ensure_ws(ctx, sizeof(double) * static_cast<size_t>(g) * (D + 2)); if (rc) return rc; }
+  double* part = reinterpret_cast<double*>(ctx->ws);
+  if (D <= 32) center_partial_kernel<1><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, part);
+  else center_partial_kernel<4><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, part);
+  CK_LAUNCH();
+  center_partial_final_kernel<<<1, 160, 0, st>>>(part, g, D, acc);
   CK_LAUNCH();
   return COSKAD_OK;
 }
@@ -663,6 +687,20 @@ extern "C" int coskad_train_contract_fwd(coskad_ctx* ctx, const float* X, const 
   return COSKAD_OK;
 }
 
+template <typename TOut>
+static int launch_partial_sum(coskad_ctx* ctx, const float* part, int nparts, int64_t stride, int64_t n, TOut* out, cudaStream_t st) {
+  partial_sum_kernel<TOut><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(part, nparts, stride, n, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_set_train_impl(coskad_ctx* ctx, int impl) {
+  if (!ctx) return COSKAD_ERR_ARG;
+  if (impl != 0 && impl != 1) return fail(ctx, COSKAD_ERR_ARG, "train impl must be 0 (FP32 CUDA cores) or 1 (tcgen05), got %d", impl);
+  ctx->train_impl = impl;
+  return COSKAD_OK;
+}
+
 extern "C" int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const float* dXres, const float* X,
                                          const float* G1, const float* A, const float* T, int64_t R, float* dX,
                                          float* dA, float* dT, void* stream_) {
@@ -670,10 +708,12 @@ extern "C" int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const
   if (R <= 0) return COSKAD_OK;
   const int64_t nblk = (R + kCRows - 1) / kCRows;
   const int g = static_cast<int>(nblk < ctx->sm_count ? nblk : ctx->sm_count);
+  { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(g) * kContractPart); if (rc) return rc; }
   CK(cudaFuncSetAttribute(train_contract_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
-  train_contract_bwd_kernel<<<g, kCThreads, kCSmemBytes, st>>>(dG, dXres, X, G1, A, T, R, dX, dA, dT);
+  train_contract_bwd_kernel<<<g, kCThreads, kCSmemBytes, st>>>(dG, dXres, X, G1, A, T, R, dX, ctx->ws);
   CK_LAUNCH();
-  return COSKAD_OK;
+  { const int rc = launch_partial_sum<float>(ctx, ctx->ws, g, kContractPart, kT * kV * kV, dA, st); if (rc) return rc; }
+  return launch_partial_sum<float>(ctx, ctx->ws + kT * kV * kV, g, kContractPart, kV * kT * kT, dT, st);
 }
 
 // chan_gemm_kernel launcher: K input channels -> M output channels over B*204 positions
@@ -697,17 +737,33 @@ static int launch_chan_gemm(coskad_ctx* ctx, bool stats_on, const float* in1, co
   return COSKAD_OK;
 }
 
+// tcgen05 forward convolution: y1, y2 and the BatchNorm statistics (per-warp partials -> fixed-order second stage)
+template <int CIP, int CO, int COP>
+static int launch_tc_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1, const float* W2,
+                             const float* b2, int64_t B, int CI, float* y1, float* y2, double* stats, cudaStream_t st) {
+  const int64_t E = B * kP, ntiles = (E + kTcT - 1) / kTcT;
+  const int per_sm = 512 / tmem_alloc_cols(4 * CIP + 2 * COP);          // TMEM columns bound the resident CTAs
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * (per_sm > 4 ? 4 : per_sm);
+  const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
+  { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(g) * 4 * 4 * CO); if (rc) return rc; }
+  tc_mix_fwd_kernel<CIP, CO, COP><<<g, kTcT, 0, st>>>(G, X, W1, b1, W2, b2, E, CI, y1, y2, ctx->ws);
+  CK_LAUNCH();
+  return launch_partial_sum<double>(ctx, ctx->ws, g * 4, 4 * CO, 4 * CO, stats, st);
+}
+
 extern "C" int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1,
                                     const float* W2, const float* b2, int64_t B, int CI, int CO, float* y1, float* y2,
                                     double* stats, void* stream_) {
   TRAIN_PRE();
   if (!chan_ok(CI) || !chan_ok(CO)) return fail(ctx, COSKAD_ERR_ARG, "training kernels support channels {2,16,32,64}, got %d->%d", CI, CO);
   if (B <= 0) return COSKAD_OK;
-  {
-    const int rc = launch_chan_gemm(ctx, true, G, X, W1, W2, 0, b1, b2, B, CI, CO, y1, y2, stats, st);
-    if (rc) return rc;
+  if (ctx->train_impl == 1) {
+#define TC_FWD(ci, co, cip, cop) if (CI == ci && CO == co) return launch_tc_mix_fwd<cip, co, cop>(ctx, G, X, W1, b1, W2, b2, B, CI, y1, y2, stats, st)
+    TC_FWD(2, 32, 8, 32); TC_FWD(32, 16, 32, 16); TC_FWD(16, 32, 16, 32); TC_FWD(32, 64, 32, 64);      // encoder
+    TC_FWD(64, 32, 64, 32); TC_FWD(32, 2, 32, 16);                                                       // decoder
+#undef TC_FWD
   }
-  return COSKAD_OK;
+  return launch_chan_gemm(ctx, true, G, X, W1, W2, 0, b1, b2, B, CI, CO, y1, y2, stats, st);
 }
 
 extern "C" int coskad_train_bn_finalize(coskad_ctx* ctx, const double* stats, int64_t n_per_channel, int CO, float eps,
@@ -736,15 +792,83 @@ extern "C" int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, con
                                          float* dy1, float* dy2, void* stream_) {
   TRAIN_PRE();
   if (B <= 0) return COSKAD_OK;
+  if (3 * CO + 32 > kTrainThreads) return fail(ctx, COSKAD_ERR_ARG, "bn_prelu_bwd supports c_out <= 64, got %d", CO);
   int nb = static_cast<int>((B + 7) / 8);
   const int cap = (ctx->sm_count * 8 + CO - 1) / CO;
   if (nb > cap) nb = cap;
-  train_bn_prelu_bwd_reduce_kernel<<<dim3(CO, nb), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, B, CO, red);
+  { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(nb) * 4 * CO); if (rc) return rc; }
+  train_bn_prelu_bwd_reduce_kernel<<<dim3(CO, nb), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, B, CO, ctx->ws);
   CK_LAUNCH();
-  train_bn_prelu_bwd_apply_kernel<<<ew_grid(ctx, B * CO * 32), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2,
-                                                                                    slope, red, B, CO, dy1, dy2);
+  train_bn_prelu_bwd_reduce_final_kernel<<<1, kTrainThreads, 0, st>>>(ctx->ws, nb, CO, red);
+  CK_LAUNCH();
+  if (dy1 && dy2) {        // NULL: the tensor-core backward (coskad_train_mix_bwd_tc) applies the BatchNorm / PReLU backward itself
+    train_bn_prelu_bwd_apply_kernel<<<ew_grid(ctx, B * CO * 32), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2,
+                                                                                      slope, red, B, CO, dy1, dy2);
+    CK_LAUNCH();
+  }
+  return COSKAD_OK;
+}
+
+template <int CO, int COK, int NP>
+static int launch_tc_bwd_data(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2, const float* mi,
+                              const float* g1, const float* be1, const float* g2, const float* be2, const float* slope,
+                              const double* red, const float* W1, const float* W2, int64_t B, int CI, float* dy1, float* dy2,
+                              float* dG, float* dXres, cudaStream_t st) {
+  const int64_t E = B * kP, ntiles = (E + kTcT - 1) / kTcT;
+  constexpr int KC = COK < 32 ? COK : 32;
+  const int per_sm = 512 / tmem_alloc_cols(4 * KC + 2 * NP);
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * (per_sm > 3 ? 3 : per_sm);
+  const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
+  tc_mix_bwd_data_kernel<CO, COK, NP><<<g, kTcT, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, E, CI, dy1, dy2,
+                                                        dG, dXres);
   CK_LAUNCH();
   return COSKAD_OK;
+}
+template <int CO, int CI8>
+static int launch_tc_bwd_weight(coskad_ctx* ctx, const float* dy1, const float* dy2, const float* G, const float* X, int64_t B,
+                                int CI, float* dW1, float* db1, float* dW2, float* db2, cudaStream_t st) {
+  const int64_t E = B * kP, ntiles = (E + kWgKT - 1) / kWgKT;
+  const size_t smem = sizeof(float) * wg_smem_floats(CI8);
+  int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));
+  const int tm = 512 / tmem_alloc_cols(2 * wg_n(CI8));
+  if (per_sm > tm) per_sm = tm;
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
+  const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
+  const size_t per = static_cast<size_t>(2) * CO * (CI + 1);
+  { const int rc = ensure_ws(ctx, sizeof(float) * per * g); if (rc) return rc; }
+  CK(cudaFuncSetAttribute(tc_mix_bwd_weight_kernel<CO, CI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  tc_mix_bwd_weight_kernel<CO, CI8><<<g, kTcT, smem, st>>>(dy1, dy2, G, X, E, CI, ctx->ws);
+  CK_LAUNCH();
+  tc_wgrad_reduce_kernel<<<static_cast<unsigned>((per + 255) / 256), 256, 0, st>>>(ctx->ws, g, CO, CI, dW1, db1, dW2, db2);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+// Tensor-core backward of the two 1x1 convolutions of a layer with the BatchNorm-train + PReLU backward fused in:
+// (dout, y1, y2, red) -> dy1, dy2 (scratch, written once) -> dG, dXres, dW1 += , db1 +=, dW2 +=, db2 +=
+extern "C" int coskad_train_mix_bwd_tc(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2, const float* mi,
+                                       const float* g1, const float* be1, const float* g2, const float* be2,
+                                       const float* slope, const double* red, const float* G, const float* X, const float* W1,
+                                       const float* W2, int64_t B, int CI, int CO, float* dy1, float* dy2, float* dG,
+                                       float* dXres, float* dW1, float* db1, float* dW2, float* db2, void* stream_) {
+  TRAIN_PRE();
+  if (!chan_ok(CI) || !chan_ok(CO)) return fail(ctx, COSKAD_ERR_ARG, "training kernels support channels {2,16,32,64}, got %d->%d", CI, CO);
+  if (B <= 0) return COSKAD_OK;
+  if (!dout || !y1 || !y2 || !mi || !red || !G || !X || !W1 || !W2 || !dy1 || !dy2 || !dG || !dXres || !dW1 || !dW2)
+    return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  int rc = COSKAD_ERR_ARG;
+#define TC_BWD(ci, co, cok, np, ci8)                                                                                         \
+  if (CI == ci && CO == co) {                                                                                                \
+    rc = launch_tc_bwd_data<co, cok, np>(ctx, dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, B, CI, dy1, dy2, dG, dXres, st); \
+    if (rc) return rc;                                                                                                       \
+    return launch_tc_bwd_weight<co, ci8>(ctx, dy1, dy2, G, X, B, CI, dW1, db1, dW2, db2, st);                                \
+  }
+  TC_BWD(2, 32, 32, 16, 8) TC_BWD(32, 16, 16, 32, 32) TC_BWD(16, 32, 32, 16, 16) TC_BWD(32, 64, 64, 32, 32)          // encoder
+  TC_BWD(64, 32, 32, 64, 64) TC_BWD(32, 2, 16, 32, 32)                                                              // decoder
+#undef TC_BWD
+  return fail(ctx, COSKAD_ERR_ARG, "train_mix_bwd_tc: unsupported channel pair %d -> %d", CI, CO);
 }
 
 extern "C" int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const float* dy2, const float* G, const float* X,
@@ -791,15 +915,24 @@ extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_sma
   if (B <= 0) return COSKAD_OK;
   const int64_t sd = w_is_fd ? 1 : F, sf = w_is_fd ? D : 1;
   if (mode == 0) {
-    CK(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(B) * D, st));      // the slices add their partial sums
+    // the feature slices write partial sums [kLinSlices][B][D]; the second stage adds them in a fixed order
+    const size_t n = static_cast<size_t>(B) * D;
+    { const int rc = ensure_ws(ctx, sizeof(float) * n * kLinSlices); if (rc) return rc; }
+    CK(cudaMemsetAsync(out, 0, sizeof(float) * n, st));
     const int rows_per_block = (kTrainThreads / 32) * kLinRows;
     lin_reduce_f_kernel<16><<<dim3(static_cast<unsigned>((B + rows_per_block - 1) / rows_per_block), kLinSlices), kTrainThreads, 0, st>>>(
-        A_wide, W, sd, sf, bias, B, F, D, out);
+        A_wide, W, sd, sf, bias, B, F, D, ctx->ws);
+    CK_LAUNCH();
+    return launch_partial_sum<float>(ctx, ctx->ws, kLinSlices, static_cast<int64_t>(n), static_cast<int64_t>(n), out, st);
   }
   else if (mode == 1) lin_expand_f_kernel<16><<<dim3((F + kTrainThreads - 1) / kTrainThreads, static_cast<unsigned>((B + kExpRows - 1) / kExpRows)), kTrainThreads, 0, st>>>(a_small, W, sd, sf, bias, B, F, D, out);
   else if (mode == 2) {
     const int nb = B >= 512 ? 4 : 1;                  // row slices: >= 16 rows per warp
-    lin_wgrad_kernel<16><<<dim3((F + kWgF - 1) / kWgF, nb), kTrainThreads, 0, st>>>(a_small, A_wide, sd, sf, B, F, D, out);
+    const size_t n = static_cast<size_t>(D) * F;
+    { const int rc = ensure_ws(ctx, sizeof(float) * n * nb); if (rc) return rc; }
+    lin_wgrad_kernel<16><<<dim3((F + kWgF - 1) / kWgF, nb), kTrainThreads, 0, st>>>(a_small, A_wide, sd, sf, B, F, D, ctx->ws);
+    CK_LAUNCH();
+    return launch_partial_sum<float>(ctx, ctx->ws, nb, static_cast<int64_t>(n), static_cast<int64_t>(n), out, st);
   } else return fail(ctx, COSKAD_ERR_ARG, "linear: unknown mode %d", mode);
   CK_LAUNCH();
   return COSKAD_OK;
@@ -809,7 +942,9 @@ extern "C" int coskad_train_col_sum(coskad_ctx* ctx, const float* a, int64_t B, 
   TRAIN_PRE();
   if (B <= 0 || N <= 0) return COSKAD_OK;
   const int64_t slices = (B + 63) / 64;               // >= 8 rows per thread
-  col_sum_kernel<<<dim3((N + 31) / 32, static_cast<unsigned>(slices < 32 ? slices : 32)), kTrainThreads, 0, st>>>(a, B, N, out);
+  const int ns = static_cast<int>(slices < 32 ? slices : 32);
+  { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(N) * ns); if (rc) return rc; }
+  col_sum_kernel<<<dim3((N + 31) / 32, static_cast<unsigned>(ns)), kTrainThreads, 0, st>>>(a, B, N, ctx->ws);
   CK_LAUNCH();
-  return COSKAD_OK;
+  return launch_partial_sum<float>(ctx, ctx->ws, ns, N, N, out, st);
 }

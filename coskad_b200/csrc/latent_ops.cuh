@@ -227,7 +227,7 @@ __global__ void ps_sample_kernel(const float* __restrict__ mu, const float* __re
 // POINCARE (gmath.weighted_midpoint, weights=None): gamma_i = lambda_x(x_i) = 2 / max(1 - |x_i|^2, 1e-15)
 // evaluated in float32 like the reference; the sums over windows run in float64.
 template <int E>
-__global__ void center_partial_kernel(int flavour, const float* __restrict__ z, int64_t B, int D, double* acc) {
+__global__ void center_partial_kernel(int flavour, const float* __restrict__ z, int64_t B, int D, double* __restrict__ part) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double sx[E], sg = 0.0, sn = 0.0;
 #pragma unroll
@@ -248,7 +248,8 @@ __global__ void center_partial_kernel(int flavour, const float* __restrict__ z, 
     }
     sn += 1.0;
   }
-  // CTA reduce (per lane slot) then one atomic per element per CTA
+  // CTA reduce (per lane slot) then one partial [D + 2] per CTA (center_partial_final_kernel adds them in a fixed order)
+  double* acc = part + static_cast<int64_t>(blockIdx.x) * (D + 2);
   __shared__ double red[kRowWarps][32 * E + 2];
 #pragma unroll
   for (int e = 0; e < E; ++e) red[warp][lane + 32 * e] = sx[e];
@@ -258,9 +259,16 @@ __global__ void center_partial_kernel(int flavour, const float* __restrict__ z, 
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kRowWarps; ++w) s += red[w][i];
-    if (i < 32 * E) { if (i < D) atomicAdd(acc + i, s); }
-    else atomicAdd(acc + D + (i - 32 * E), s);
+    if (i < 32 * E) { if (i < D) acc[i] = s; }
+    else acc[D + (i - 32 * E)] = s;
   }
+}
+__global__ void center_partial_final_kernel(const double* __restrict__ part, int nblk, int D, double* acc) {
+  const int i = threadIdx.x;
+  if (i >= D + 2) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += part[static_cast<int64_t>(b) * (D + 2) + i];
+  acc[i] += s;
 }
 
 // single warp

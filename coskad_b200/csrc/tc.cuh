@@ -79,6 +79,15 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T (both operands through shared-memory descriptors)
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // ---- TMEM <-> registers (32 lanes x 32 bit, 16 consecutive columns; the warp owns lanes 32*(warp%4)..+31) ----
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(

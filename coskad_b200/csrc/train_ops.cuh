@@ -83,13 +83,14 @@ constexpr int kTrainThreads = 256;
 // memory and pushed through the register-blocked FFMA2 contraction stages of the eval kernel (fused_eval.cuh:
 // temporal_stage_c32 / spatial_stage_c32: lane = row % 32, three 32-row groups per lane, weights broadcast from shared
 // memory).  The backward pass runs the same stages with transposed weights and accumulates dA / dT as per-thread register
-// tiles over the block's rows (one atomicAdd per element per block at the end).
+// tiles over the block's rows (one partial block per CTA, summed in a fixed order afterwards).
 constexpr int kCRows = kNW * 32;                 // 96
 constexpr int kCThreads = 384;
 constexpr int kCWarps = kCThreads / 32;
 constexpr int kCSmemFloats = 2 * kCRows * kCS + kTwFloats + kAwFloats;
 constexpr int kCSmemBytes = kCSmemFloats * 4;
 static_assert(kCSmemBytes <= 227 * 1024, "contraction kernels: shared memory plan exceeds 227 KB");
+constexpr int kContractPart = kT * kV * kV + kV * kT * kT;     // floats of one block's [dA | dT] partial
 
 // Row-block copies, one warp per row (rows warp, warp + 12, ..), lanes = positions p = lane + 32 k: one pointer per row and
 // a few instructions per element (a flat element index cost ~20 integer instructions per 4-byte copy).
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_fwd_kernel(const 
 // dA[t,v,w] += G1[t,v] dG[t,w];       dT[v,t,q] += X[t,v] dG1[q,v]      (summed over rows)
 __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
     const float* __restrict__ dG, const float* __restrict__ dXres, const float* __restrict__ X, const float* __restrict__ G1,
-    const float* __restrict__ A, const float* __restrict__ T, int64_t R, float* __restrict__ dX, float* dA, float* dT) {
+    const float* __restrict__ A, const float* __restrict__ T, int64_t R, float* __restrict__ dX, float* __restrict__ part) {
   extern __shared__ __align__(128) float csm[];
   float* P0 = csm;                                 // dG -> dG1 (in place)
   float* P1 = P0 + kCRows * kCS;                   // G1, then X, then dX
@@ -255,18 +256,22 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
     __syncthreads();
     contract_store_rows(dX, P1, dXres, r0, nr, tid);
   }
+  // per-block partial sums [dA (T*V*V) | dT (V*T*T)]: every element has exactly one owner thread, so these are plain stores;
+  // the blocks' partials are added in a fixed order by partial_sum_kernel (no floating-point atomics: bit-reproducible)
+  float* pA = part + static_cast<int64_t>(blockIdx.x) * kContractPart;
+  float* pT = pA + kT * kV * kV;
   if (hasA) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (4 * avg + i < kV && 4 * awg + j < kV) atomicAdd(dA + (at * kV + 4 * avg + i) * kV + 4 * awg + j, accA[i][j]);
+        if (4 * avg + i < kV && 4 * awg + j < kV) pA[(at * kV + 4 * avg + i) * kV + 4 * awg + j] = accA[i][j];
   }
   if (hasT) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) atomicAdd(dT + tv * (kT * kT) + (4 * ttg + i) * kT + 2 * tqg + j, accT[i][j]);
+      for (int j = 0; j < 2; ++j) pT[tv * (kT * kT) + (4 * ttg + i) * kT + 2 * tqg + j] = accT[i][j];
   }
 }
 
@@ -336,7 +341,8 @@ __global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout,
                                                  const float* __restrict__ y2, const float* __restrict__ mi,
                                                  const float* __restrict__ g1, const float* __restrict__ be1,
                                                  const float* __restrict__ g2, const float* __restrict__ be2,
-                                                 const float* __restrict__ slope, int64_t B, int CO, double* red) {
+                                                 const float* __restrict__ slope, int64_t B, int CO,
+                                                 float* __restrict__ part /*[gridDim.y][4][CO]*/) {
   const int co = blockIdx.x;
   const float a = slope[0];
   const float m1 = mi[co], i1 = mi[CO + co], m2 = mi[2 * CO + co], i2 = mi[3 * CO + co];
@@ -369,8 +375,25 @@ __global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout,
   if (threadIdx.x < 4) {
     double t = 0.0;
     for (int w = 0; w < nwarp; ++w) t += static_cast<double>(sh[threadIdx.x][w]);
-    if (threadIdx.x < 3) atomicAdd(red + threadIdx.x * CO + co, t);
-    else atomicAdd(red + 3 * CO, t);
+    part[(static_cast<int64_t>(blockIdx.y) * 4 + threadIdx.x) * CO + co] = static_cast<float>(t);
+  }
+}
+// second stage of the reduction above, fixed order: red[0..3CO) += per-channel sums over the batch slices, red[3CO] += the
+// PReLU-slope sum over slices and channels (one warp, lane-strided then a fixed shuffle tree)
+__global__ void train_bn_prelu_bwd_reduce_final_kernel(const float* __restrict__ part, int nb, int CO, double* red) {
+  const int i = threadIdx.x;
+  if (i < 3 * CO) {
+    const int q = i / CO, co = i % CO;
+    double s = 0.0;
+    for (int y = 0; y < nb; ++y) s += static_cast<double>(part[(static_cast<int64_t>(y) * 4 + q) * CO + co]);
+    red[i] += s;
+  }
+  if (i >= blockDim.x - 32) {
+    const int lane = i & 31;
+    double s = 0.0;
+    for (int j = lane; j < nb * CO; j += 32) s += static_cast<double>(part[(static_cast<int64_t>(j / CO) * 4 + 3) * CO + j % CO]);
+    s = warp_sum(s);
+    if (lane == 0) red[3 * CO] += s;
   }
 }
 
@@ -702,7 +725,7 @@ __global__ void __launch_bounds__(kGThreads) chan_gemm_kernel(const float* __res
 // out[b,d] += sum_{f in slice} A[b,f] W(d,f) (+ bias[d] from slice 0)   (wide-in: head forward, rev_btlnk input gradient)
 // grid (ceil(B / 32), kLinSlices): a block owns 32 rows (4 per warp) and one slice of the features; it stages W chunks of
 // [DMAX][kLinFC] in shared memory once for all its rows (one row per block re-read all 835 KB of W per row from L2) and
-// adds its partial sums to `out` (zeroed by the caller) with atomics.  A lane takes 4 consecutive features: 16-byte loads
+// writes its partial sums to its slice of `out` ([slices][B][D]); partial_sum_kernel adds the slices in a fixed order.  A lane takes 4 consecutive features: 16-byte loads
 // of the activations (4 in flight per lane) and of the staged weights; F % 4 == 0 (host-checked).
 constexpr int kLinRows = 4;            // rows per warp
 constexpr int kLinFC = 512;            // features per staged chunk
@@ -759,7 +782,8 @@ __global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) {
       const float s = warp_sum(acc[r][d]);
-      if (lane == 0 && d < D && b0 + r < B) atomicAdd(out + (b0 + r) * D + d, s + ((blockIdx.y == 0 && bias) ? bias[d] : 0.f));
+      if (lane == 0 && d < D && b0 + r < B)      // one partial per feature slice: out is [kLinSlices][B][D] here
+        out[(static_cast<int64_t>(blockIdx.y) * B + b0 + r) * D + d] = s + ((blockIdx.y == 0 && bias) ? bias[d] : 0.f);
     }
 }
 // out[b,f] = sum_d a[b,d] W(d,f) + bias[f]           (wide-out: rev_btlnk forward, head input gradient)
@@ -793,8 +817,8 @@ __global__ void lin_expand_f_kernel(const float* __restrict__ a, const float* __
   }
 }
 // dW(d,f) += sum_b a[b,d] A[b,f].  grid (ceil(F/128), NB): the 8 warps of a block share 128 features (a lane owns 4
-// consecutive ones, 16-byte loads) and split the block's rows; their partial sums meet in shared memory, so the block
-// issues one atomicAdd per weight (one per thread and row slice was 6.7 M atomics for the 16 x 13056 bottleneck).
+// consecutive ones, 16-byte loads) and split the block's rows; their partial sums meet in shared memory and the block
+// writes one partial per weight and row slice (summed in a fixed order by partial_sum_kernel).
 constexpr int kWgF = 128;
 template <int DMAX>
 __global__ void __launch_bounds__(kTrainThreads) lin_wgrad_kernel(const float* __restrict__ a, const float* __restrict__ A,
@@ -868,10 +892,10 @@ __global__ void __launch_bounds__(kTrainThreads) lin_wgrad_kernel(const float* _
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kHalf; ++w) s += red[w][d][fl];
-    atomicAdd(dW + d * sd + fo * sf, s);
+    dW[static_cast<int64_t>(blockIdx.y) * D * F + d * sd + fo * sf] = s;       // partial of this row slice: [gridDim.y][D*F]
   }
 }
-// column sums: out[j] += sum_b a[b, j]   (bias gradients); grid (ceil(N/32), row slices): a block owns 32 columns and
+// column sums: partial[y][j] = sum over the slice's rows of a[b, j]   (bias gradients); grid (ceil(N/32), row slices): a block owns 32 columns and
 // every gridDim.y-th group of 8 rows
 __global__ void col_sum_kernel(const float* __restrict__ a, int64_t B, int N, float* out) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -885,7 +909,7 @@ __global__ void col_sum_kernel(const float* __restrict__ a, int64_t B, int N, fl
   if ((threadIdx.x >> 5) == 0 && j < N) {
     float t = 0.f;
     for (int r = 0; r < nrow; ++r) t += sh[r][threadIdx.x & 31];
-    atomicAdd(out + j, t);
+    out[static_cast<int64_t>(blockIdx.y) * N + j] = t;                          // partial of this row slice: [gridDim.y][N]
   }
 }
 

@@ -1,0 +1,496 @@
+// train_tc.cuh -- the GEMM-shaped parts of a training step on the 5th-generation tensor cores (tcgen05, TMEM).
+//
+// A train-mode ST_GCNN layer (models/graph_layers/stsgcn.py:94-116 under autograd) holds three GEMMs over the
+// E = B*204 positions of a batch, all with tiny channel extents (2..64):
+//   forward        y1[e,co] = sum_ci W1[co,ci] G[e,ci] + b1[co],  y2 likewise from X / W2     (M = e, N = co, K = ci)
+//   backward data  dG[e,ci] = sum_co W1[co,ci] dy1[e,co],         dXres likewise              (M = e, N = ci, K = co)
+//   weight grad    dW1[co,ci] = sum_e dy1[e,co] G[e,ci], db1[co] = sum_e dy1[e,co]            (M = co, N = ci, K = e)
+// Single-pass TF32 breaks the 1e-4 tolerance, so every product is the 3xTF32 split of tc.cuh:
+// a = a_hi + a_lo, D += A_hi B_hi + A_lo B_hi + A_hi B_lo.  With the tensor pipe doing the MACs these kernels are bound by
+// HBM (activations are [B, C, 204] float32 between kernels) instead of by the FP32 pipe.
+//
+//  * forward / backward data: M-tile = 128 consecutive positions, one thread per position (= TMEM lane).  The thread loads
+//    its position's channel values (coalesced across the warp), splits them and writes them as the A operand straight into
+//    TMEM (tcgen05.st); the weights are canonical K-major shared-memory images built once per CTA; D comes back with
+//    tcgen05.ld and is stored coalesced.  The backward-data kernel computes dy1 / dy2 = BatchNorm-train + PReLU backward of
+//    (dout, y1, y2) on the fly (the former element-wise "apply" kernel is gone) and writes them once for the weight gradient.
+//  * weight gradient: both operands are K-major in global memory already (positions are contiguous per channel row), so
+//    16-byte loads go through registers (split) into padded canonical images (LBO = 144 B: conflict-free STS.128); M = 64
+//    rows of dy^T, N = c_in rows of G^T plus one row of ones (its column of D is the bias gradient); the accumulators stay
+//    in TMEM for all tiles of a CTA (split-K over the grid) and leave as one partial block per CTA.
+//  * every cross-CTA sum (BatchNorm statistics, dW, db) goes through per-CTA partials and a fixed-order second stage
+//    (partial_sum_kernel): no floating-point atomics, two runs are bit-identical.
+#pragma once
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace coskad {
+
+constexpr int kTcT = 128;                       // threads per CTA = positions per M-tile = TMEM lanes
+
+__host__ __device__ constexpr int tmem_alloc_cols(int need) {
+  return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+}
+// canonical K-major, no swizzle: element (n, k) of an [N][K] operand; LBO = (N/8)*128 B, SBO = 128 B (fold.cuh, tc_test.cuh)
+__device__ __forceinline__ int kmaj_idx(int n, int k, int N) { return ((k >> 2) * (N >> 3) + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3); }
+
+// out[i] += sum_j part[j*stride + i] in a FIXED order (double accumulator): the second stage of every cross-CTA reduction
+template <typename TOut>
+__global__ void partial_sum_kernel(const float* __restrict__ part, int nparts, int64_t stride, int64_t n, TOut* out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int j = 0; j < nparts; ++j) s += static_cast<double>(part[static_cast<int64_t>(j) * stride + i]);
+  out[i] += static_cast<TOut>(s);
+}
+
+// ---- forward: y1 = conv1x1(G; W1, b1), y2 = conv1x1(X; W2, b2) + per-CTA BatchNorm statistics ---------------------------
+// part [gridDim.x * 4 warps][4*CO] = sum y1, sum y1^2, sum y2, sum y2^2 per channel of the positions the warp owned.
+// CIP = c_in padded to a multiple of 8 (K step of kind::tf32), COP = c_out padded to a multiple of 16 (N of an M = 128 MMA).
+template <int CIP, int CO, int COP>
+__global__ void __launch_bounds__(kTcT) tc_mix_fwd_kernel(const float* __restrict__ G, const float* __restrict__ X,
+                                                         const float* __restrict__ W1, const float* __restrict__ b1,
+                                                         const float* __restrict__ W2, const float* __restrict__ b2, int64_t E,
+                                                         int CI, float* __restrict__ y1, float* __restrict__ y2,
+                                                         float* __restrict__ part) {
+  constexpr int kColD = 4 * CIP;                                  // A: G_hi, G_lo, X_hi, X_lo; D: y1 | y2
+  constexpr int kAlloc = tmem_alloc_cols(4 * CIP + 2 * COP);
+  constexpr int NQ = 2 * COP / 16;                                // 16-column chunks of [y1 | y2]
+  __shared__ __align__(128) float wimg[4][COP * CIP];             // W1 hi, W1 lo, W2 hi, W2 lo
+  __shared__ float bias_s[2 * COP];
+  __shared__ float tr[4][32][17];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < COP * CIP; i += kTcT) {
+    const int n = i / CIP, k = i - n * CIP;
+    const bool in = n < CO && k < CI;
+    uint32_t h, l;
+    tc::split_tf32(in ? W1[n * CI + k] : 0.f, h, l);
+    wimg[0][kmaj_idx(n, k, COP)] = __uint_as_float(h); wimg[1][kmaj_idx(n, k, COP)] = __uint_as_float(l);
+    tc::split_tf32(in ? W2[n * CI + k] : 0.f, h, l);
+    wimg[2][kmaj_idx(n, k, COP)] = __uint_as_float(h); wimg[3][kmaj_idx(n, k, COP)] = __uint_as_float(l);
+  }
+  for (int i = tid; i < 2 * COP; i += kTcT) {
+    const int br = i / COP, co = i % COP;
+    const float* bp = br ? b2 : b1;
+    bias_s[i] = (co < CO && bp) ? bp[co] : 0.f;
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, kAlloc);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_base = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+  const int64_t ntiles = (E + kTcT - 1) / kTcT;
+  float sacc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) sacc[q] = 0.f;
+  float g[CIP], x[CIP];
+  auto load_tile = [&](int64_t t) {
+    const int64_t e = t * kTcT + tid;
+    const bool ok = t < ntiles && e < E;
+    const int64_t b = ok ? e / kP : 0;
+    const int64_t base = (b * CI) * kP + (ok ? e - b * kP : 0);
+#pragma unroll
+    for (int c = 0; c < CIP; ++c) {
+      g[c] = (ok && c < CI) ? __ldg(G + base + static_cast<int64_t>(c) * kP) : 0.f;
+      x[c] = (ok && c < CI) ? __ldg(X + base + static_cast<int64_t>(c) * kP) : 0.f;
+    }
+  };
+  uint32_t phase = 0;
+  load_tile(blockIdx.x);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // registers -> split -> A operand in TMEM
+#pragma unroll
+    for (int c0 = 0; c0 < CIP; c0 += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tc::split_tf32(g[c0 + j], hi[j], lo[j]);
+      tc::tmem_st8(lane_base + c0, hi);
+      tc::tmem_st8(lane_base + CIP + c0, lo);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tc::split_tf32(x[c0 + j], hi[j], lo[j]);
+      tc::tmem_st8(lane_base + 2 * CIP + c0, hi);
+      tc::tmem_st8(lane_base + 3 * CIP + c0, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::make_idesc_tf32(128, COP);
+      const uint32_t lbo = (COP / 8) * 128, sbo = 128;
+#pragma unroll
+      for (int kb = 0; kb < CIP / 8; ++kb) {
+        const uint32_t offs = kb * 2 * lbo;
+        const uint64_t d1h = tc::make_smem_desc(tc::smem_u32(wimg[0]) + offs, lbo, sbo);
+        const uint64_t d1l = tc::make_smem_desc(tc::smem_u32(wimg[1]) + offs, lbo, sbo);
+        const uint64_t d2h = tc::make_smem_desc(tc::smem_u32(wimg[2]) + offs, lbo, sbo);
+        const uint64_t d2l = tc::make_smem_desc(tc::smem_u32(wimg[3]) + offs, lbo, sbo);
+        tc::mma_tf32_ts(tbase + kColD, tbase + kb * 8, d1h, idesc, kb > 0 ? 1u : 0u);
+        tc::mma_tf32_ts(tbase + kColD, tbase + CIP + kb * 8, d1h, idesc, 1u);
+        tc::mma_tf32_ts(tbase + kColD, tbase + kb * 8, d1l, idesc, 1u);
+        tc::mma_tf32_ts(tbase + kColD + COP, tbase + 2 * CIP + kb * 8, d2h, idesc, kb > 0 ? 1u : 0u);
+        tc::mma_tf32_ts(tbase + kColD + COP, tbase + 3 * CIP + kb * 8, d2h, idesc, 1u);
+        tc::mma_tf32_ts(tbase + kColD + COP, tbase + 2 * CIP + kb * 8, d2l, idesc, 1u);
+      }
+      tc::mma_commit(&bar);
+    }
+    const int64_t e = t * kTcT + tid;
+    const bool ok = e < E;
+    const int64_t b = ok ? e / kP : 0;
+    const int64_t obase = (b * CO) * kP + (ok ? e - b * kP : 0);
+    load_tile(t + gridDim.x);                       // the next tile's loads fly while the tensor pipe and the epilogue run
+    tc::mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      uint32_t v[16];
+      tc::tmem_ld16(lane_base + kColD + q * 16, v);
+      tc::wait_ld();
+      float* out = (q * 16 < COP) ? y1 : y2;
+      const int co0 = (q * 16) % COP;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float val = __uint_as_float(v[j]) + bias_s[q * 16 + j];
+        if (ok && co0 + j < CO) out[obase + static_cast<int64_t>(co0 + j) * kP] = val;
+        tr[warp][lane][j] = ok ? val : 0.f;
+      }
+      __syncwarp();
+      float s = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) { const float a = tr[warp][r][lane & 15]; s += (lane < 16) ? a : a * a; }
+      sacc[q] += s;
+      __syncwarp();
+    }
+  }
+  {
+    float* dst = part + (static_cast<int64_t>(blockIdx.x) * 4 + warp) * (4 * CO);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int c = q * 16 + (lane & 15), branch = c / COP, co = c % COP;
+      if (co < CO) dst[(2 * branch + (lane >= 16 ? 1 : 0)) * CO + co] = sacc[q];
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, kAlloc);
+}
+
+// ---- backward data with the BatchNorm-train + PReLU backward fused in -----------------------------------------------------
+// dy1 = g1*is1*(ds - mean(ds) - yhat1*mean(ds*yhat1)), ds = dout * PReLU'(BN1(y1) + BN2(y2)); dy2 likewise
+// (train_bn_prelu_bwd_apply_kernel's expressions, bit for bit); dG = W1^T dy1, dXres = W2^T dy2.
+// NP = max(16, c_in) output columns per branch; the K = COK = max(16, c_out) channels go through TMEM in chunks of KC <= 32.
+template <int CO, int COK, int NP>
+__global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
+    const float* __restrict__ dout, const float* __restrict__ y1, const float* __restrict__ y2, const float* __restrict__ mi,
+    const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ g2, const float* __restrict__ be2,
+    const float* __restrict__ slope, const double* __restrict__ red, const float* __restrict__ W1, const float* __restrict__ W2,
+    int64_t E, int CI, float* __restrict__ dy1, float* __restrict__ dy2, float* __restrict__ dG, float* __restrict__ dXres) {
+  constexpr int KC = COK < 32 ? COK : 32;
+  constexpr int NCH = COK / KC;
+  constexpr int kColD = 4 * KC;                                   // A: dy1_hi, dy1_lo, dy2_hi, dy2_lo; D: dG | dXres
+  constexpr int kAlloc = tmem_alloc_cols(4 * KC + 2 * NP);
+  __shared__ __align__(128) float wimg[4][NP * COK];              // (W1^T) hi, lo, (W2^T) hi, lo: [N = ci][K = co]
+  __shared__ float cst[13][COK];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < NP * COK; i += kTcT) {
+    const int n = i / COK, k = i - n * COK;                       // n = ci, k = co
+    const bool in = n < CI && k < CO;
+    uint32_t h, l;
+    tc::split_tf32(in ? W1[k * CI + n] : 0.f, h, l);
+    wimg[0][kmaj_idx(n, k, NP)] = __uint_as_float(h); wimg[1][kmaj_idx(n, k, NP)] = __uint_as_float(l);
+    tc::split_tf32(in ? W2[k * CI + n] : 0.f, h, l);
+    wimg[2][kmaj_idx(n, k, NP)] = __uint_as_float(h); wimg[3][kmaj_idx(n, k, NP)] = __uint_as_float(l);
+  }
+  const double Nd = static_cast<double>(E);
+  for (int co = tid; co < COK; co += kTcT) {
+    if (co >= CO) {
+#pragma unroll
+      for (int q = 0; q < 13; ++q) cst[q][co] = 0.f;
+      continue;
+    }
+    const float i1 = mi[CO + co], i2 = mi[3 * CO + co], ga1 = g1[co], ga2 = g2[co];
+    cst[0][co] = mi[co]; cst[1][co] = i1; cst[2][co] = mi[2 * CO + co]; cst[3][co] = i2;
+    cst[4][co] = ga1; cst[5][co] = be1[co]; cst[6][co] = ga2; cst[7][co] = be2[co];
+    cst[8][co] = static_cast<float>(red[co] / Nd);
+    cst[9][co] = static_cast<float>(red[CO + co] / Nd);
+    cst[10][co] = static_cast<float>(red[2 * CO + co] / Nd);
+    cst[11][co] = ga1 * i1; cst[12][co] = ga2 * i2;
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, kAlloc);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_base = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+  const float a = slope[0];
+  const int64_t ntiles = (E + kTcT - 1) / kTcT;
+  uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t e = t * kTcT + tid;
+    const bool ok = e < E;
+    const int64_t b = ok ? e / kP : 0;
+    const int p = ok ? static_cast<int>(e - b * kP) : 0;
+    const int64_t ybase = (b * CO) * kP + p;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (ch > 0) {                                               // the previous chunk's MMAs still read the A columns
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < KC; c0 += 16) {
+        float dv[16], uv[16], vv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int64_t o = ybase + static_cast<int64_t>(ch * KC + c0 + j) * kP;
+          const bool in = ok && ch * KC + c0 + j < CO;
+          dv[j] = in ? __ldg(dout + o) : 0.f;
+          uv[j] = in ? __ldg(y1 + o) : 0.f;
+          vv[j] = in ? __ldg(y2 + o) : 0.f;
+        }
+        uint32_t h1[16], l1[16], h2[16], l2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = ch * KC + c0 + j;
+          float hh1, hh2;
+          const float pre = bn_pre(uv[j], vv[j], cst[0][co], cst[1][co], cst[2][co], cst[3][co], cst[4][co], cst[5][co],
+                                   cst[6][co], cst[7][co], hh1, hh2);
+          const float ds = pre > 0.f ? dv[j] : a * dv[j];
+          const bool in = ok && co < CO;
+          const float r1 = in ? cst[11][co] * (ds - cst[8][co] - hh1 * cst[9][co]) : 0.f;
+          const float r2 = in ? cst[12][co] * (ds - cst[8][co] - hh2 * cst[10][co]) : 0.f;
+          if (in) {
+            const int64_t o = ybase + static_cast<int64_t>(co) * kP;
+            dy1[o] = r1;
+            dy2[o] = r2;
+          }
+          tc::split_tf32(r1, h1[j], l1[j]);
+          tc::split_tf32(r2, h2[j], l2[j]);
+        }
+        tc::tmem_st16(lane_base + c0, h1);
+        tc::tmem_st16(lane_base + KC + c0, l1);
+        tc::tmem_st16(lane_base + 2 * KC + c0, h2);
+        tc::tmem_st16(lane_base + 3 * KC + c0, l2);
+      }
+      tc::wait_st();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::make_idesc_tf32(128, NP);
+        const uint32_t lbo = (NP / 8) * 128, sbo = 128;
+#pragma unroll
+        for (int kb = 0; kb < KC / 8; ++kb) {
+          const uint32_t offs = (ch * (KC / 8) + kb) * 2 * lbo;
+          const uint64_t d1h = tc::make_smem_desc(tc::smem_u32(wimg[0]) + offs, lbo, sbo);
+          const uint64_t d1l = tc::make_smem_desc(tc::smem_u32(wimg[1]) + offs, lbo, sbo);
+          const uint64_t d2h = tc::make_smem_desc(tc::smem_u32(wimg[2]) + offs, lbo, sbo);
+          const uint64_t d2l = tc::make_smem_desc(tc::smem_u32(wimg[3]) + offs, lbo, sbo);
+          const uint32_t acc = (ch > 0 || kb > 0) ? 1u : 0u;
+          tc::mma_tf32_ts(tbase + kColD, tbase + kb * 8, d1h, idesc, acc);
+          tc::mma_tf32_ts(tbase + kColD, tbase + KC + kb * 8, d1h, idesc, 1u);
+          tc::mma_tf32_ts(tbase + kColD, tbase + kb * 8, d1l, idesc, 1u);
+          tc::mma_tf32_ts(tbase + kColD + NP, tbase + 2 * KC + kb * 8, d2h, idesc, acc);
+          tc::mma_tf32_ts(tbase + kColD + NP, tbase + 3 * KC + kb * 8, d2h, idesc, 1u);
+          tc::mma_tf32_ts(tbase + kColD + NP, tbase + 2 * KC + kb * 8, d2l, idesc, 1u);
+        }
+        tc::mma_commit(&bar);
+      }
+    }
+    tc::mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+    const int64_t xbase = (b * CI) * kP + p;
+#pragma unroll
+    for (int q = 0; q < 2 * NP / 16; ++q) {
+      uint32_t v[16];
+      tc::tmem_ld16(lane_base + kColD + q * 16, v);
+      tc::wait_ld();
+      float* out = (q * 16 < NP) ? dG : dXres;
+      const int ci0 = (q * 16) % NP;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (ok && ci0 + j < CI) out[xbase + static_cast<int64_t>(ci0 + j) * kP] = __uint_as_float(v[j]);
+    }
+    // the next tile's tcgen05.st must not overtake this tile's tcgen05.ld of other warps' MMAs: ordered by the barrier of the
+    // next chunk (every thread finishes its epilogue before it arrives there)
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, kAlloc);
+}
+
+// ---- weight gradient: dW1 = dy1^T G, db1 = dy1^T 1, dW2 = dy2^T X, db2 = dy2^T 1, split-K over the grid ----------------------
+// part [gridDim.x][2][CO][CI + 1] (column CI = bias gradient).  KT = 32 positions per tile; images are padded canonical
+// K-major: element (r, k) at (r/8)*kWgSbo + (k/4)*kWgLbo + (r%8)*4 + (k%4) floats.
+constexpr int kWgKT = 32;
+constexpr int kWgLbo = 36;                      // floats (144 B): the 8 lanes of an STS.128 wavefront hit 32 distinct banks
+constexpr int kWgSbo = (kWgKT / 4) * kWgLbo;    // floats per 8-row group (1152 B)
+__host__ __device__ constexpr int wg_n(int ci8) { return ci8 + 8; }
+__host__ __device__ constexpr int wg_smem_floats(int ci8) { return 4 * 8 * kWgSbo + 4 * (wg_n(ci8) / 8) * kWgSbo; }
+
+template <int CO, int CI8>
+__global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
+                                                                const float* __restrict__ G, const float* __restrict__ X,
+                                                                int64_t E, int CI, float* __restrict__ part) {
+  constexpr int N = wg_n(CI8);
+  constexpr int kAimg = 8 * kWgSbo;                               // M = 64 rows
+  constexpr int kBimg = (N / 8) * kWgSbo;
+  constexpr int kAlloc = tmem_alloc_cols(2 * N);
+  constexpr int kItemsMax = ((2 * CO + 2 * CI8) * (kWgKT / 4) + kTcT - 1) / kTcT;   // float4 per thread and tile
+  extern __shared__ __align__(128) float wsm[];
+  float* Aimg = wsm;                                              // dy1 hi, dy1 lo, dy2 hi, dy2 lo
+  float* Bimg = wsm + 4 * kAimg;                                  // G hi, G lo, X hi, X lo (+ the row of ones at row CI8 of the hi images)
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 4 * kBimg; i += kTcT) Bimg[i] = 0.f;
+  for (int i = tid; i < 4 * kAimg; i += kTcT) Aimg[i] = 0.f;
+  __syncthreads();
+  if (tid < kWgKT) {                                              // ones: row CI8 (first row of the last group), every k
+    const int o = (CI8 / 8) * kWgSbo + (tid >> 2) * kWgLbo + (tid & 3);
+    Bimg[0 * kBimg + o] = 1.f;
+    Bimg[2 * kBimg + o] = 1.f;
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, kAlloc);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const int rows = 2 * CO + 2 * CI;
+  const int items = rows * (kWgKT / 4);
+  const int64_t ntiles = (E + kWgKT - 1) / kWgKT;
+  uint32_t phase = 0;
+  bool first = true;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t e0 = t * kWgKT;
+    const int64_t b0 = e0 / kP;
+    const int p0 = static_cast<int>(e0 - b0 * kP);
+    float4 v[kItemsMax];
+#pragma unroll
+    for (int u = 0; u < kItemsMax; ++u) {
+      const int it = tid + u * kTcT;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (it < items) {
+        const int r = it >> 3, kc = it & 7;
+        int p = p0 + 4 * kc;
+        int64_t b = b0;
+        if (p >= kP) { p -= kP; b += 1; }
+        if (e0 + 4 * kc < E) {                                    // E % 4 == 0: a float4 is entirely in or out
+          const float* src;
+          int C, c;
+          if (r < CO) { src = dy1; C = CO; c = r; }
+          else if (r < 2 * CO) { src = dy2; C = CO; c = r - CO; }
+          else if (r < 2 * CO + CI) { src = G; C = CI; c = r - 2 * CO; }
+          else { src = X; C = CI; c = r - 2 * CO - CI; }
+          v[u] = __ldg(reinterpret_cast<const float4*>(src + (b * C + c) * kP + p));
+        }
+      }
+    }
+    if (!first) {                                                 // the previous tile's MMAs still read the images
+      tc::mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+#pragma unroll
+    for (int u = 0; u < kItemsMax; ++u) {
+      const int it = tid + u * kTcT;
+      if (it < items) {
+        const int r = it >> 3, kc = it & 7;
+        float* hi_img;
+        int rr;
+        if (r < CO) { hi_img = Aimg; rr = r; }
+        else if (r < 2 * CO) { hi_img = Aimg + 2 * kAimg; rr = r - CO; }
+        else if (r < 2 * CO + CI) { hi_img = Bimg; rr = r - 2 * CO; }
+        else { hi_img = Bimg + 2 * kBimg; rr = r - 2 * CO - CI; }
+        const int img = (r < 2 * CO) ? kAimg : kBimg;
+        const int o = (rr >> 3) * kWgSbo + kc * kWgLbo + (rr & 7) * 4;
+        uint32_t h[4], l[4];
+        tc::split_tf32(v[u].x, h[0], l[0]); tc::split_tf32(v[u].y, h[1], l[1]);
+        tc::split_tf32(v[u].z, h[2], l[2]); tc::split_tf32(v[u].w, h[3], l[3]);
+        *reinterpret_cast<uint4*>(hi_img + o) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(hi_img + img + o) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+    tc::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::make_idesc_tf32(64, N);
+      const uint32_t lbo = kWgLbo * 4, sbo = kWgSbo * 4;
+      const uint32_t a0 = tc::smem_u32(Aimg), bb = tc::smem_u32(Bimg);
+#pragma unroll
+      for (int ks = 0; ks < kWgKT / 8; ++ks) {
+        const uint32_t offs = ks * 2 * lbo;
+        const uint32_t acc = (!first || ks > 0) ? 1u : 0u;
+        const uint64_t a1h = tc::make_smem_desc(a0 + offs, lbo, sbo), a1l = tc::make_smem_desc(a0 + kAimg * 4 + offs, lbo, sbo);
+        const uint64_t a2h = tc::make_smem_desc(a0 + 2 * kAimg * 4 + offs, lbo, sbo), a2l = tc::make_smem_desc(a0 + 3 * kAimg * 4 + offs, lbo, sbo);
+        const uint64_t b1h = tc::make_smem_desc(bb + offs, lbo, sbo), b1l = tc::make_smem_desc(bb + kBimg * 4 + offs, lbo, sbo);
+        const uint64_t b2h = tc::make_smem_desc(bb + 2 * kBimg * 4 + offs, lbo, sbo), b2l = tc::make_smem_desc(bb + 3 * kBimg * 4 + offs, lbo, sbo);
+        tc::mma_tf32_ss(tbase, a1h, b1h, idesc, acc);
+        tc::mma_tf32_ss(tbase, a1l, b1h, idesc, 1u);
+        tc::mma_tf32_ss(tbase, a1h, b1l, idesc, 1u);
+        tc::mma_tf32_ss(tbase + N, a2h, b2h, idesc, acc);
+        tc::mma_tf32_ss(tbase + N, a2l, b2h, idesc, 1u);
+        tc::mma_tf32_ss(tbase + N, a2h, b2l, idesc, 1u);
+      }
+      tc::mma_commit(&bar);
+    }
+    first = false;
+  }
+  // every CTA owns at least one tile (grid <= ntiles): wait for the last commit, then write the partial block
+  tc::mbar_wait(&bar, phase);
+  tc::fence_after_sync();
+  {
+    // M = 64 accumulator layout: row m lives in TMEM lane (m % 16) + 32 * (m / 16): warp w holds rows 16 w .. 16 w + 15 in its
+    // lanes 0..15
+    const uint32_t lane_base = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+    const int row = 16 * warp + lane;
+    float* dst = part + static_cast<int64_t>(blockIdx.x) * 2 * CO * (CI + 1);
+#pragma unroll
+    for (int q = 0; q < (2 * N + 15) / 16; ++q) {
+      uint32_t v[16];
+      tc::tmem_ld16(lane_base + q * 16, v);
+      tc::wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = q * 16 + j;
+        if (c < 2 * N && lane < 16 && row < CO) {
+          const int branch = c / N, n = c % N;
+          if (n < CI) dst[(branch * CO + row) * (CI + 1) + n] = __uint_as_float(v[j]);
+          else if (n == CI8) dst[(branch * CO + row) * (CI + 1) + CI] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, kAlloc);
+}
+
+// second stage: dW[co,ci] += sum_blocks part, db[co] += ...; one thread per (branch, co, n), fixed order, double accumulator
+__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int nblk, int CO, int CI, float* dW1, float* db1,
+                                       float* dW2, float* db2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = CO * (CI + 1);
+  if (i >= 2 * per) return;
+  double s = 0.0;
+  for (int j = 0; j < nblk; ++j) s += static_cast<double>(part[static_cast<int64_t>(j) * 2 * per + i]);
+  const int branch = i / per, r = i % per, co = r / (CI + 1), n = r % (CI + 1);
+  if (n < CI) { float* dW = branch ? dW2 : dW1; dW[co * CI + n] += static_cast<float>(s); }
+  else { float* db = branch ? db2 : db1; if (db) db[co] += static_cast<float>(s); }
+}
+
+}  // namespace coskad

@@ -17,10 +17,24 @@ import torch
 from . import _lib
 
 P = 12 * 17
+#: 1: the 1x1 convolutions (forward, backward data, weight gradient) run on the tensor cores (tcgen05, 3xTF32) with the
+#: BatchNorm / PReLU backward fused into the backward kernels; 0: the FP32 CUDA-core kernels (A/B measurement)
+TRAIN_IMPL = 1
+
+
+def set_train_impl(impl: int) -> None:
+    global TRAIN_IMPL
+    if impl not in (0, 1):
+        raise ValueError('train impl must be 0 (FP32 CUDA cores) or 1 (tcgen05)')
+    TRAIN_IMPL = int(impl)
 
 
 def _ctx(t: torch.Tensor) -> _lib.Context:
-    return _lib.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    c = _lib.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    if getattr(c, 'train_impl', 1) != TRAIN_IMPL:
+        c.check(c.lib.coskad_set_train_impl(c.h, TRAIN_IMPL), 'coskad_set_train_impl')
+        c.train_impl = TRAIN_IMPL
+    return c
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -90,16 +104,24 @@ class _LayerFn(torch.autograd.Function):
         red = seg[0].view(torch.float64)
         dy1 = torch.empty_like(y1)
         dy2 = torch.empty_like(y2)
-        c.check(lib.coskad_train_bn_prelu_bwd(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
-                                              g1.data_ptr(), be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(),
-                                              B, CO, red.data_ptr(), dy1.data_ptr(), dy2.data_ptr(), st),
-                'coskad_train_bn_prelu_bwd')
         dG = torch.empty_like(X)
         dXres = torch.empty_like(X)
         dW1, dW2, db1, db2 = seg[1].view_as(W1), seg[2].view_as(W2), seg[3], seg[4]
-        c.check(lib.coskad_train_mix_bwd(c.h, dy1.data_ptr(), dy2.data_ptr(), G.data_ptr(), X.data_ptr(), W1.data_ptr(),
-                                         W2.data_ptr(), B, CI, CO, dG.data_ptr(), dXres.data_ptr(), dW1.data_ptr(),
-                                         db1.data_ptr(), dW2.data_ptr(), db2.data_ptr(), st), 'coskad_train_mix_bwd')
+        tc = getattr(c, 'train_impl', 1) == 1
+        c.check(lib.coskad_train_bn_prelu_bwd(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
+                                              g1.data_ptr(), be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(),
+                                              B, CO, red.data_ptr(), None if tc else dy1.data_ptr(),
+                                              None if tc else dy2.data_ptr(), st), 'coskad_train_bn_prelu_bwd')
+        if tc:      # BatchNorm / PReLU backward applied inside the tensor-core data-gradient kernel
+            c.check(lib.coskad_train_mix_bwd_tc(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(), g1.data_ptr(),
+                                                be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(), red.data_ptr(),
+                                                G.data_ptr(), X.data_ptr(), W1.data_ptr(), W2.data_ptr(), B, CI, CO,
+                                                dy1.data_ptr(), dy2.data_ptr(), dG.data_ptr(), dXres.data_ptr(), dW1.data_ptr(),
+                                                db1.data_ptr(), dW2.data_ptr(), db2.data_ptr(), st), 'coskad_train_mix_bwd_tc')
+        else:
+            c.check(lib.coskad_train_mix_bwd(c.h, dy1.data_ptr(), dy2.data_ptr(), G.data_ptr(), X.data_ptr(), W1.data_ptr(),
+                                             W2.data_ptr(), B, CI, CO, dG.data_ptr(), dXres.data_ptr(), dW1.data_ptr(),
+                                             db1.data_ptr(), dW2.data_ptr(), db2.data_ptr(), st), 'coskad_train_mix_bwd')
         dX = torch.empty_like(X)
         dA, dT = seg[5].view_as(A), seg[6].view_as(T)
         c.check(lib.coskad_train_contract_bwd(c.h, dG.data_ptr(), dXres.data_ptr(), X.data_ptr(), G1.data_ptr(),

@@ -218,7 +218,10 @@ class Trainer:
         use_graph = self.cuda_graph and bool(getattr(model, 'graph_safe', False))
         if self.cuda_graph and not use_graph and self.verbose and cdist.rank() == 0:
             print(f'cuda_graph: {type(model).__name__} is not graph_safe, training eagerly')
-        if use_graph:
+        # always the capturable optimizer form (step counters and learning rate on the device): the eager and the replayed
+        # step then run the very same kernels, and with the fixed-order reductions of the training path their loss
+        # trajectories are bit-identical
+        if self.device.type == 'cuda':
             _make_capturable(opt, self.device)
         step = TrainStep(model, opt, bucket, self.device)
         self.train_step = step

@@ -225,7 +225,7 @@ int coskad_train_bn_prelu_fwd(coskad_ctx* ctx, const float* y1, const float* y2,
                               const float* be1, const float* g2, const float* be2, const float* slope, int64_t B, int CO,
                               float* out, void* stream);
 /* red (double)[3*CO+1] += sum ds, sum ds*yhat1, sum ds*yhat2 per channel (= d beta, d gamma1, d gamma2) and d slope;
- * dy1, dy2 = gradients w.r.t. the conv outputs */
+ * dy1, dy2 = gradients w.r.t. the conv outputs (both NULL: only `red` is reduced) */
 int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2, const float* mi,
                               const float* g1, const float* be1, const float* g2, const float* be2, const float* slope,
                               int64_t B, int CO, double* red, float* dy1, float* dy2, void* stream);
@@ -233,6 +233,20 @@ int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, const float* y
 int coskad_train_mix_bwd(coskad_ctx* ctx, const float* dy1, const float* dy2, const float* G, const float* X,
                          const float* W1, const float* W2, int64_t B, int CI, int CO, float* dG, float* dXres,
                          float* dW1, float* db1, float* dW2, float* db2, void* stream);
+/* The same backward on the tensor cores (tcgen05, 3xTF32), with the BatchNorm-train + PReLU backward fused in: call
+ * coskad_train_bn_prelu_bwd with dy1 = dy2 = NULL first (it then only reduces `red`), then this.  dy1 / dy2 are scratch
+ * [B, CO, 204] (written once, read by the weight-gradient kernel); dW*, db* are accumulated into (zero them first).
+ * replaces: autograd of nn.Conv2d 1x1 + nn.BatchNorm2d(train) + nn.PReLU, models/graph_layers/stsgcn.py:56-82,106-110 */
+int coskad_train_mix_bwd_tc(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2, const float* mi,
+                            const float* g1, const float* be1, const float* g2, const float* be2, const float* slope,
+                            const double* red, const float* G, const float* X, const float* W1, const float* W2, int64_t B,
+                            int CI, int CO, float* dy1, float* dy2, float* dG, float* dXres, float* dW1, float* db1,
+                            float* dW2, float* db2, void* stream);
+/* 1 (default): coskad_train_mix_fwd runs on the tensor cores; 0: the FP32 CUDA-core kernels (A/B measurement).  Every
+ * cross-CTA reduction of the training path (BatchNorm statistics, weight / bias / graph-operator gradients, linear heads)
+ * is a fixed-order two-stage sum through a ctx-owned workspace: two runs on the same inputs are bit-identical.  The
+ * workspace is sized by the first (eager) call; do not make the FIRST training call of a ctx inside a stream capture. */
+int coskad_set_train_impl(coskad_ctx* ctx, int impl);
 /* linear layers over the F = C*204 flattened features (btlnk / fc_mean / fc_var / rev_btlnk, models/sts/ae.py:155,206):
  * mode 0: out[B,D] = A_wide[B,F] W^T + bias; mode 1: out[B,F] = a_small[B,D] W + bias[F]; mode 2: out(=dW) += a_small^T A_wide.
  * w_is_fd = 0: W is [D,F] (btlnk); 1: W is [F,D] (rev_btlnk).  D <= 16, F % 4 == 0 (rows are read with 16-byte loads:
