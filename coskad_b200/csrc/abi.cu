@@ -689,7 +689,8 @@ extern "C" int coskad_train_contract_fwd(coskad_ctx* ctx, const float* X, const 
 
 template <typename TOut>
 static int launch_partial_sum(coskad_ctx* ctx, const float* part, int nparts, int64_t stride, int64_t n, TOut* out, cudaStream_t st) {
-  partial_sum_kernel<TOut><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(part, nparts, stride, n, out);
+  if (nparts >= 32) partial_sum_wide_kernel<TOut><<<static_cast<unsigned>((n + 31) / 32), dim3(32, kPsRows), 0, st>>>(part, nparts, stride, n, out);
+  else partial_sum_kernel<TOut><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(part, nparts, stride, n, out);
   CK_LAUNCH();
   return COSKAD_OK;
 }
@@ -737,15 +738,28 @@ static int launch_chan_gemm(coskad_ctx* ctx, bool stats_on, const float* in1, co
   return COSKAD_OK;
 }
 
+// Dynamic shared memory requested only to make the block scheduler's CTAs-per-SM limit equal to what TMEM can hold: with
+// the kernels' small footprint it places up to 5-9 CTAs on an SM, the ones past the TMEM capacity block inside tcgen05.alloc
+// until a resident CTA exits, and other SMs sit idle meanwhile (measured: 2-3x the kernel time).
+template <typename K>
+static size_t tmem_pad_smem(K kernel, int per_sm) {
+  cudaFuncAttributes attr{};
+  if (cudaFuncGetAttributes(&attr, kernel) != cudaSuccess) return 0;
+  const size_t target = (static_cast<size_t>(228) * 1024) / static_cast<size_t>(per_sm) - 1536;   // 1 KB per CTA is reserved
+  return target > attr.sharedSizeBytes ? target - attr.sharedSizeBytes : 0;
+}
 // tcgen05 forward convolution: y1, y2 and the BatchNorm statistics (per-warp partials -> fixed-order second stage)
 template <int CIP, int CO, int COP>
 static int launch_tc_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1, const float* W2,
                              const float* b2, int64_t B, int CI, float* y1, float* y2, double* stats, cudaStream_t st) {
   const int64_t E = B * kP, ntiles = (E + kTcT - 1) / kTcT;
-  const int per_sm = 512 / tmem_alloc_cols(4 * CIP + 2 * COP);          // TMEM columns bound the resident CTAs
-  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * (per_sm > 4 ? 4 : per_sm);
+  int per_sm = 512 / tmem_alloc_cols(4 * CIP + 2 * COP);                // TMEM columns bound the resident CTAs
+  if (per_sm > 4) per_sm = 4;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
   const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
   { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(g) * 4 * 4 * CO); if (rc) return rc; }
+  // no shared-memory padding here (tmem_pad_smem): measured 15-35 % slower for this kernel -- the large carve-out shrinks L1,
+  // and the 128-byte row segments of neighbouring warps share cache lines (rows start at multiples of 816 B)
   tc_mix_fwd_kernel<CIP, CO, COP><<<g, kTcT, 0, st>>>(G, X, W1, b1, W2, b2, E, CI, y1, y2, ctx->ws);
   CK_LAUNCH();
   return launch_partial_sum<double>(ctx, ctx->ws, g * 4, 4 * CO, 4 * CO, stats, st);
@@ -815,11 +829,13 @@ static int launch_tc_bwd_data(coskad_ctx* ctx, const float* dout, const float* y
                               const double* red, const float* W1, const float* W2, int64_t B, int CI, float* dy1, float* dy2,
                               float* dG, float* dXres, cudaStream_t st) {
   const int64_t E = B * kP, ntiles = (E + kTcT - 1) / kTcT;
-  constexpr int KC = COK < 32 ? COK : 32;
-  const int per_sm = 512 / tmem_alloc_cols(4 * KC + 2 * NP);
-  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * (per_sm > 3 ? 3 : per_sm);
+  int per_sm = 512 / tmem_alloc_cols(4 * kBwdKC + 2 * NP);
+  if (per_sm > 4) per_sm = 4;
+  const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
   const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
-  tc_mix_bwd_data_kernel<CO, COK, NP><<<g, kTcT, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, E, CI, dy1, dy2,
+  const size_t pad = tmem_pad_smem(tc_mix_bwd_data_kernel<CO, COK, NP>, per_sm);
+  CK(cudaFuncSetAttribute(tc_mix_bwd_data_kernel<CO, COK, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pad)));
+  tc_mix_bwd_data_kernel<CO, COK, NP><<<g, kTcT, pad, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, E, CI, dy1, dy2,
                                                         dG, dXres);
   CK_LAUNCH();
   return COSKAD_OK;
@@ -841,7 +857,7 @@ static int launch_tc_bwd_weight(coskad_ctx* ctx, const float* dy1, const float* 
   CK(cudaFuncSetAttribute(tc_mix_bwd_weight_kernel<CO, CI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   tc_mix_bwd_weight_kernel<CO, CI8><<<g, kTcT, smem, st>>>(dy1, dy2, G, X, E, CI, ctx->ws);
   CK_LAUNCH();
-  tc_wgrad_reduce_kernel<<<static_cast<unsigned>((per + 255) / 256), 256, 0, st>>>(ctx->ws, g, CO, CI, dW1, db1, dW2, db2);
+  tc_wgrad_reduce_kernel<<<static_cast<unsigned>((per + 31) / 32), dim3(32, kPsRows), 0, st>>>(ctx->ws, g, CO, CI, dW1, db1, dW2, db2);
   CK_LAUNCH();
   return COSKAD_OK;
 }

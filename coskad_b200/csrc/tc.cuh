@@ -107,6 +107,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 
+// Global loads that STAY where they are written: the compiler sinks plain (predicated) loads next to their first use, which
+// serialises one HBM latency per value; a batch of volatile loads is issued back to back and waited for once.
+__device__ __forceinline__ float ldg_stay(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stay4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(a) & 0xFFFFE000u;
   lo = __float_as_uint(a - __uint_as_float(hi)) & 0xFFFFE000u;

@@ -34,7 +34,9 @@ __host__ __device__ constexpr int tmem_alloc_cols(int need) {
 // canonical K-major, no swizzle: element (n, k) of an [N][K] operand; LBO = (N/8)*128 B, SBO = 128 B (fold.cuh, tc_test.cuh)
 __device__ __forceinline__ int kmaj_idx(int n, int k, int N) { return ((k >> 2) * (N >> 3) + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3); }
 
-// out[i] += sum_j part[j*stride + i] in a FIXED order (double accumulator): the second stage of every cross-CTA reduction
+// out[i] += sum_j part[j*stride + i] in a FIXED order (double accumulator): the second stage of every cross-CTA reduction.
+// Few partials: one thread per element.  Many partials (hundreds of CTAs): a 32 x 8 block owns 32 consecutive elements,
+// row y sums the partials y, y + 8, .. (coalesced across x), the 8 rows meet in shared memory in a fixed order.
 template <typename TOut>
 __global__ void partial_sum_kernel(const float* __restrict__ part, int nparts, int64_t stride, int64_t n, TOut* out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -42,6 +44,26 @@ __global__ void partial_sum_kernel(const float* __restrict__ part, int nparts, i
   double s = 0.0;
   for (int j = 0; j < nparts; ++j) s += static_cast<double>(part[static_cast<int64_t>(j) * stride + i]);
   out[i] += static_cast<TOut>(s);
+}
+constexpr int kPsRows = 8;
+__device__ __forceinline__ double partial_sum_block(const float* __restrict__ part, int nparts, int64_t stride, int64_t i, bool ok,
+                                                    double (*sh)[33]) {
+  double s = 0.0;
+  if (ok) for (int j = threadIdx.y; j < nparts; j += kPsRows) s += static_cast<double>(part[static_cast<int64_t>(j) * stride + i]);
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.y == 0)
+#pragma unroll
+    for (int y = 0; y < kPsRows; ++y) t += sh[y][threadIdx.x];
+  return t;
+}
+template <typename TOut>
+__global__ void partial_sum_wide_kernel(const float* __restrict__ part, int nparts, int64_t stride, int64_t n, TOut* out) {
+  __shared__ double sh[kPsRows][33];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
+  const double t = partial_sum_block(part, nparts, stride, i, i < n, sh);
+  if (threadIdx.y == 0 && i < n) out[i] += static_cast<TOut>(t);
 }
 
 // ---- forward: y1 = conv1x1(G; W1, b1), y2 = conv1x1(X; W2, b2) + per-CTA BatchNorm statistics ---------------------------
@@ -90,14 +112,20 @@ __global__ void __launch_bounds__(kTcT) tc_mix_fwd_kernel(const float* __restric
   for (int q = 0; q < NQ; ++q) sacc[q] = 0.f;
   float g[CIP], x[CIP];
   auto load_tile = [&](int64_t t) {
+    // out-of-range threads / tiles read a valid address (element 0 of their channel row) and are masked afterwards, so that
+    // the whole batch is unconditional loads in flight together
     const int64_t e = t * kTcT + tid;
     const bool ok = t < ntiles && e < E;
     const int64_t b = ok ? e / kP : 0;
     const int64_t base = (b * CI) * kP + (ok ? e - b * kP : 0);
 #pragma unroll
     for (int c = 0; c < CIP; ++c) {
-      g[c] = (ok && c < CI) ? __ldg(G + base + static_cast<int64_t>(c) * kP) : 0.f;
-      x[c] = (ok && c < CI) ? __ldg(X + base + static_cast<int64_t>(c) * kP) : 0.f;
+      if (c < CI) { g[c] = tc::ldg_stay(G + base + static_cast<int64_t>(c) * kP); x[c] = tc::ldg_stay(X + base + static_cast<int64_t>(c) * kP); }
+      else { g[c] = 0.f; x[c] = 0.f; }
+    }
+    if (!ok) {
+#pragma unroll
+      for (int c = 0; c < CIP; ++c) { g[c] = 0.f; x[c] = 0.f; }
     }
   };
   uint32_t phase = 0;
@@ -184,14 +212,16 @@ __global__ void __launch_bounds__(kTcT) tc_mix_fwd_kernel(const float* __restric
 // ---- backward data with the BatchNorm-train + PReLU backward fused in -----------------------------------------------------
 // dy1 = g1*is1*(ds - mean(ds) - yhat1*mean(ds*yhat1)), ds = dout * PReLU'(BN1(y1) + BN2(y2)); dy2 likewise
 // (train_bn_prelu_bwd_apply_kernel's expressions, bit for bit); dG = W1^T dy1, dXres = W2^T dy2.
-// NP = max(16, c_in) output columns per branch; the K = COK = max(16, c_out) channels go through TMEM in chunks of KC <= 32.
+// NP = max(16, c_in) output columns per branch; the K = COK = max(16, c_out) channels go through TMEM in chunks of KC = 16
+// (few TMEM columns per CTA: the resident CTAs, not a deeper pipeline inside one, hide the HBM latency).
+constexpr int kBwdKC = 16;
 template <int CO, int COK, int NP>
 __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
     const float* __restrict__ dout, const float* __restrict__ y1, const float* __restrict__ y2, const float* __restrict__ mi,
     const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ g2, const float* __restrict__ be2,
     const float* __restrict__ slope, const double* __restrict__ red, const float* __restrict__ W1, const float* __restrict__ W2,
     int64_t E, int CI, float* __restrict__ dy1, float* __restrict__ dy2, float* __restrict__ dG, float* __restrict__ dXres) {
-  constexpr int KC = COK < 32 ? COK : 32;
+  constexpr int KC = kBwdKC;                                      // 16 channels per pass: 64 + 2 NP columns -> 4 CTAs per SM
   constexpr int NCH = COK / KC;
   constexpr int kColD = 4 * KC;                                   // A: dy1_hi, dy1_lo, dy2_hi, dy2_lo; D: dG | dXres
   constexpr int kAlloc = tmem_alloc_cols(4 * KC + 2 * NP);
@@ -235,6 +265,26 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
   const float a = slope[0];
   const int64_t ntiles = (E + kTcT - 1) / kTcT;
   uint32_t phase = 0;
+  static_assert(KC == 16, "one 16-channel group per pass");
+  // the (dout, y1, y2) values of a 16-channel pass: 48 unconditional loads in flight together (an out-of-range thread reads
+  // row 0 and is masked later).  Loading one pass AHEAD was measured slower: +70 registers cost a resident CTA per SM, and
+  // it is the resident CTAs (4 per SM) that hide the HBM latency here
+  float nd[16], nu[16], nv[16];
+  auto issue = [&](int64_t t, int ch) {
+    const int64_t e = t * kTcT + tid;
+    const bool ok = t < ntiles && e < E;
+    const int64_t b = ok ? e / kP : 0;
+    const int64_t ybase = (b * CO) * kP + (ok ? e - b * kP : 0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (ch * KC + j < CO) {
+        const int64_t o = ybase + static_cast<int64_t>(ch * KC + j) * kP;
+        nd[j] = tc::ldg_stay(dout + o);
+        nu[j] = tc::ldg_stay(y1 + o);
+        nv[j] = tc::ldg_stay(y2 + o);
+      } else { nd[j] = 0.f; nu[j] = 0.f; nv[j] = 0.f; }
+    }
+  };
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t e = t * kTcT + tid;
     const bool ok = e < E;
@@ -243,46 +293,38 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
     const int64_t ybase = (b * CO) * kP + p;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
-      if (ch > 0) {                                               // the previous chunk's MMAs still read the A columns
+      float dv[16], uv[16], vv[16];
+      issue(t, ch);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { dv[j] = nd[j]; uv[j] = nu[j]; vv[j] = nv[j]; }
+      uint32_t h1[16], l1[16], h2[16], l2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = ch * KC + j;
+        float hh1, hh2;
+        const float pre = bn_pre(uv[j], vv[j], cst[0][co], cst[1][co], cst[2][co], cst[3][co], cst[4][co], cst[5][co],
+                                 cst[6][co], cst[7][co], hh1, hh2);
+        const float ds = pre > 0.f ? dv[j] : a * dv[j];
+        const bool in = ok && co < CO;
+        const float r1 = in ? cst[11][co] * (ds - cst[8][co] - hh1 * cst[9][co]) : 0.f;
+        const float r2 = in ? cst[12][co] * (ds - cst[8][co] - hh2 * cst[10][co]) : 0.f;
+        if (in) {
+          const int64_t o = ybase + static_cast<int64_t>(co) * kP;
+          dy1[o] = r1;
+          dy2[o] = r2;
+        }
+        tc::split_tf32(r1, h1[j], l1[j]);
+        tc::split_tf32(r2, h2[j], l2[j]);
+      }
+      if (ch > 0) {                                               // the previous pass's MMAs still read the A columns
         tc::mbar_wait(&bar, phase);
         phase ^= 1;
         tc::fence_after_sync();
       }
-#pragma unroll
-      for (int c0 = 0; c0 < KC; c0 += 16) {
-        float dv[16], uv[16], vv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int64_t o = ybase + static_cast<int64_t>(ch * KC + c0 + j) * kP;
-          const bool in = ok && ch * KC + c0 + j < CO;
-          dv[j] = in ? __ldg(dout + o) : 0.f;
-          uv[j] = in ? __ldg(y1 + o) : 0.f;
-          vv[j] = in ? __ldg(y2 + o) : 0.f;
-        }
-        uint32_t h1[16], l1[16], h2[16], l2[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = ch * KC + c0 + j;
-          float hh1, hh2;
-          const float pre = bn_pre(uv[j], vv[j], cst[0][co], cst[1][co], cst[2][co], cst[3][co], cst[4][co], cst[5][co],
-                                   cst[6][co], cst[7][co], hh1, hh2);
-          const float ds = pre > 0.f ? dv[j] : a * dv[j];
-          const bool in = ok && co < CO;
-          const float r1 = in ? cst[11][co] * (ds - cst[8][co] - hh1 * cst[9][co]) : 0.f;
-          const float r2 = in ? cst[12][co] * (ds - cst[8][co] - hh2 * cst[10][co]) : 0.f;
-          if (in) {
-            const int64_t o = ybase + static_cast<int64_t>(co) * kP;
-            dy1[o] = r1;
-            dy2[o] = r2;
-          }
-          tc::split_tf32(r1, h1[j], l1[j]);
-          tc::split_tf32(r2, h2[j], l2[j]);
-        }
-        tc::tmem_st16(lane_base + c0, h1);
-        tc::tmem_st16(lane_base + KC + c0, l1);
-        tc::tmem_st16(lane_base + 2 * KC + c0, h2);
-        tc::tmem_st16(lane_base + 3 * KC + c0, l2);
-      }
+      tc::tmem_st16(lane_base, h1);
+      tc::tmem_st16(lane_base + KC, l1);
+      tc::tmem_st16(lane_base + 2 * KC, h2);
+      tc::tmem_st16(lane_base + 3 * KC, l2);
       tc::wait_st();
       tc::fence_before_sync();
       __syncthreads();
@@ -375,30 +417,40 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
   const int64_t ntiles = (E + kWgKT - 1) / kWgKT;
   uint32_t phase = 0;
   bool first = true;
+  // the 16-byte loads of a tile: unconditional, all in flight together while the previous tile's MMAs run; an item past the
+  // end of the batch (E % 4 == 0: entirely in or out) or past the row list reads a valid address and is zeroed when consumed
+  float4 vn[kItemsMax];
+  auto issue = [&](int64_t t) {
+    const int64_t e0 = t * kWgKT;
+    const bool live = t < ntiles;
+    const int64_t b0 = live ? e0 / kP : 0;
+    const int p0 = live ? static_cast<int>(e0 - b0 * kP) : 0;
+#pragma unroll
+    for (int u = 0; u < kItemsMax; ++u) {
+      int it = tid + u * kTcT;
+      if (it >= items) it = items - 1;
+      const int r = it >> 3, kc = it & 7;
+      int p = p0 + 4 * kc;
+      int64_t b = b0;
+      if (p >= kP) { p -= kP; b += 1; }
+      if (!live || e0 + 4 * kc >= E) { b = 0; p = 0; }
+      const float* src;
+      int C, c;
+      if (r < CO) { src = dy1; C = CO; c = r; }
+      else if (r < 2 * CO) { src = dy2; C = CO; c = r - CO; }
+      else if (r < 2 * CO + CI) { src = G; C = CI; c = r - 2 * CO; }
+      else { src = X; C = CI; c = r - 2 * CO - CI; }
+      vn[u] = tc::ldg_stay4(src + (b * C + c) * kP + p);
+    }
+  };
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t e0 = t * kWgKT;
-    const int64_t b0 = e0 / kP;
-    const int p0 = static_cast<int>(e0 - b0 * kP);
+    issue(t);                                                       // overlaps the previous tile's MMAs (waited for below)
     float4 v[kItemsMax];
 #pragma unroll
     for (int u = 0; u < kItemsMax; ++u) {
       const int it = tid + u * kTcT;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (it < items) {
-        const int r = it >> 3, kc = it & 7;
-        int p = p0 + 4 * kc;
-        int64_t b = b0;
-        if (p >= kP) { p -= kP; b += 1; }
-        if (e0 + 4 * kc < E) {                                    // E % 4 == 0: a float4 is entirely in or out
-          const float* src;
-          int C, c;
-          if (r < CO) { src = dy1; C = CO; c = r; }
-          else if (r < 2 * CO) { src = dy2; C = CO; c = r - CO; }
-          else if (r < 2 * CO + CI) { src = G; C = CI; c = r - 2 * CO; }
-          else { src = X; C = CI; c = r - 2 * CO - CI; }
-          v[u] = __ldg(reinterpret_cast<const float4*>(src + (b * C + c) * kP + p));
-        }
-      }
+      v[u] = (it >= items || e0 + 4 * (it & 7) >= E) ? make_float4(0.f, 0.f, 0.f, 0.f) : vn[u];
     }
     if (!first) {                                                 // the previous tile's MMAs still read the images
       tc::mbar_wait(&bar, phase);
@@ -480,14 +532,14 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
   if (warp == 0) tc::tmem_dealloc(tbase, kAlloc);
 }
 
-// second stage: dW[co,ci] += sum_blocks part, db[co] += ...; one thread per (branch, co, n), fixed order, double accumulator
+// second stage: dW[co,ci] += sum_blocks part, db[co] += ...; 32 x 8 blocks over the (branch, co, n) elements, fixed order
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int nblk, int CO, int CI, float* dW1, float* db1,
                                        float* dW2, float* db2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double sh[kPsRows][33];
   const int per = CO * (CI + 1);
-  if (i >= 2 * per) return;
-  double s = 0.0;
-  for (int j = 0; j < nblk; ++j) s += static_cast<double>(part[static_cast<int64_t>(j) * 2 * per + i]);
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const double s = partial_sum_block(part, nblk, 2 * per, i, i < 2 * per, sh);
+  if (threadIdx.y != 0 || i >= 2 * per) return;
   const int branch = i / per, r = i % per, co = r / (CI + 1), n = r % (CI + 1);
   if (n < CI) { float* dW = branch ? dW2 : dW1; dW[co * CI + n] += static_cast<float>(s); }
   else { float* db = branch ? db2 : db1; if (db) db[co] += static_cast<float>(s); }

@@ -254,3 +254,30 @@ def test_power_spherical_restatement_is_the_distribution_it_claims():
     assert torch.allclose((z * loc).sum(-1), tt.squeeze(-1), atol=1e-4)
     z1 = ops.rsample_from_noise(loc, torch.ones(64, 1, dtype=torch.float64), v)
     assert torch.allclose(z1, loc, atol=2e-3)        # sqrt(clamp(1 - t^2, 1e-7)) leaves a 3e-4 tangential component upstream too
+
+
+def test_pin_geoopt_script_plumbing(tmp_path):
+    """tools/pin_geoopt.py: exits 2 without geoopt (the state of this image: parity of the hyperbolic tail UNPINNED), and
+    diffs every function when a module of that name is importable -- exercised here with a stand-in package that re-exports
+    the restatement, which must then come out as 'agree' (exit 0)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, 'tools', 'pin_geoopt.py')
+    try:
+        import geoopt  # noqa: F401
+        have = True
+    except Exception:
+        have = False
+    if not have:
+        res = subprocess.run([sys.executable, script], capture_output=True, text=True, cwd=str(tmp_path))
+        assert res.returncode == 2 and 'UNPINNED' in res.stdout, res.stdout + res.stderr
+    pkg = tmp_path / 'geoopt' / 'manifolds' / 'stereographic'
+    pkg.mkdir(parents=True)
+    for d in (tmp_path / 'geoopt', tmp_path / 'geoopt' / 'manifolds', pkg):
+        (d / '__init__.py').write_text('__version__ = "stand-in"\n')
+    (pkg / 'math.py').write_text('from oracle.geoopt_math import *  # noqa\n')
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(tmp_path), root]))
+    res = subprocess.run([sys.executable, script], capture_output=True, text=True, cwd=str(tmp_path), env=env)
+    assert res.returncode == 0 and 'PINNED' in res.stdout and 'DIFF' not in res.stdout, res.stdout + res.stderr

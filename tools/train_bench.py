@@ -4,11 +4,13 @@
     COSKAD_TB_GRAPH=1 python tools/train_bench.py                the step as one CUDA-graph replay (what Trainer(cuda_graph=True) does)
     torchrun --nproc-per-node N tools/train_bench.py             data parallel: flat NCCL gradient all-reduce per step, max over ranks
     COSKAD_TB_NOAR=1 / COSKAD_TB_FOREACH=1                       A/B switches: skip the all-reduce / for-each instead of fused Adam
+    COSKAD_TRAIN_IMPL=0                                          A/B: the FP32 CUDA-core convolution kernels instead of tcgen05
 """
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from coskad_b200 import synth, gmath, _lib
+from coskad_b200 import synth, gmath, _lib, train as _train
+_train.set_train_impl(int(os.environ.get('COSKAD_TRAIN_IMPL', '1')))      # 1: tcgen05 convolutions (default), 0: FP32 CUDA-core kernels
 from coskad_b200.losses import calc_reg_loss
 
 import torch.distributed as dist
