@@ -713,6 +713,8 @@ extern "C" int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const
   CK(cudaFuncSetAttribute(train_contract_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
   train_contract_bwd_kernel<<<g, kCThreads, kCSmemBytes, st>>>(dG, dXres, X, G1, A, T, R, dX, ctx->ws);
   CK_LAUNCH();
+  if (dT == dA + kT * kV * kV)      // the usual case (one zeroed gradient buffer per layer): one second-stage launch for both
+    return launch_partial_sum<float>(ctx, ctx->ws, g, kContractPart, kContractPart, dA, st);
   { const int rc = launch_partial_sum<float>(ctx, ctx->ws, g, kContractPart, kT * kV * kV, dA, st); if (rc) return rc; }
   return launch_partial_sum<float>(ctx, ctx->ws + kT * kV * kV, g, kContractPart, kV * kT * kT, dT, st);
 }
@@ -757,12 +759,12 @@ static int launch_tc_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, co
   if (per_sm > 4) per_sm = 4;
   const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
   const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
-  { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(g) * 4 * 4 * CO); if (rc) return rc; }
+  { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(g) * 4 * CO); if (rc) return rc; }
   // no shared-memory padding here (tmem_pad_smem): measured 15-35 % slower for this kernel -- the large carve-out shrinks L1,
   // and the 128-byte row segments of neighbouring warps share cache lines (rows start at multiples of 816 B)
   tc_mix_fwd_kernel<CIP, CO, COP><<<g, kTcT, 0, st>>>(G, X, W1, b1, W2, b2, E, CI, y1, y2, ctx->ws);
   CK_LAUNCH();
-  return launch_partial_sum<double>(ctx, ctx->ws, g * 4, 4 * CO, 4 * CO, stats, st);
+  return launch_partial_sum<double>(ctx, ctx->ws, g, 4 * CO, 4 * CO, stats, st);
 }
 
 extern "C" int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1,
@@ -840,11 +842,11 @@ static int launch_tc_bwd_data(coskad_ctx* ctx, const float* dout, const float* y
   CK_LAUNCH();
   return COSKAD_OK;
 }
-template <int CO, int CI8>
+template <int CO, int CI8, int KT>
 static int launch_tc_bwd_weight(coskad_ctx* ctx, const float* dy1, const float* dy2, const float* G, const float* X, int64_t B,
                                 int CI, float* dW1, float* db1, float* dW2, float* db2, cudaStream_t st) {
-  const int64_t E = B * kP, ntiles = (E + kWgKT - 1) / kWgKT;
-  const size_t smem = sizeof(float) * wg_smem_floats(CI8);
+  const int64_t E = B * kP, ntiles = (E + KT - 1) / KT;
+  const size_t smem = sizeof(float) * wg_smem_floats(CO, CI8, KT);
   int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));
   const int tm = 512 / tmem_alloc_cols(2 * wg_n(CI8));
   if (per_sm > tm) per_sm = tm;
@@ -854,8 +856,8 @@ static int launch_tc_bwd_weight(coskad_ctx* ctx, const float* dy1, const float* 
   const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
   const size_t per = static_cast<size_t>(2) * CO * (CI + 1);
   { const int rc = ensure_ws(ctx, sizeof(float) * per * g); if (rc) return rc; }
-  CK(cudaFuncSetAttribute(tc_mix_bwd_weight_kernel<CO, CI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  tc_mix_bwd_weight_kernel<CO, CI8><<<g, kTcT, smem, st>>>(dy1, dy2, G, X, E, CI, ctx->ws);
+  CK(cudaFuncSetAttribute(tc_mix_bwd_weight_kernel<CO, CI8, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  tc_mix_bwd_weight_kernel<CO, CI8, KT><<<g, kTcT, smem, st>>>(dy1, dy2, G, X, E, CI, ctx->ws);
   CK_LAUNCH();
   tc_wgrad_reduce_kernel<<<static_cast<unsigned>((per + 31) / 32), dim3(32, kPsRows), 0, st>>>(ctx->ws, g, CO, CI, dW1, db1, dW2, db2);
   CK_LAUNCH();
@@ -875,14 +877,14 @@ extern "C" int coskad_train_mix_bwd_tc(coskad_ctx* ctx, const float* dout, const
   if (!dout || !y1 || !y2 || !mi || !red || !G || !X || !W1 || !W2 || !dy1 || !dy2 || !dG || !dXres || !dW1 || !dW2)
     return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
   int rc = COSKAD_ERR_ARG;
-#define TC_BWD(ci, co, cok, np, ci8)                                                                                         \
+#define TC_BWD(ci, co, cok, np, ci8, kt)                                                                                       \
   if (CI == ci && CO == co) {                                                                                                \
     rc = launch_tc_bwd_data<co, cok, np>(ctx, dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, B, CI, dy1, dy2, dG, dXres, st); \
     if (rc) return rc;                                                                                                       \
-    return launch_tc_bwd_weight<co, ci8>(ctx, dy1, dy2, G, X, B, CI, dW1, db1, dW2, db2, st);                                \
+    return launch_tc_bwd_weight<co, ci8, kt>(ctx, dy1, dy2, G, X, B, CI, dW1, db1, dW2, db2, st);                                \
   }
-  TC_BWD(2, 32, 32, 16, 8) TC_BWD(32, 16, 16, 32, 32) TC_BWD(16, 32, 32, 16, 16) TC_BWD(32, 64, 64, 32, 32)          // encoder
-  TC_BWD(64, 32, 32, 64, 64) TC_BWD(32, 2, 16, 32, 32)                                                              // decoder
+  TC_BWD(2, 32, 32, 16, 8, 64) TC_BWD(32, 16, 16, 32, 32, 64) TC_BWD(16, 32, 32, 16, 16, 64) TC_BWD(32, 64, 64, 32, 32, 32)   // encoder
+  TC_BWD(64, 32, 32, 64, 64, 32) TC_BWD(32, 2, 16, 32, 32, 64)                                                          // decoder
 #undef TC_BWD
   return fail(ctx, COSKAD_ERR_ARG, "train_mix_bwd_tc: unsupported channel pair %d -> %d", CI, CO);
 }

@@ -67,7 +67,7 @@ __global__ void partial_sum_wide_kernel(const float* __restrict__ part, int npar
 }
 
 // ---- forward: y1 = conv1x1(G; W1, b1), y2 = conv1x1(X; W2, b2) + per-CTA BatchNorm statistics ---------------------------
-// part [gridDim.x * 4 warps][4*CO] = sum y1, sum y1^2, sum y2, sum y2^2 per channel of the positions the warp owned.
+// part [gridDim.x][4*CO] = sum y1, sum y1^2, sum y2, sum y2^2 per channel of the positions the CTA owned.
 // CIP = c_in padded to a multiple of 8 (K step of kind::tf32), COP = c_out padded to a multiple of 16 (N of an M = 128 MMA).
 template <int CIP, int CO, int COP>
 __global__ void __launch_bounds__(kTcT) tc_mix_fwd_kernel(const float* __restrict__ G, const float* __restrict__ X,
@@ -197,12 +197,18 @@ __global__ void __launch_bounds__(kTcT) tc_mix_fwd_kernel(const float* __restric
     }
   }
   {
-    float* dst = part + (static_cast<int64_t>(blockIdx.x) * 4 + warp) * (4 * CO);
+    // the 4 warps' sums meet in shared memory in a fixed order: one partial [4*CO] per CTA
+    float* wsum = &tr[0][0][0];                      // 4 * 32 * 17 floats >= 4 warps x 4*CO
+    static_assert(4 * 32 * 17 >= 4 * 4 * CO, "stats scratch");
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int c = q * 16 + (lane & 15), branch = c / COP, co = c % COP;
-      if (co < CO) dst[(2 * branch + (lane >= 16 ? 1 : 0)) * CO + co] = sacc[q];
+      if (co < CO) wsum[warp * (4 * CO) + (2 * branch + (lane >= 16 ? 1 : 0)) * CO + co] = sacc[q];
     }
+    __syncthreads();
+    float* dst = part + static_cast<int64_t>(blockIdx.x) * (4 * CO);
+    for (int i = tid; i < 4 * CO; i += kTcT) dst[i] = ((wsum[i] + wsum[4 * CO + i]) + wsum[8 * CO + i]) + wsum[12 * CO + i];
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -374,34 +380,39 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
 }
 
 // ---- weight gradient: dW1 = dy1^T G, db1 = dy1^T 1, dW2 = dy2^T X, db2 = dy2^T 1, split-K over the grid ----------------------
-// part [gridDim.x][2][CO][CI + 1] (column CI = bias gradient).  KT = 32 positions per tile; images are padded canonical
-// K-major: element (r, k) at (r/8)*kWgSbo + (k/4)*kWgLbo + (r%8)*4 + (k%4) floats.
-constexpr int kWgKT = 32;
+// part [gridDim.x][2][CO][CI + 1] (column CI = bias gradient).  KT positions per tile (32 for the 64-channel layer, 64
+// otherwise: the per-tile barrier + MMA round trip is amortised over more bytes where shared memory allows 3 CTAs per SM);
+// images are padded canonical K-major: element (r, k) at (r/8)*sbo + (k/4)*kWgLbo + (r%8)*4 + (k%4) floats.  An A image holds
+// only the c_out rows that exist; the M = 64 MMA reads on into the images that follow (finite data), which only fills
+// accumulator rows >= c_out that nobody reads.
 constexpr int kWgLbo = 36;                      // floats (144 B): the 8 lanes of an STS.128 wavefront hit 32 distinct banks
-constexpr int kWgSbo = (kWgKT / 4) * kWgLbo;    // floats per 8-row group (1152 B)
 __host__ __device__ constexpr int wg_n(int ci8) { return ci8 + 8; }
-__host__ __device__ constexpr int wg_smem_floats(int ci8) { return 4 * 8 * kWgSbo + 4 * (wg_n(ci8) / 8) * kWgSbo; }
+__host__ __device__ constexpr int wg_sbo(int kt) { return (kt / 4) * kWgLbo; }            // floats per 8-row group
+__host__ __device__ constexpr int wg_agroups(int co) { return co < 8 ? 1 : co / 8; }
+__host__ __device__ constexpr int wg_smem_floats(int co, int ci8, int kt) { return 4 * (wg_agroups(co) + wg_n(ci8) / 8) * wg_sbo(kt); }
 
-template <int CO, int CI8>
+template <int CO, int CI8, int KT>
 __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
                                                                 const float* __restrict__ G, const float* __restrict__ X,
                                                                 int64_t E, int CI, float* __restrict__ part) {
   constexpr int N = wg_n(CI8);
-  constexpr int kAimg = 8 * kWgSbo;                               // M = 64 rows
-  constexpr int kBimg = (N / 8) * kWgSbo;
+  constexpr int kCh = KT / 4;                                     // 16-byte chunks per row and tile
+  constexpr int kSbo = wg_sbo(KT);
+  constexpr int kAimg = wg_agroups(CO) * kSbo;
+  constexpr int kBimg = (N / 8) * kSbo;
+  static_assert(wg_agroups(CO) + 4 * (N / 8) >= 8, "the M = 64 read of the last A image must stay inside the allocation");
   constexpr int kAlloc = tmem_alloc_cols(2 * N);
-  constexpr int kItemsMax = ((2 * CO + 2 * CI8) * (kWgKT / 4) + kTcT - 1) / kTcT;   // float4 per thread and tile
+  constexpr int kItemsMax = ((2 * CO + 2 * CI8) * kCh + kTcT - 1) / kTcT;   // float4 per thread and tile
   extern __shared__ __align__(128) float wsm[];
   float* Aimg = wsm;                                              // dy1 hi, dy1 lo, dy2 hi, dy2 lo
   float* Bimg = wsm + 4 * kAimg;                                  // G hi, G lo, X hi, X lo (+ the row of ones at row CI8 of the hi images)
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 4 * kBimg; i += kTcT) Bimg[i] = 0.f;
-  for (int i = tid; i < 4 * kAimg; i += kTcT) Aimg[i] = 0.f;
+  for (int i = tid; i < 4 * (kAimg + kBimg); i += kTcT) wsm[i] = 0.f;
   __syncthreads();
-  if (tid < kWgKT) {                                              // ones: row CI8 (first row of the last group), every k
-    const int o = (CI8 / 8) * kWgSbo + (tid >> 2) * kWgLbo + (tid & 3);
+  if (tid < KT) {                                                 // ones: row CI8 (first row of the last group), every k
+    const int o = (CI8 / 8) * kSbo + (tid >> 2) * kWgLbo + (tid & 3);
     Bimg[0 * kBimg + o] = 1.f;
     Bimg[2 * kBimg + o] = 1.f;
   }
@@ -413,27 +424,26 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
   const int rows = 2 * CO + 2 * CI;
-  const int items = rows * (kWgKT / 4);
-  const int64_t ntiles = (E + kWgKT - 1) / kWgKT;
+  const int items = rows * kCh;
+  const int64_t ntiles = (E + KT - 1) / KT;
   uint32_t phase = 0;
   bool first = true;
   // the 16-byte loads of a tile: unconditional, all in flight together while the previous tile's MMAs run; an item past the
   // end of the batch (E % 4 == 0: entirely in or out) or past the row list reads a valid address and is zeroed when consumed
   float4 vn[kItemsMax];
   auto issue = [&](int64_t t) {
-    const int64_t e0 = t * kWgKT;
-    const bool live = t < ntiles;
-    const int64_t b0 = live ? e0 / kP : 0;
-    const int p0 = live ? static_cast<int>(e0 - b0 * kP) : 0;
+    const int64_t e0 = t * KT;
+    const int64_t b0 = e0 / kP;
+    const int p0 = static_cast<int>(e0 - b0 * kP);
 #pragma unroll
     for (int u = 0; u < kItemsMax; ++u) {
       int it = tid + u * kTcT;
       if (it >= items) it = items - 1;
-      const int r = it >> 3, kc = it & 7;
+      const int r = it / kCh, kc = it % kCh;
       int p = p0 + 4 * kc;
       int64_t b = b0;
       if (p >= kP) { p -= kP; b += 1; }
-      if (!live || e0 + 4 * kc >= E) { b = 0; p = 0; }
+      if (e0 + 4 * kc >= E) { b = 0; p = 0; }
       const float* src;
       int C, c;
       if (r < CO) { src = dy1; C = CO; c = r; }
@@ -444,23 +454,19 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
     }
   };
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t e0 = t * kWgKT;
+    const int64_t e0 = t * KT;
     issue(t);                                                       // overlaps the previous tile's MMAs (waited for below)
-    float4 v[kItemsMax];
-#pragma unroll
-    for (int u = 0; u < kItemsMax; ++u) {
-      const int it = tid + u * kTcT;
-      v[u] = (it >= items || e0 + 4 * (it & 7) >= E) ? make_float4(0.f, 0.f, 0.f, 0.f) : vn[u];
-    }
-    if (!first) {                                                 // the previous tile's MMAs still read the images
+    if (!first) {                                                   // the previous tile's MMAs still read the images
       tc::mbar_wait(&bar, phase);
       phase ^= 1;
+      tc::fence_after_sync();
     }
 #pragma unroll
     for (int u = 0; u < kItemsMax; ++u) {
       const int it = tid + u * kTcT;
       if (it < items) {
-        const int r = it >> 3, kc = it & 7;
+        const int r = it / kCh, kc = it % kCh;
+        const float4 v = (e0 + 4 * kc >= E) ? make_float4(0.f, 0.f, 0.f, 0.f) : vn[u];
         float* hi_img;
         int rr;
         if (r < CO) { hi_img = Aimg; rr = r; }
@@ -468,10 +474,10 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
         else if (r < 2 * CO + CI) { hi_img = Bimg; rr = r - 2 * CO; }
         else { hi_img = Bimg + 2 * kBimg; rr = r - 2 * CO - CI; }
         const int img = (r < 2 * CO) ? kAimg : kBimg;
-        const int o = (rr >> 3) * kWgSbo + kc * kWgLbo + (rr & 7) * 4;
+        const int o = (rr >> 3) * kSbo + kc * kWgLbo + (rr & 7) * 4;
         uint32_t h[4], l[4];
-        tc::split_tf32(v[u].x, h[0], l[0]); tc::split_tf32(v[u].y, h[1], l[1]);
-        tc::split_tf32(v[u].z, h[2], l[2]); tc::split_tf32(v[u].w, h[3], l[3]);
+        tc::split_tf32(v.x, h[0], l[0]); tc::split_tf32(v.y, h[1], l[1]);
+        tc::split_tf32(v.z, h[2], l[2]); tc::split_tf32(v.w, h[3], l[3]);
         *reinterpret_cast<uint4*>(hi_img + o) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(hi_img + img + o) = make_uint4(l[0], l[1], l[2], l[3]);
       }
@@ -481,10 +487,10 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
     if (tid == 0) {
       tc::fence_after_sync();
       const uint32_t idesc = tc::make_idesc_tf32(64, N);
-      const uint32_t lbo = kWgLbo * 4, sbo = kWgSbo * 4;
+      const uint32_t lbo = kWgLbo * 4, sbo = kSbo * 4;
       const uint32_t a0 = tc::smem_u32(Aimg), bb = tc::smem_u32(Bimg);
 #pragma unroll
-      for (int ks = 0; ks < kWgKT / 8; ++ks) {
+      for (int ks = 0; ks < KT / 8; ++ks) {
         const uint32_t offs = ks * 2 * lbo;
         const uint32_t acc = (!first || ks > 0) ? 1u : 0u;
         const uint64_t a1h = tc::make_smem_desc(a0 + offs, lbo, sbo), a1l = tc::make_smem_desc(a0 + kAimg * 4 + offs, lbo, sbo);
