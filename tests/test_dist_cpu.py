@@ -108,3 +108,70 @@ def test_compat_shims_register_reference_import_paths():
     assert 'rev_btlnk.weight' in a.state_dict()
     import geoopt.manifolds.stereographic.math as gmath
     assert all(hasattr(gmath, f) for f in ('expmap0', 'project', 'dist', 'dist0', 'weighted_midpoint'))
+
+
+class _TinyLit(torch.nn.Module):
+    """a LightningModule-shaped toy (torch ops only) to drive trainer.TrainStep on the CPU"""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(5)
+        self.net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.PReLU(), torch.nn.Linear(4, 1))
+
+    def training_step(self, batch, batch_idx):
+        x, y = batch
+        return torch.nn.functional.mse_loss(self.net(x), y)
+
+
+def _step_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from coskad_b200 import dist as cdist
+    from coskad_b200.trainer import TrainStep
+    out = {}
+    # sharded loader: rank r takes batches r, r + world, ..; every rank the same number (the ragged tail is dropped)
+    loader = [[torch.full((2, 6), float(i)), torch.full((2, 1), float(i))] for i in range(7)]
+    mine = [int(b[0][0, 0]) for b in cdist.ShardedLoader(loader)]
+    out['shard_ok'] = mine == [i for i in range(6) if i % world == rank] and len(cdist.ShardedLoader(loader)) == 3
+    # data-parallel eager step through the attached flat bucket == single-process step on the averaged gradient
+    g = torch.Generator().manual_seed(100)
+    xs, ys = torch.randn(world, 8, 6, generator=g), torch.randn(world, 8, 1, generator=g)
+    lit = _TinyLit()
+    cdist.broadcast_module_(lit)
+    opt = torch.optim.SGD(lit.parameters(), lr=0.1)
+    bucket = cdist.FlatGradBucket(lit.parameters()).attach()
+    out['views_ok'] = bucket.attached() and all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lit.parameters())
+    ts = TrainStep(lit, opt, bucket, torch.device('cpu'))
+    for _ in range(3):
+        ts.eager([xs[rank], ys[rank]], 0)
+    out['still_attached'] = bucket.attached()          # zero_() instead of zero_grad(set_to_none=True) keeps the views
+    ref = _TinyLit()
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    for _ in range(3):
+        ropt.zero_grad()
+        sum(ref.training_step([xs[r], ys[r]], 0) for r in range(world)).div(world).backward()
+        ropt.step()
+    out['step_ok'] = all(torch.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(lit.parameters(), ref.parameters()))
+    flat = torch.cat([p.detach().reshape(-1) for p in lit.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    out['replicas_identical'] = all(torch.equal(gathered[0], t) for t in gathered[1:])
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_trainstep_gloo():
+    """world_size 2 on the CPU: the sharded loader, the attached flat gradient bucket (in-place all-reduce, DDP averaging) and
+    trainer.TrainStep's eager step -- the host logic of BASELINE configs[4]"""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_step_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(2):
+        assert all(res[r].values()), res
