@@ -39,7 +39,17 @@ struct coskad_ctx {
   float* ws = nullptr;
   size_t ws_bytes = 0;
   int train_impl = 1;      // 1 = 1x1 convolutions / weight gradients on tcgen05 (3xTF32), 0 = the FP32 CUDA-core kernels (A/B)
+  int contract_rows = 0;   // rows per block of the training graph-contraction kernels: 48 (two blocks per SM) or 96 (one); 0 = unset
 };
+
+// COSKAD_CONTRACT_ROWS=96 selects the one-block-per-SM contraction kernels (A/B measurement); default 48
+static int contract_rows(coskad_ctx* ctx) {
+  if (ctx->contract_rows == 0) {
+    const char* e = getenv("COSKAD_CONTRACT_ROWS");
+    ctx->contract_rows = (e != nullptr && atoi(e) == kCRows) ? kCRows : kCRowsSmall;
+  }
+  return ctx->contract_rows;
+}
 
 static thread_local std::string g_create_err;
 
@@ -679,10 +689,18 @@ extern "C" int coskad_train_contract_fwd(coskad_ctx* ctx, const float* X, const 
                                          float* G1, float* G, void* stream_) {
   TRAIN_PRE();
   if (R <= 0) return COSKAD_OK;
-  const int64_t nblk = (R + kCRows - 1) / kCRows;
-  const int g = static_cast<int>(nblk < ctx->sm_count ? nblk : ctx->sm_count);
-  CK(cudaFuncSetAttribute(train_contract_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
-  train_contract_fwd_kernel<<<g, kCThreads, kCSmemBytes, st>>>(X, A, T, R, G1, G);
+  if (contract_rows(ctx) == kCRows) {
+    const int64_t nblk = (R + kCRows - 1) / kCRows;
+    const int g = static_cast<int>(nblk < ctx->sm_count ? nblk : ctx->sm_count);
+    CK(cudaFuncSetAttribute(train_contract_fwd_kernel<kCRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
+    train_contract_fwd_kernel<kCRows><<<g, kCThreads, kCSmemBytes, st>>>(X, A, T, R, G1, G);
+  } else {
+    constexpr int smem = contract_smem_bytes(kCRowsSmall);
+    const int64_t nblk = (R + kCRowsSmall - 1) / kCRowsSmall;
+    const int g = static_cast<int>(nblk < 2 * ctx->sm_count ? nblk : 2 * ctx->sm_count);
+    CK(cudaFuncSetAttribute(train_contract_fwd_kernel<kCRowsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    train_contract_fwd_kernel<kCRowsSmall><<<g, kCThreads, smem, st>>>(X, A, T, R, G1, G);
+  }
   CK_LAUNCH();
   return COSKAD_OK;
 }
@@ -707,11 +725,19 @@ extern "C" int coskad_train_contract_bwd(coskad_ctx* ctx, const float* dG, const
                                          float* dA, float* dT, void* stream_) {
   TRAIN_PRE();
   if (R <= 0) return COSKAD_OK;
-  const int64_t nblk = (R + kCRows - 1) / kCRows;
-  const int g = static_cast<int>(nblk < ctx->sm_count ? nblk : ctx->sm_count);
+  const bool big = contract_rows(ctx) == kCRows;
+  const int nr = big ? kCRows : kCRowsSmall, cap = big ? ctx->sm_count : 2 * ctx->sm_count;
+  const int64_t nblk = (R + nr - 1) / nr;
+  const int g = static_cast<int>(nblk < cap ? nblk : cap);
   { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(g) * kContractPart); if (rc) return rc; }
-  CK(cudaFuncSetAttribute(train_contract_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
-  train_contract_bwd_kernel<<<g, kCThreads, kCSmemBytes, st>>>(dG, dXres, X, G1, A, T, R, dX, ctx->ws);
+  if (big) {
+    CK(cudaFuncSetAttribute(train_contract_bwd_kernel<kCRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCSmemBytes));
+    train_contract_bwd_kernel<kCRows><<<g, kCThreads, kCSmemBytes, st>>>(dG, dXres, X, G1, A, T, R, dX, ctx->ws);
+  } else {
+    constexpr int smem = contract_smem_bytes(kCRowsSmall);
+    CK(cudaFuncSetAttribute(train_contract_bwd_kernel<kCRowsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    train_contract_bwd_kernel<kCRowsSmall><<<g, kCThreads, smem, st>>>(dG, dXres, X, G1, A, T, R, dX, ctx->ws);
+  }
   CK_LAUNCH();
   if (dT == dA + kT * kV * kV)      // the usual case (one zeroed gradient buffer per layer): one second-stage launch for both
     return launch_partial_sum<float>(ctx, ctx->ws, g, kContractPart, kContractPart, dA, st);
@@ -784,10 +810,19 @@ extern "C" int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float
 
 extern "C" int coskad_train_bn_finalize(coskad_ctx* ctx, const double* stats, int64_t n_per_channel, int CO, float eps,
                                         float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi,
-                                        void* stream_) {
+                                        int64_t* nbt1, int64_t* nbt2, void* stream_) {
   TRAIN_PRE();
   train_bn_finalize_kernel<<<(CO + 63) / 64, 64, 0, st>>>(stats, static_cast<double>(n_per_channel), CO, eps, momentum, rm1,
-                                                         rv1, rm2, rv2, mi);
+                                                         rv1, rm2, rv2, mi, nbt1, nbt2);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_bn_param_grads(coskad_ctx* ctx, const double* red, int CO, float* dg1, float* dbe1, float* dg2,
+                                           float* dbe2, float* dslope, void* stream_) {
+  TRAIN_PRE();
+  if (red == nullptr || CO <= 0) return fail(ctx, COSKAD_ERR_ARG, "coskad_train_bn_param_grads: red is NULL or CO = %d", CO);
+  train_bn_param_grads_kernel<<<(CO + 63) / 64, 64, 0, st>>>(red, CO, dg1, dbe1, dg2, dbe2, dslope);
   CK_LAUNCH();
   return COSKAD_OK;
 }

@@ -87,17 +87,40 @@ constexpr int kTrainThreads = 256;
 constexpr int kCRows = kNW * 32;                 // 96
 constexpr int kCThreads = 384;
 constexpr int kCWarps = kCThreads / 32;
-constexpr int kCSmemFloats = 2 * kCRows * kCS + kTwFloats + kAwFloats;
-constexpr int kCSmemBytes = kCSmemFloats * 4;
+// Two block sizes: NR = 96 rows (one 182 KB block per SM, the C = 32 stages: lane = row % 32) and NR = 48 rows (two 102 KB
+// blocks per SM, the C = 16 stages: lane = (row % 16, output half)): with two resident blocks the load -> compute -> store
+// phases of one overlap the other's and the FP32 stages see 24 instead of 12 warps per SM.
+constexpr int kCRowsSmall = kNW * 16;            // 48
+__host__ __device__ constexpr int contract_smem_bytes(int nr) { return (2 * nr * kCS + kTwFloats + kAwFloats) * 4; }
+constexpr int kCSmemBytes = contract_smem_bytes(kCRows);
 static_assert(kCSmemBytes <= 227 * 1024, "contraction kernels: shared memory plan exceeds 227 KB");
+static_assert(2 * (contract_smem_bytes(kCRowsSmall) + 1024) <= 227 * 1024, "two 48-row blocks per SM");
+template <int NR> struct ContractStages;
+template <> struct ContractStages<kCRows> {
+  static __device__ __forceinline__ void temporal(const float* src, float* dst, const float* Tw, int warp, int lane) {
+    temporal_stage_c32<kCThreads / 32>(src, dst, Tw, warp, lane);
+  }
+  static __device__ __forceinline__ void spatial(float* buf, const float* Aw, int warp, int lane) {
+    spatial_stage_c32<kCThreads / 32>(buf, Aw, warp, lane);
+  }
+};
+template <> struct ContractStages<kCRowsSmall> {
+  static __device__ __forceinline__ void temporal(const float* src, float* dst, const float* Tw, int warp, int lane) {
+    temporal_stage_c16<kCThreads / 32>(src, dst, Tw, warp, lane);
+  }
+  static __device__ __forceinline__ void spatial(float* buf, const float* Aw, int warp, int lane) {
+    spatial_stage_c16<EpiIdentity, kCThreads / 32>(buf, Aw, EpiIdentity{}, warp, lane);
+  }
+};
 constexpr int kContractPart = kT * kV * kV + kV * kT * kT;     // floats of one block's [dA | dT] partial
 
 // Row-block copies, one warp per row (rows warp, warp + 12, ..), lanes = positions p = lane + 32 k: one pointer per row and
 // a few instructions per element (a flat element index cost ~20 integer instructions per 4-byte copy).
 constexpr int kRowIters = (kP + 31) / 32;                         // 7
+template <int NR>
 __device__ __forceinline__ void contract_load_rows(float* dst, const float* __restrict__ src, int64_t r0, int nr, int tid) {
   const int warp = tid >> 5, lane = tid & 31;
-  for (int row = warp; row < kCRows; row += kCWarps) {
+  for (int row = warp; row < NR; row += kCWarps) {
     const float* s = src + (r0 + (row < nr ? row : nr - 1)) * kP;   // ragged last block: replicate the last row, never stored
     float* d = dst + row * kCS;
 #pragma unroll
@@ -108,12 +131,13 @@ __device__ __forceinline__ void contract_load_rows(float* dst, const float* __re
   }
 }
 // dst rows [r0, r0+nr) = planes (+ add, nullable); the loads of `add` are batched four rows at a time
+template <int NR>
 __device__ __forceinline__ void contract_store_rows(float* __restrict__ dst, const float* planes, const float* __restrict__ add,
                                                     int64_t r0, int nr, int tid) {
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int kRB = 4;
-  static_assert(kCRows % (kCWarps * kRB) == 0, "row-block store plan");
-  for (int rb = warp; rb < kCRows; rb += kCWarps * kRB) {
+  static_assert(NR % (kCWarps * kRB) == 0, "row-block store plan");
+  for (int rb = warp; rb < NR; rb += kCWarps * kRB) {
     float a[kRB][kRowIters];
 #pragma unroll
     for (int j = 0; j < kRB; ++j) {
@@ -141,53 +165,55 @@ __device__ __forceinline__ void contract_store_rows(float* __restrict__ dst, con
 }
 
 // G1 = einsum('nctv,vtq->ncqv', X, T); G = einsum('nctv,tvw->nctw', G1, A)      (stsgcn.py:154-155)
-__global__ void __launch_bounds__(kCThreads, 1) train_contract_fwd_kernel(const float* __restrict__ X, const float* __restrict__ A,
+template <int NR>
+__global__ void __launch_bounds__(kCThreads, NR == kCRows ? 1 : 2) train_contract_fwd_kernel(const float* __restrict__ X, const float* __restrict__ A,
                                                                          const float* __restrict__ T, int64_t R,
                                                                          float* __restrict__ G1, float* __restrict__ G) {
   extern __shared__ __align__(128) float csm[];
   float* Xs = csm;
-  float* Gs = Xs + kCRows * kCS;
-  float* Ts = Gs + kCRows * kCS;
+  float* Gs = Xs + NR * kCS;
+  float* Ts = Gs + NR * kCS;
   float* As = Ts + kTwFloats;                      // rows padded 17 -> kAW
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < kTwFloats; i += kCThreads) Ts[i] = T[i];
   for (int i = tid; i < kAwFloats; i += kCThreads) { const int w = i % kAW, tv = i / kAW; As[i] = (w < kV) ? A[tv * kV + w] : 0.f; }
-  const int64_t nblk = (R + kCRows - 1) / kCRows;
+  const int64_t nblk = (R + NR - 1) / NR;
   if (static_cast<int64_t>(blockIdx.x) < nblk) {
-    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kCRows;
-    contract_load_rows(Xs, X, r0, static_cast<int>(R - r0 < kCRows ? R - r0 : kCRows), tid);
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * NR;
+    contract_load_rows<NR>(Xs, X, r0, static_cast<int>(R - r0 < NR ? R - r0 : NR), tid);
   }
   cp_async_commit();
   for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int64_t r0 = blk * kCRows;
-    const int nr = static_cast<int>(R - r0 < kCRows ? R - r0 : kCRows);
+    const int64_t r0 = blk * NR;
+    const int nr = static_cast<int>(R - r0 < NR ? R - r0 : NR);
     cp_async_wait_all();
     __syncthreads();
-    temporal_stage_c32<kCWarps>(Xs, Gs, Ts, warp, lane);
+    ContractStages<NR>::temporal(Xs, Gs, Ts, warp, lane);
     __syncthreads();
     {   // Xs is dead: prefetch the next block's rows while this one finishes
       const int64_t nb = blk + gridDim.x;
-      if (nb < nblk) { const int64_t n0 = nb * kCRows; contract_load_rows(Xs, X, n0, static_cast<int>(R - n0 < kCRows ? R - n0 : kCRows), tid); }
+      if (nb < nblk) { const int64_t n0 = nb * NR; contract_load_rows<NR>(Xs, X, n0, static_cast<int>(R - n0 < NR ? R - n0 : NR), tid); }
       cp_async_commit();
     }
-    contract_store_rows(G1, Gs, nullptr, r0, nr, tid);
+    contract_store_rows<NR>(G1, Gs, nullptr, r0, nr, tid);
     __syncthreads();
-    spatial_stage_c32<kCWarps>(Gs, As, warp, lane);
+    ContractStages<NR>::spatial(Gs, As, warp, lane);
     __syncthreads();
-    contract_store_rows(G, Gs, nullptr, r0, nr, tid);
+    contract_store_rows<NR>(G, Gs, nullptr, r0, nr, tid);
   }
   cp_async_wait_all();
 }
 
 // dG1[t,v] = sum_w dG[t,w] A[t,v,w];  dX[t,v] = dXres[t,v] + sum_q dG1[q,v] T[v,t,q]
 // dA[t,v,w] += G1[t,v] dG[t,w];       dT[v,t,q] += X[t,v] dG1[q,v]      (summed over rows)
-__global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
+template <int NR>
+__global__ void __launch_bounds__(kCThreads, NR == kCRows ? 1 : 2) train_contract_bwd_kernel(
     const float* __restrict__ dG, const float* __restrict__ dXres, const float* __restrict__ X, const float* __restrict__ G1,
     const float* __restrict__ A, const float* __restrict__ T, int64_t R, float* __restrict__ dX, float* __restrict__ part) {
   extern __shared__ __align__(128) float csm[];
   float* P0 = csm;                                 // dG -> dG1 (in place)
-  float* P1 = P0 + kCRows * kCS;                   // G1, then X, then dX
-  float* Tt = P1 + kCRows * kCS;                   // Tt[v][q][t] = T[v][t][q]
+  float* P1 = P0 + NR * kCS;                   // G1, then X, then dX
+  float* Tt = P1 + NR * kCS;                   // Tt[v][q][t] = T[v][t][q]
   float* At = Tt + kTwFloats;                      // At[t][w][v] = A[t][v][w], rows padded 17 -> kAW
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < kTwFloats; i += kCThreads) { const int v = i / (kT * kT), q = (i / kT) % kT, t = i % kT; Tt[i] = T[v * (kT * kT) + t * kT + q]; }
@@ -214,13 +240,13 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < 4; ++j) accA[i][j] = 0.f;
   }
-  const int64_t nblk = (R + kCRows - 1) / kCRows;
+  const int64_t nblk = (R + NR - 1) / NR;
   for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int64_t r0 = blk * kCRows;
-    const int nr = static_cast<int>(R - r0 < kCRows ? R - r0 : kCRows);
+    const int64_t r0 = blk * NR;
+    const int nr = static_cast<int>(R - r0 < NR ? R - r0 : NR);
     __syncthreads();
-    contract_load_rows(P0, dG, r0, nr, tid);
-    contract_load_rows(P1, G1, r0, nr, tid);
+    contract_load_rows<NR>(P0, dG, r0, nr, tid);
+    contract_load_rows<NR>(P1, G1, r0, nr, tid);
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
@@ -236,9 +262,9 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
       }
     }
     __syncthreads();
-    contract_load_rows(P1, X, r0, nr, tid);          // G1 is dead
+    contract_load_rows<NR>(P1, X, r0, nr, tid);          // G1 is dead
     cp_async_commit();
-    spatial_stage_c32<kCWarps>(P0, At, warp, lane);  // dG -> dG1 in place
+    ContractStages<NR>::spatial(P0, At, warp, lane);  // dG -> dG1 in place
     cp_async_wait_all();
     __syncthreads();
     if (hasT) {
@@ -252,9 +278,9 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
       }
     }
     __syncthreads();
-    temporal_stage_c32<kCWarps>(P0, P1, Tt, warp, lane);      // dG1 -> temporal^T -> P1 (X is dead)
+    ContractStages<NR>::temporal(P0, P1, Tt, warp, lane);      // dG1 -> temporal^T -> P1 (X is dead)
     __syncthreads();
-    contract_store_rows(dX, P1, dXres, r0, nr, tid);
+    contract_store_rows<NR>(dX, P1, dXres, r0, nr, tid);
   }
   // per-block partial sums [dA (T*V*V) | dT (V*T*T)]: every element has exactly one owner thread, so these are plain stores;
   // the blocks' partials are added in a fixed order by partial_sum_kernel (no floating-point atomics: bit-reproducible)
@@ -277,8 +303,13 @@ __global__ void __launch_bounds__(kCThreads, 1) train_contract_bwd_kernel(
 
 // mean / invstd from the sums, running-statistics update (momentum 0.1, unbiased variance), nn.BatchNorm2d semantics
 __global__ void train_bn_finalize_kernel(const double* __restrict__ stats, double N, int CO, float eps, float momentum,
-                                         float* rm1, float* rv1, float* rm2, float* rv2, float* __restrict__ mi) {
+                                         float* rm1, float* rv1, float* rm2, float* rv2, float* __restrict__ mi,
+                                         int64_t* nbt1, int64_t* nbt2) {
   const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co == 0) {                                   // nn.BatchNorm2d.num_batches_tracked += 1 (was two one-element torch kernels per layer)
+    if (nbt1) *nbt1 += 1;
+    if (nbt2) *nbt2 += 1;
+  }
   if (co >= CO) return;
   for (int br = 0; br < 2; ++br) {
     const double mean = stats[(2 * br) * CO + co] / N;
@@ -395,6 +426,22 @@ __global__ void train_bn_prelu_bwd_reduce_final_kernel(const float* __restrict__
     s = warp_sum(s);
     if (lane == 0) red[3 * CO] += s;
   }
+}
+
+// parameter gradients of the two BatchNorms and the PReLU from the float64 sums `red` (train_bn_prelu_bwd_reduce_*):
+// d beta1 = d beta2 += red[0..CO), d gamma1 += red[CO..2CO), d gamma2 += red[2CO..3CO), d slope += red[3CO]
+// (accumulating: the destinations are the zeroed .grad views of the flat gradient bucket, or zeroed temporaries)
+__global__ void train_bn_param_grads_kernel(const double* __restrict__ red, int CO, float* dg1, float* dbe1, float* dg2,
+                                            float* dbe2, float* dslope) {
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co < CO) {
+    const float db = static_cast<float>(red[co]);
+    if (dbe1) dbe1[co] += db;
+    if (dbe2) dbe2[co] += db;
+    if (dg1) dg1[co] += static_cast<float>(red[CO + co]);
+    if (dg2) dg2[co] += static_cast<float>(red[2 * CO + co]);
+  }
+  if (co == 0 && dslope) dslope[0] += static_cast<float>(red[3 * CO]);
 }
 
 // dy1 = g1*is1*(ds - mean(ds) - yhat1*mean(ds*yhat1)), dy2 likewise (BatchNorm train backward); one warp per row, float4

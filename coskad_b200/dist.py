@@ -65,7 +65,16 @@ class FlatGradBucket:
                 if p.grad is not None:
                     v.copy_(p.grad)
                 p.grad = v
+            # the training kernels may accumulate into the (zeroed) views themselves instead of handing the gradient to
+            # autograd's AccumulateGrad: one add_ launch per parameter and step less (train._direct, losses._L2Reg)
+            p.coskad_direct_grad = True
         return self
+
+    def detach(self) -> None:
+        """give the gradients back to autograd (``p.grad = None``): after this the kernels return their gradients"""
+        for p in self.params:
+            p.grad = None
+            p.coskad_direct_grad = False
 
     def zero_(self) -> None:
         """replaces optimizer.zero_grad(set_to_none=True), which would detach the views"""

@@ -19,6 +19,7 @@ class _L2Reg(torch.autograd.Function):
     @staticmethod
     def forward(ctx, n_avg: float, *params: torch.Tensor) -> torch.Tensor:
         ctx.n_avg = n_avg
+        ctx.params = params                       # the leaves themselves (backward looks at their .grad)
         ctx.save_for_backward(*params)
         norms = torch._foreach_norm([p.detach() for p in params], 2)
         return 0.5 * torch.stack(norms).square().sum() / n_avg
@@ -28,7 +29,13 @@ class _L2Reg(torch.autograd.Function):
         params = ctx.saved_tensors
         scale = g / ctx.n_avg
         grads = torch._foreach_mul([p.detach() for p in params], scale)
-        return (None, *grads)
+        # parameters whose .grad is a view of an attached dist.FlatGradBucket: one multi-tensor add into the bucket instead
+        # of one AccumulateGrad add_ launch per tensor (42 of them per step); the others go back to autograd
+        direct = [getattr(p, 'coskad_direct_grad', False) and p.grad is not None for p in ctx.params]
+        if any(direct):
+            with torch.no_grad():
+                torch._foreach_add_([p.grad for p, d in zip(ctx.params, direct) if d], [g_ for g_, d in zip(grads, direct) if d])
+        return (None, *[None if d else g_ for g_, d in zip(grads, direct)])
 
 
 def calc_reg_loss(model, reg_type: str = 'l2', avg: bool = True):

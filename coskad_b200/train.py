@@ -41,6 +41,21 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+def _direct(p) -> Optional[torch.Tensor]:
+    """the gradient destination the backward kernels may accumulate into themselves: ``p.grad`` when it is a view of an
+    attached ``dist.FlatGradBucket`` (which zeroes it at the start of every step and marks the parameter).  Every
+    second-stage reduction of the training kernels ADDS to its destination, so writing there is what autograd's
+    AccumulateGrad would do -- minus one ``add_`` launch per parameter per step (~60 one-microsecond kernels).  The
+    Function then returns ``None`` for that input.  Parameters that are not marked (plain ``loss.backward()`` without a
+    bucket, ``torch.autograd.grad``) take the ordinary path: gradients are returned to autograd."""
+    if p is None or not getattr(p, 'coskad_direct_grad', False):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
+
+
 class _LayerFn(torch.autograd.Function):
     """one ST_GCNN_layer, train (batch statistics) or eval (running statistics) BatchNorm"""
 
@@ -67,10 +82,9 @@ class _LayerFn(torch.autograd.Function):
             mi = torch.empty(4 * CO, device=X.device, dtype=torch.float32)
             c.check(lib.coskad_train_bn_finalize(c.h, stats.data_ptr(), B * P, CO, float(bn1.eps), float(bn1.momentum),
                                                  bn1.running_mean.data_ptr(), bn1.running_var.data_ptr(),
-                                                 bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), mi.data_ptr(), st),
+                                                 bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), mi.data_ptr(),
+                                                 _nbt_ptr(bn1, X.device), _nbt_ptr(bn2, X.device), st),
                     'coskad_train_bn_finalize')
-            bn1.num_batches_tracked += 1
-            bn2.num_batches_tracked += 1
         else:   # eval: normalise with the running statistics (parameter prep, 4*CO numbers)
             mi = torch.cat([bn1.running_mean, torch.rsqrt(bn1.running_var + bn1.eps),
                             bn2.running_mean, torch.rsqrt(bn2.running_var + bn2.eps)]).to(torch.float32).contiguous()
@@ -80,6 +94,7 @@ class _LayerFn(torch.autograd.Function):
                                               out.data_ptr(), st), 'coskad_train_bn_prelu_fwd')
         ctx.save_for_backward(X, G1, G, y1, y2, mi, A, T, W1, W2, g1, be1, g2, be2, slope)
         ctx.has_b = (b1 is not None, b2 is not None)
+        ctx.params = (A, T, W1, b1, g1, be1, W2, b2, g2, be2, slope)      # the leaves themselves: backward looks at their .grad
         ctx.training = training
         return out
 
@@ -93,25 +108,35 @@ class _LayerFn(torch.autograd.Function):
         c = _ctx(X)
         st = _lib.stream_ptr(X.device)
         lib = c.lib
-        # every accumulator of this layer's backward (float64 BN/PReLU sums, weight / bias / graph-operator gradients)
-        # lives in one zeroed buffer: one memset per layer instead of seven
-        sizes = (2 * (3 * CO + 1), W1.numel(), W2.numel(), CO, CO, A.numel(), T.numel())
-        offs = [0]
-        for n in sizes:
+        # Gradient destinations: the parameter's .grad view of the flat bucket when there is one (the kernels' second stages
+        # add to their destination), else a slice of one zeroed buffer (one memset per layer) that is returned to autograd.
+        pA, pT, pW1, pb1, pg1, pbe1, pW2, pb2, pg2, pbe2, pslope = ctx.params
+        dests = [_direct(p) for p in (pW1, pW2, pb1, pb2, pA, pT, pg1, pbe1, pg2, pbe2, pslope)]
+        # dA and dT take one second-stage launch when they are adjacent (as in the bucket): both direct or both temporary
+        if dests[4] is None or dests[5] is None:
+            dests[4] = dests[5] = None
+        shapes = (W1.shape, W2.shape, (CO,), (CO,), A.shape, T.shape, (CO,), (CO,), (CO,), (CO,), (1,))
+        need = [(i, int(torch.Size(sh).numel())) for i, sh in enumerate(shapes) if dests[i] is None]
+        offs = [(2 * (3 * CO + 1) + 3) // 4 * 4]
+        for _, n in need:
             offs.append(offs[-1] + (n + 3) // 4 * 4)
         zbuf = torch.zeros(offs[-1], device=X.device, dtype=torch.float32)
-        seg = [zbuf[offs[i]:offs[i] + n] for i, n in enumerate(sizes)]
-        red = seg[0].view(torch.float64)
+        red = zbuf[:2 * (3 * CO + 1)].view(torch.float64)
+        out = list(dests)
+        for k, (i, n) in enumerate(need):
+            out[i] = zbuf[offs[k]:offs[k] + n].view(shapes[i])
+        dW1, dW2, db1, db2, dA, dT, dg1, dbe1, dg2, dbe2, dslope = out
         dy1 = torch.empty_like(y1)
         dy2 = torch.empty_like(y2)
         dG = torch.empty_like(X)
         dXres = torch.empty_like(X)
-        dW1, dW2, db1, db2 = seg[1].view_as(W1), seg[2].view_as(W2), seg[3], seg[4]
         tc = getattr(c, 'train_impl', 1) == 1
         c.check(lib.coskad_train_bn_prelu_bwd(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
                                               g1.data_ptr(), be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(),
                                               B, CO, red.data_ptr(), None if tc else dy1.data_ptr(),
                                               None if tc else dy2.data_ptr(), st), 'coskad_train_bn_prelu_bwd')
+        c.check(lib.coskad_train_bn_param_grads(c.h, red.data_ptr(), CO, dg1.data_ptr(), dbe1.data_ptr(), dg2.data_ptr(),
+                                                dbe2.data_ptr(), dslope.data_ptr(), st), 'coskad_train_bn_param_grads')
         if tc:      # BatchNorm / PReLU backward applied inside the tensor-core data-gradient kernel
             c.check(lib.coskad_train_mix_bwd_tc(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(), g1.data_ptr(),
                                                 be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(), red.data_ptr(),
@@ -123,14 +148,24 @@ class _LayerFn(torch.autograd.Function):
                                              W2.data_ptr(), B, CI, CO, dG.data_ptr(), dXres.data_ptr(), dW1.data_ptr(),
                                              db1.data_ptr(), dW2.data_ptr(), db2.data_ptr(), st), 'coskad_train_mix_bwd')
         dX = torch.empty_like(X)
-        dA, dT = seg[5].view_as(A), seg[6].view_as(T)
         c.check(lib.coskad_train_contract_bwd(c.h, dG.data_ptr(), dXres.data_ptr(), X.data_ptr(), G1.data_ptr(),
                                               A.data_ptr(), T.data_ptr(), B * CI, dX.data_ptr(), dA.data_ptr(),
                                               dT.data_ptr(), st), 'coskad_train_contract_bwd')
-        redf = red.to(torch.float32)
-        dbeta = redf[:CO]
-        return (dX, dA, dT, dW1, db1 if ctx.has_b[0] else None, redf[CO:2 * CO], dbeta,
-                dW2, db2 if ctx.has_b[1] else None, redf[2 * CO:3 * CO], dbeta.clone(), redf[3 * CO:3 * CO + 1], None, None)
+
+        def ret(i, present=True):       # None: the kernels already accumulated into .grad (or the input does not exist)
+            return out[i] if (present and dests[i] is None) else None
+        return (dX, ret(4), ret(5), ret(0), ret(2, ctx.has_b[0]), ret(6), ret(7),
+                ret(1), ret(3, ctx.has_b[1]), ret(8), ret(9), ret(10), None, None)
+
+
+def _nbt_ptr(bn, device):
+    """device pointer of ``num_batches_tracked`` (int64 scalar) or None: the finalize kernel increments it"""
+    t = getattr(bn, 'num_batches_tracked', None)
+    if t is None:
+        return None
+    if t.device != device or t.dtype != torch.int64:
+        raise _lib.CoskadError(f'num_batches_tracked must be an int64 tensor on {device}, got {t.dtype} on {t.device}')
+    return t.data_ptr()
 
 
 def _check_params(*tensors) -> None:
@@ -168,6 +203,7 @@ class _LinearReduceFn(torch.autograd.Function):
                                           out.data_ptr(), _lib.stream_ptr(H.device)), 'coskad_train_linear(0)')
         ctx.save_for_backward(H, W)
         ctx.has_bias = bias is not None
+        ctx.params = (W, bias)
         return out
 
     @staticmethod
@@ -181,14 +217,16 @@ class _LinearReduceFn(torch.autograd.Function):
         dH = torch.empty_like(H)
         c.check(c.lib.coskad_train_linear(c.h, 1, dz.data_ptr(), None, W.data_ptr(), 0, None, B, F, D, dH.data_ptr(), st),
                 'coskad_train_linear(1)')
-        dW = torch.zeros_like(W)
+        pW, pb = ctx.params
+        gW, gb = _direct(pW), _direct(pb)
+        dW = gW if gW is not None else torch.zeros_like(W)
         c.check(c.lib.coskad_train_linear(c.h, 2, dz.data_ptr(), H.data_ptr(), None, 0, None, B, F, D, dW.data_ptr(), st),
                 'coskad_train_linear(2)')
         db = None
         if ctx.has_bias:
-            db = torch.zeros(D, device=H.device, dtype=torch.float32)
+            db = gb if gb is not None else torch.zeros(D, device=H.device, dtype=torch.float32)
             c.check(c.lib.coskad_train_col_sum(c.h, dz.data_ptr(), B, D, db.data_ptr(), st), 'coskad_train_col_sum')
-        return dH, dW, db
+        return dH, (None if gW is not None else dW), (None if gb is not None else db)
 
 
 class _LinearExpandFn(torch.autograd.Function):
@@ -205,6 +243,7 @@ class _LinearExpandFn(torch.autograd.Function):
                                           out.data_ptr(), _lib.stream_ptr(z.device)), 'coskad_train_linear(1)')
         ctx.save_for_backward(z, W)
         ctx.has_bias = bias is not None
+        ctx.params = (W, bias)
         return out
 
     @staticmethod
@@ -218,14 +257,16 @@ class _LinearExpandFn(torch.autograd.Function):
         dz = torch.empty_like(z)
         c.check(c.lib.coskad_train_linear(c.h, 0, None, dH.data_ptr(), W.data_ptr(), 1, None, B, F, D, dz.data_ptr(), st),
                 'coskad_train_linear(0)')
-        dW = torch.zeros_like(W)
+        pW, pb = ctx.params
+        gW, gb = _direct(pW), _direct(pb)
+        dW = gW if gW is not None else torch.zeros_like(W)
         c.check(c.lib.coskad_train_linear(c.h, 2, z.data_ptr(), dH.data_ptr(), None, 1, None, B, F, D, dW.data_ptr(), st),
                 'coskad_train_linear(2)')
         db = None
         if ctx.has_bias:
-            db = torch.zeros(F, device=z.device, dtype=torch.float32)
+            db = gb if gb is not None else torch.zeros(F, device=z.device, dtype=torch.float32)
             c.check(c.lib.coskad_train_col_sum(c.h, dH.data_ptr(), B, F, db.data_ptr(), st), 'coskad_train_col_sum')
-        return dz, dW, db
+        return dz, (None if gW is not None else dW), (None if gb is not None else db)
 
 
 def linear_reduce(H, W, bias):

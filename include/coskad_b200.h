@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define COSKAD_ABI_VERSION 1
+#define COSKAD_ABI_VERSION 2
 
 typedef struct coskad_ctx coskad_ctx;
 
@@ -217,9 +217,16 @@ int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const 
                          const float* W2, const float* b2, int64_t B, int CI, int CO, float* y1, float* y2,
                          double* stats, void* stream);
 /* mi[4*CO] = mean1, invstd1, mean2, invstd2 (biased variance, eps); running stats updated like nn.BatchNorm2d
- * (momentum, unbiased variance); n_per_channel = B*204 */
+ * (momentum, unbiased variance); n_per_channel = B*204; nbt1 / nbt2 (nullable): the two num_batches_tracked counters
+ * (int64 device scalars), incremented by one.  replaces: nn.BatchNorm2d(train) forward bookkeeping, stsgcn.py:62,79 */
 int coskad_train_bn_finalize(coskad_ctx* ctx, const double* stats, int64_t n_per_channel, int CO, float eps,
-                             float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi, void* stream);
+                             float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi, int64_t* nbt1,
+                             int64_t* nbt2, void* stream);
+/* parameter gradients of the layer's two BatchNorms and its PReLU from `red` (coskad_train_bn_prelu_bwd), ACCUMULATED into
+ * dg1 / dbe1 / dg2 / dbe2 [CO] and dslope [1] (each nullable): d beta1 = d beta2 = red[0..CO), d gamma1 = red[CO..2CO),
+ * d gamma2 = red[2CO..3CO), d slope = red[3CO].  replaces: autograd of nn.BatchNorm2d / nn.PReLU parameters, stsgcn.py:62,79,82 */
+int coskad_train_bn_param_grads(coskad_ctx* ctx, const double* red, int CO, float* dg1, float* dbe1, float* dg2,
+                                float* dbe2, float* dslope, void* stream);
 /* out = PReLU(BN1(y1) + BN2(y2))   (stsgcn.py:106-110) */
 int coskad_train_bn_prelu_fwd(coskad_ctx* ctx, const float* y1, const float* y2, const float* mi, const float* g1,
                               const float* be1, const float* g2, const float* be2, const float* slope, int64_t B, int CO,

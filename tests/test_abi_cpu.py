@@ -28,7 +28,7 @@ def test_binding_table_covers_header(built_lib):
     from coskad_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.coskad_abi_version() == 1
+    assert lib.coskad_abi_version() == 2
 
 
 def test_sm100_code_only(built_lib):

@@ -5,6 +5,7 @@
     torchrun --nproc-per-node N tools/train_bench.py             data parallel: flat NCCL gradient all-reduce per step, max over ranks
     COSKAD_TB_NOAR=1 / COSKAD_TB_FOREACH=1                       A/B switches: skip the all-reduce / for-each instead of fused Adam
     COSKAD_TRAIN_IMPL=0                                          A/B: the FP32 CUDA-core convolution kernels instead of tcgen05
+    COSKAD_TB_NODIRECT=1                                         A/B: gradients handed to autograd instead of accumulated into the bucket views
 """
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -34,6 +35,7 @@ x = torch.empty(B, 2, 12, 17, device=dev)
 synth.synth_windows_(x, g)
 c = torch.zeros(16, device=dev); c[0] = 0.1
 acc = gmath.center_accumulator(16, dev)
+DIRECT = not os.environ.get('COSKAD_TB_NODIRECT')         # A/B: COSKAD_TB_NODIRECT=1 = gradients through autograd's AccumulateGrad
 
 def step():
     hidden = m(x)
@@ -41,7 +43,8 @@ def step():
     dist_c, hid = gmath.poincare_score(hidden, c, True)
     gmath.center_partial(hid, acc, _lib.SCORE_POINCARE)
     loss = dist_c.mean() + 1e-6 * reg
-    opt.zero_grad(set_to_none=True)
+    if DIRECT: bucket.zero_()                             # attached bucket (trainer.TrainStep): kernels accumulate into the .grad views
+    else: opt.zero_grad(set_to_none=True)
     loss.backward()
     if not os.environ.get('COSKAD_TB_NOAR'):
         bucket.allreduce_()                               # flat NCCL all-reduce of the gradients (no-op on one GPU)
@@ -84,4 +87,4 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=28, max_name_column_width=60))
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=60))
