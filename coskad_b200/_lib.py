@@ -50,6 +50,9 @@ SIGNATURES = {
     'coskad_poincare_score_bwd': (C.c_int, [c_ctx_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     'coskad_center_partial': (C.c_int, [c_ctx_p, C.c_int, c_float_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     'coskad_center_finalize': (C.c_int, [c_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_float, c_float_p, C.c_void_p]),
+    'coskad_mahalanobis': (C.c_int, [c_ctx_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
+    'coskad_mahalanobis_bwd': (C.c_int, [c_ctx_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_int, c_float_p, C.c_void_p]),
+    'coskad_cov_partial': (C.c_int, [c_ctx_p, c_float_p, c_float_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     'coskad_frame_aggregate': (C.c_int, [c_ctx_p, c_float_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -362,12 +362,14 @@ def windows_based_loss_hy(hidden_c, hidden_out_fig, frames_fig, n_frames, loss_f
     return _scatter(loss, frames_fig, n_frames)
 
 
-def windows_based_loss_mahalanobis(*_args, **_kwargs):
-    """utils/eval_utils.py:41-55 (Mahalanobis distance to the center with ``inv_cov_matrix``).  No shipped reference config
-    selects ``distance: 'mahalanobis'`` and no kernel implements it: rejected loudly instead of being scored with another
-    distance."""
-    raise NotImplementedError("distance 'mahalanobis' (utils/eval_utils.py:41-55) is not implemented in coskad_b200: no "
-                              "reference config uses it; use 'euclidean' / 'poincare' / the cosine score")
+def windows_based_loss_mahalanobis(hidden_c, hidden_out_fig, VI, frames_fig, n_frames):
+    """utils/eval_utils.py:41-55: per-window Mahalanobis distance to the center with the inverse covariance matrix ``VI``
+    (``coskad_mahalanobis``), scattered to the windows' frames like windows_based_loss_hy"""
+    from . import gmath
+    z = torch.as_tensor(hidden_out_fig, dtype=torch.float32).cuda()
+    c = torch.as_tensor(hidden_c, dtype=torch.float32).cuda().view(-1)
+    vi = torch.as_tensor(VI, dtype=torch.float32).cuda()
+    return _scatter(gmath.mahalanobis_score(z, c, vi), frames_fig, n_frames)
 
 
 def windows_based_loss_rec_and_hy(gt_fig, out_fig, hidden_c, hidden_out_fig, frames_fig, n_frames, loss_fn=None,

@@ -537,6 +537,45 @@ extern "C" int coskad_center_partial(coskad_ctx* ctx, int flavour, const float* 
   return COSKAD_OK;
 }
 
+extern "C" int coskad_mahalanobis(coskad_ctx* ctx, const float* z, const float* center, const float* VI, int64_t B, int D,
+                                  float* out, void* stream_) {
+  CHECK_BD();
+  if (D > kMahD) return fail(ctx, COSKAD_ERR_ARG, "mahalanobis supports D <= %d, got %d", kMahD, D);
+  if (!z || !center || !VI || !out) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  mahalanobis_kernel<<<row_grid(ctx, B), kRowWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(z, center, VI, B, D, out);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_mahalanobis_bwd(coskad_ctx* ctx, const float* z, const float* center, const float* VI, const float* gs,
+                                      int64_t B, int D, float* gz, void* stream_) {
+  CHECK_BD();
+  if (D > kMahD) return fail(ctx, COSKAD_ERR_ARG, "mahalanobis supports D <= %d, got %d", kMahD, D);
+  if (!z || !center || !VI || !gs || !gz) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  mahalanobis_bwd_kernel<<<row_grid(ctx, B), kRowWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(z, center, VI, gs, B, D, gz);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_cov_partial(coskad_ctx* ctx, const float* z, const float* mu, int64_t B, int D, double* acc, void* stream_) {
+  CHECK_BD();
+  if (D > kMahD) return fail(ctx, COSKAD_ERR_ARG, "cov_partial supports D <= %d, got %d", kMahD, D);
+  if (!z || !mu || !acc) return fail(ctx, COSKAD_ERR_ARG, "NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  int g = row_grid(ctx, B);
+  if (g > ctx->sm_count * 2) g = ctx->sm_count * 2;
+  const int n = D * D + 1;
+  { const int rc = ensure_ws(ctx, sizeof(double) * static_cast<size_t>(g) * n); if (rc) return rc; }
+  double* part = reinterpret_cast<double*>(ctx->ws);
+  if (D <= 8) cov_partial_kernel<8><<<g, kRowWarps * 32, 0, st>>>(z, mu, B, D, part);
+  else if (D <= 16) cov_partial_kernel<16><<<g, kRowWarps * 32, 0, st>>>(z, mu, B, D, part);
+  else cov_partial_kernel<32><<<g, kRowWarps * 32, 0, st>>>(z, mu, B, D, part);
+  CK_LAUNCH();
+  cov_partial_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(part, g, n, acc);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
 extern "C" int coskad_center_finalize(coskad_ctx* ctx, int flavour, const double* acc, int D, float eps, float* center,
                                       void* stream_) {
   if (!ctx) return COSKAD_ERR_ARG;

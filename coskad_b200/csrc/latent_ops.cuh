@@ -223,6 +223,89 @@ __global__ void ps_sample_kernel(const float* __restrict__ mu, const float* __re
   }
 }
 
+// ---- Mahalanobis distance to the center (distance: 'mahalanobis') -----------------------------------------------
+// utils/eval_utils.py:28-38 mahalanobis(u, v, VI): sqrt((u - v)^T VI (u - v)) per row, evaluated like the reference's two
+// matmuls: t = (u - v)^T VI first, then t (u - v).  One warp per row, lane = component (D <= 32); VI staged in shared memory.
+constexpr int kMahD = 32;
+__global__ void mahalanobis_kernel(const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ VI,
+                                   int64_t B, int D, float* __restrict__ out) {
+  __shared__ float vi[kMahD][kMahD + 1];
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) vi[i / D][i % D] = VI[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const float cl = lane < D ? c[lane] : 0.f;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    const float d = lane < D ? z[r * D + lane] - cl : 0.f;
+    float t = 0.f;
+    for (int i = 0; i < D; ++i) t = fmaf(__shfl_sync(0xffffffffu, d, i), lane < D ? vi[i][lane] : 0.f, t);
+    const float q = warp_sum(t * d);
+    if (lane == 0) out[r] = sqrtf(q);
+  }
+}
+// gz[r, :] = gs[r] * (VI + VI^T)(z_r - c) / (2 sqrt(q_r))   (autograd of the expression above w.r.t. u; q = 0: zero gradient)
+__global__ void mahalanobis_bwd_kernel(const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ VI,
+                                       const float* __restrict__ gs, int64_t B, int D, float* __restrict__ gz) {
+  __shared__ float vi[kMahD][kMahD + 1];
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) vi[i / D][i % D] = VI[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const float cl = lane < D ? c[lane] : 0.f;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5); r < B; r += wpg) {
+    const float d = lane < D ? z[r * D + lane] - cl : 0.f;
+    float t = 0.f, s = 0.f;                      // t = (d^T VI)[lane], s = (VI d)[lane]
+    for (int i = 0; i < D; ++i) {
+      const float di = __shfl_sync(0xffffffffu, d, i);
+      if (lane < D) { t = fmaf(di, vi[i][lane], t); s = fmaf(di, vi[lane][i], s); }
+    }
+    const float q = warp_sum(t * d);
+    const float f = q > 0.f ? gs[r] / (2.f * sqrtf(q)) : 0.f;
+    if (lane < D) gz[r * D + lane] = f * (t + s);
+  }
+}
+// sum over rows of (x - mu)(x - mu)^T (models/euclidean_encoder_staticCenter.py:40-46 batch_cov_mat_step), shard-additive:
+// one float64 partial [D*D + 1] (the last entry counts the rows) per CTA, added in a fixed order by cov_partial_final_kernel.
+// Lane i of a row's warp owns row i of the outer product; the products are float32 like the reference's matmul.
+template <int DMAX>
+__global__ void cov_partial_kernel(const float* __restrict__ z, const float* __restrict__ mu, int64_t B, int D,
+                                   double* __restrict__ part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float ml = lane < D ? mu[lane] : 0.f;
+  double acc[DMAX];
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) acc[j] = 0.0;
+  double cnt = 0.0;
+  const int64_t wpg = static_cast<int64_t>(gridDim.x) * kRowWarps;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kRowWarps + warp; r < B; r += wpg) {
+    const float d = lane < D ? z[r * D + lane] - ml : 0.f;
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j) acc[j] += static_cast<double>(d * __shfl_sync(0xffffffffu, d, j));
+    cnt += 1.0;
+  }
+  // CTA reduction in warp order (fixed: the partial is bit-reproducible); one [DMAX][33] buffer, the warps add in turn
+  __shared__ double red[DMAX][33];
+  __shared__ double rc;
+  for (int w = 0; w < kRowWarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < DMAX; ++j) red[j][lane] = (w == 0 ? 0.0 : red[j][lane]) + acc[j];
+      if (lane == 0) rc = (w == 0 ? 0.0 : rc) + cnt;
+    }
+    __syncthreads();
+  }
+  double* out = part + static_cast<int64_t>(blockIdx.x) * (D * D + 1);
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) out[e] = red[e % D][e / D];
+  if (threadIdx.x == 0) out[D * D] = rc;
+}
+__global__ void cov_partial_final_kernel(const double* __restrict__ part, int nblk, int n, double* acc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += part[static_cast<int64_t>(b) * n + i];
+  acc[i] += s;
+}
+
 // ---- center partial sums ----------------------------------------------------------------------
 // POINCARE (gmath.weighted_midpoint, weights=None): gamma_i = lambda_x(x_i) = 2 / max(1 - |x_i|^2, 1e-15)
 // evaluated in float32 like the reference; the sums over windows run in float64.

@@ -221,6 +221,73 @@ def dist0(x: torch.Tensor, *, k=-1.0, keepdim: bool = False, dim: int = -1) -> t
     return out.unsqueeze(-1) if keepdim else out
 
 
+# ---- Mahalanobis distance to the center (distance: 'mahalanobis') -----------------------------
+class _MahalanobisFn(torch.autograd.Function):
+    """sqrt((u - c)^T VI (u - c)) per row, differentiable w.r.t. u (the loss of models/euclidean_encoder_staticCenter.py:185)"""
+
+    @staticmethod
+    def forward(ctx, u, c, VI):
+        u2, D = _prep(u, 'u')
+        c2 = c.detach().to(device=u2.device, dtype=torch.float32).contiguous().view(-1)
+        vi = VI.detach().to(device=u2.device, dtype=torch.float32).contiguous()
+        if c2.numel() != D or tuple(vi.shape) != (D, D):
+            raise _lib.CoskadError(f'mahalanobis: u [.., {D}] needs a center [{D}] and VI [{D}, {D}], got {tuple(c.shape)} / {tuple(VI.shape)}')
+        out = torch.empty(u2.shape[0], device=u2.device, dtype=torch.float32)
+        cx = _ctx(u2)
+        cx.check(cx.lib.coskad_mahalanobis(cx.h, u2.data_ptr(), c2.data_ptr(), vi.data_ptr(), u2.shape[0], D, out.data_ptr(),
+                                           _lib.stream_ptr(u2.device)), 'coskad_mahalanobis')
+        ctx.save_for_backward(u2, c2, vi)
+        ctx.shape = u.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gs):
+        u2, c2, vi = ctx.saved_tensors
+        gs = gs.detach().to(torch.float32).contiguous()
+        gz = torch.empty_like(u2)
+        cx = _ctx(u2)
+        cx.check(cx.lib.coskad_mahalanobis_bwd(cx.h, u2.data_ptr(), c2.data_ptr(), vi.data_ptr(), gs.data_ptr(), u2.shape[0],
+                                               u2.shape[1], gz.data_ptr(), _lib.stream_ptr(u2.device)), 'coskad_mahalanobis_bwd')
+        return gz.view(ctx.shape), None, None
+
+
+def mahalanobis_score(u: torch.Tensor, c: torch.Tensor, VI: torch.Tensor) -> torch.Tensor:
+    """per-row distance [B]: ``mahalanobis(u, c, VI, reduce='none')`` of utils/eval_utils.py:28-38 without the two trailing
+    singleton dimensions"""
+    return _MahalanobisFn.apply(u, c, VI)
+
+
+def mahalanobis(u: torch.Tensor, v: torch.Tensor, VI: torch.Tensor, reduce: str = 'mean') -> torch.Tensor:
+    """utils/eval_utils.py:28-38, same signature: ``v`` is the center [D] (or [1, D]); returns the mean distance, or the
+    per-row distances shaped [B, 1, 1] like the reference's matmul result for ``reduce != 'mean'``"""
+    d = mahalanobis_score(u, v.reshape(-1), VI)
+    return d.mean() if reduce == 'mean' else d.view(-1, 1, 1)
+
+
+def cov_accumulator(D: int, device) -> torch.Tensor:
+    """zeroed [D*D + 1] float64 accumulator: the scatter matrix (row-major) and the row count"""
+    return torch.zeros(D * D + 1, dtype=torch.float64, device=device)
+
+
+def cov_partial(z: torch.Tensor, mu: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc += sum_b (z_b - mu)(z_b - mu)^T  (batch_cov_mat_step, models/euclidean_encoder_staticCenter.py:40-46); partial sums
+    of batches and ranks add"""
+    z2, D = _prep(z, 'z')
+    mu2 = mu.detach().to(device=z2.device, dtype=torch.float32).contiguous().view(-1)
+    assert acc.dtype == torch.float64 and acc.numel() == D * D + 1 and acc.is_cuda and mu2.numel() == D
+    cx = _ctx(z2)
+    cx.check(cx.lib.coskad_cov_partial(cx.h, z2.data_ptr(), mu2.data_ptr(), z2.shape[0], D, acc.data_ptr(),
+                                       _lib.stream_ptr(z2.device)), 'coskad_cov_partial')
+
+
+def inv_cov_finalize(acc: torch.Tensor, D: int) -> torch.Tensor:
+    """inverse of the sample covariance ``scatter / (n - 1)`` (compute_inv_cov_mat, models/euclidean_encoder_staticCenter.py:133-142):
+    a D x D inverse once per epoch -- parameter preparation, done by torch.linalg in float32 like the reference"""
+    n = acc[D * D]
+    cov = (acc[:D * D] / (n - 1.0)).to(torch.float32).view(D, D)
+    return torch.inverse(cov)
+
+
 # ---- center update: per-shard partial sums (float64) -> [all-reduce] -> finalize --------------
 def center_accumulator(D: int, device) -> torch.Tensor:
     """zeroed [D+2] float64 accumulator: D sums, the gamma-1 sum, the window count"""

@@ -111,6 +111,12 @@ class LitEncoder(LightningModule):
         self.temp: Optional[torch.Tensor] = None
         self._acc: Optional[torch.Tensor] = None
         self.centers: List[torch.Tensor] = []
+        # distance 'mahalanobis' (models/euclidean_encoder_staticCenter.py:125-142,182-185; Euclidean encoder only): the
+        # scatter matrix of the epoch's latents around the center is accumulated batch by batch (shard-additive float64
+        # sums, all-reduced) instead of caching every latent batch (hidden_out_cache upstream) -- the center is constant
+        # within an epoch, so the two are the same sum
+        self.distance = 'euclidean' if self.hyperbolic else str(getattr(args, 'distance', 'euclidean')).lower()
+        self._cov: Optional[torch.Tensor] = None
 
     # ---------------------------------------------------------------- forward (predict / validation)
     def forward(self, x):
@@ -120,6 +126,17 @@ class LitEncoder(LightningModule):
     @property
     def _flavour(self) -> int:
         return _lib.SCORE_POINCARE if self.hyperbolic else _lib.SCORE_EUCLID
+
+    def _update_inv_cov(self) -> None:
+        """compute_inv_cov_mat (euclidean_encoder_staticCenter.py:133-142) from the accumulated scatter matrix; in place, so a
+        captured training step keeps reading the same buffer"""
+        D = self.model.latent_dim
+        cdist.allreduce_center_acc(self._cov)
+        vi = gmath.inv_cov_finalize(self._cov, D)
+        if self.model.inv_cov_matrix.shape == vi.shape and self.model.inv_cov_matrix.device == vi.device:
+            self.model.inv_cov_matrix.copy_(vi)
+        else:
+            self.model.inv_cov_matrix = vi
 
     def _finalize_center(self, acc: torch.Tensor) -> torch.Tensor:
         cdist.allreduce_center_acc(acc)
@@ -146,6 +163,14 @@ class LitEncoder(LightningModule):
         self.model.c = c
         self.temp = c
         self.centers.append(c.clone())
+        if self.distance == 'mahalanobis':           # second pass: the scatter matrix needs the finished center (:125-126)
+            self._cov = gmath.cov_accumulator(self.model.latent_dim, dev)
+            with torch.no_grad():
+                for batch in loader:
+                    data = (batch[0][0] if getattr(self.args, 'dataset_double_item', False) else batch[0]).to(dev)
+                    z, _ = self.model.encode_score(data)
+                    gmath.cov_partial(z, c, self._cov)
+            self._update_inv_cov()
         self.model.train()
 
     graph_safe = True
@@ -153,6 +178,8 @@ class LitEncoder(LightningModule):
     def on_train_epoch_start(self) -> None:
         if self._acc is not None:
             self._acc.zero_()
+        if self._cov is not None:                     # hidden_out_cache = [] upstream (:157-160)
+            self._cov.zero_()
 
     # ---------------------------------------------------------------- training (:137-188)
     def training_step(self, batch, batch_idx):
@@ -174,13 +201,19 @@ class LitEncoder(LightningModule):
         else:
             if dynamic:
                 gmath.center_partial(hidden_out.detach(), self._acc, _lib.SCORE_EUCLID)
-            loss_main = F.mse_loss(hidden_out, self.model.c.expand_as(hidden_out))
+            if self.distance == 'mahalanobis':       # :182-185
+                gmath.cov_partial(hidden_out.detach(), self.model.c, self._cov)
+                loss_main = gmath.mahalanobis(hidden_out, self.model.c, self.model.inv_cov_matrix)
+            else:
+                loss_main = F.mse_loss(hidden_out, self.model.c.expand_as(hidden_out))
             self.log('hypersphere_loss', loss_main)
         loss = loss_main + self.args.alpha * loss_reg
         self.log('loss', loss)
         return loss
 
     def training_epoch_end(self, outputs) -> None:
+        if self.distance == 'mahalanobis' and self._cov is not None:      # on_train_epoch_end :145-148, before the center moves
+            self._update_inv_cov()
         if self.args.static_center or self._acc is None:
             return
         c = self._finalize_center(self._acc)
@@ -219,6 +252,8 @@ class LitEncoder(LightningModule):
         if self.hyperbolic:
             x = gmath.expmap0(z, k=-1.0) if validation else gmath.expmap0_project(z)
             return gmath.dist(x, c, k=-1.0)
+        if self.distance == 'mahalanobis':           # windows_based_loss_mahalanobis, utils/eval_utils.py:41-55
+            return gmath.mahalanobis_score(z, c, self.model.inv_cov_matrix.to(dev))
         return gmath.euclid_score(z, c)
 
     def post_processing(self, hidden_out, trans, meta, frames, validation: bool = True):

@@ -170,6 +170,21 @@ int coskad_center_partial(coskad_ctx* ctx, int flavour, const float* zproj, int6
 /* eps: center_tolerance clamp of the Euclidean flavour (<=0 disables). */
 int coskad_center_finalize(coskad_ctx* ctx, int flavour, const double* acc, int D, float eps, float* center, void* stream);
 
+/* ---- Mahalanobis distance to the center (distance: 'mahalanobis'; D <= 32) -------------------
+ * out[b] = sqrt((z_b - c)^T VI (z_b - c)), VI [D, D] row-major (the inverse covariance matrix).
+ * replaces: utils/eval_utils.py:28-38 mahalanobis(u, v, VI, reduce='none') as called by
+ * windows_based_loss_mahalanobis (:41-55) and models/euclidean_encoder_staticCenter.py:185 */
+int coskad_mahalanobis(coskad_ctx* ctx, const float* z, const float* center, const float* VI, int64_t B, int D,
+                       float* out, void* stream);
+/* gz[b, :] = gs[b] (VI + VI^T)(z_b - c) / (2 out[b])  -- autograd of the above w.r.t. z (training loss,
+ * models/euclidean_encoder_staticCenter.py:185); rows with a zero distance get a zero gradient */
+int coskad_mahalanobis_bwd(coskad_ctx* ctx, const float* z, const float* center, const float* VI, const float* gs,
+                           int64_t B, int D, float* gz, void* stream);
+/* acc (double)[D*D + 1] += sum_b (z_b - mu)(z_b - mu)^T (row-major) and the row count in acc[D*D]; partial sums of
+ * several batches / shards add (all-reduce them), then cov = acc / (count - 1) and VI = inverse(cov) on the host side.
+ * replaces: batch_cov_mat_step + compute_inv_cov_mat, models/euclidean_encoder_staticCenter.py:40-46,133-142 */
+int coskad_cov_partial(coskad_ctx* ctx, const float* z, const float* mu, int64_t B, int D, double* acc, void* stream);
+
 /* ---- frame-level aggregation ---------------------------------------------------------------
  * Bit-exact replacement of the Python triple loop: for each person scatter score -> frames
  * (index frames-1 with the reference's wrap of frame id 0 -> last frame), treat exact zeros as

@@ -35,7 +35,58 @@ def _stub(name: str) -> types.ModuleType:
     return mod
 
 
-def main() -> None:
+_ONLY = ''
+
+
+def _savez(path: str, **arrays) -> None:
+    """np.savez, restricted to ``<only>_ref.npz`` under --only (the other fixtures stay byte-identical on disk)"""
+    if _ONLY and os.path.basename(path) != f'{_ONLY}_ref.npz':
+        return
+    np.savez(path, **arrays)
+
+
+def _ref_function(path: str, name: str):
+    """one top-level function of a reference file that cannot be imported as a module here (its module imports Lightning):
+    compiled from the reference's own source at generation time -- nothing is copied into this repository"""
+    import ast
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {'torch': torch, 'np': np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), ns)
+    return ns[name]
+
+
+def mahalanobis_fixture(ref_eu) -> None:
+    """distance 'mahalanobis': utils/eval_utils.py:28-55 + models/euclidean_encoder_staticCenter.py:40-46,133-142"""
+    from oracle import mahalanobis as omah
+    ref_cov_step = _ref_function(os.path.join(REF, 'models', 'euclidean_encoder_staticCenter.py'), 'batch_cov_mat_step')
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for D in (8, 16):
+        A = torch.randn(D, D, generator=g) * 0.3 + torch.eye(D)
+        z = torch.randn(700, D, generator=g) @ A.T * 0.2 + 0.05          # correlated latents
+        z[5] = z[6]                                                       # a repeated row
+        mu = z.mean(0)
+        scat_ref = sum(ref_cov_step(z[i:i + 256], mu) for i in range(0, 700, 256))
+        scat_or = sum(omah.batch_cov_mat_step(z[i:i + 256], mu) for i in range(0, 700, 256))
+        assert torch.equal(scat_ref, scat_or), 'oracle.mahalanobis.batch_cov_mat_step differs from the reference'
+        VI = torch.inverse(scat_ref / (700 - 1))                          # compute_inv_cov_mat :142
+        assert torch.equal(VI, omah.inv_cov([z[i:i + 256] for i in range(0, 700, 256)], mu))
+        zq = torch.cat([z[:200], mu.view(1, -1)])                         # the center itself: distance 0
+        d_ref = ref_eu.mahalanobis(zq, mu, VI, reduce='none')
+        assert torch.equal(d_ref, omah.mahalanobis(zq, mu, VI, reduce='none'))
+        assert torch.equal(ref_eu.mahalanobis(zq, mu, VI), omah.mahalanobis(zq, mu, VI))
+        frames = (np.arange(12)[None, :] + np.arange(1, 41)[:, None]).astype(np.int64)
+        pose_ref = ref_eu.windows_based_loss_mahalanobis(mu, zq[:40].numpy(), VI, frames, 60)
+        assert np.array_equal(pose_ref, omah.windows_based_loss_mahalanobis(mu, zq[:40].numpy(), VI, frames, 60))
+        out.update({f'z{D}': z.numpy(), f'mu{D}': mu.numpy(), f'scatter{D}': scat_ref.numpy(), f'VI{D}': VI.numpy(),
+                    f'zq{D}': zq.numpy(), f'dist{D}': d_ref.reshape(-1).numpy(), f'pose{D}': pose_ref, f'frames{D}': frames})
+    _savez(os.path.join(GOLD, 'mahalanobis_ref.npz'), **out)
+
+
+def main(only: str = '') -> None:
+    global _ONLY
+    _ONLY = only
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(4)
     from oracle import aggregate as oagg
@@ -68,7 +119,7 @@ def main() -> None:
     pre = torch.einsum('oc,nctv->notv', w1, g) + torch.einsum('oc,nctv->notv', w2, x) + b[None, :, None, None]
     h1_fold = torch.nn.functional.prelu(pre, sd['encoder.model.0.prelu.weight'])
     assert (h1_fold - h1_ref).abs().max() < 2e-5
-    np.savez(os.path.join(GOLD, 'stse_ref.npz'), x=x.numpy(), z=z_ref.numpy(), h1=h1_ref.numpy(),
+    _savez(os.path.join(GOLD, 'stse_ref.npz'), x=x.numpy(), z=z_ref.numpy(), h1=h1_ref.numpy(),
              sd_checksum=np.float64(sum(float(v.double().sum()) for k, v in sd.items() if v.is_floating_point())))
 
     # training-mode forward + backward of the reference (loss = mean of z^2 as a stand-in upstream grad)
@@ -84,7 +135,7 @@ def main() -> None:
     ref_sd_after = ref.state_dict()
     for k, v in new_stats.items():
         assert (ref_sd_after[k] - v).abs().max() < 1e-6, k
-    np.savez(os.path.join(GOLD, 'stse_train_ref.npz'), x=xt.numpy(), z=zt.detach().numpy(),
+    _savez(os.path.join(GOLD, 'stse_train_ref.npz'), x=xt.numpy(), z=zt.detach().numpy(),
              **{'grad.' + k: v.numpy() for k, v in grads.items() if k in (
                  'encoder.model.0.gcn.A', 'encoder.model.0.gcn.T', 'encoder.model.3.tcn.0.weight',
                  'encoder.model.1.tcn.1.weight', 'encoder.model.2.prelu.weight', 'btlnk.bias',
@@ -106,7 +157,7 @@ def main() -> None:
         z_ae, xh_ae = ref_aem(x)
         z_ae_or, xh_ae_or = onet.stsae_forward(x, sd_ae)
     assert (z_ae - z_ae_or).abs().max() < 1e-6 and (xh_ae - xh_ae_or).abs().max() < 1e-6
-    np.savez(os.path.join(GOLD, 'stsae_ref.npz'), x=x.numpy(), z=z_ae.numpy(), xhat=xh_ae.numpy())
+    _savez(os.path.join(GOLD, 'stsae_ref.npz'), x=x.numpy(), z=z_ae.numpy(), xhat=xh_ae.numpy())
 
     # ---- utils/hyper_math.py (the pinned geometry flavour) ----------------------------------------
     g_ = torch.Generator().manual_seed(5)
@@ -119,13 +170,13 @@ def main() -> None:
     assert torch.allclose(e_ref, ohm.expmap0(u)) and torch.allclose(p_ref, ohm.project(e_ref))
     assert torch.allclose(d_ref, ohm.dist(p_ref, cen.expand_as(p_ref)), rtol=1e-6, atol=1e-7)
     assert torch.allclose(m_ref, ohm.poincare_mean(p_ref[:40] * 0.5), rtol=1e-6, atol=1e-7)
-    np.savez(os.path.join(GOLD, 'geometry_hyper_math.npz'), u=u.numpy(), center=cen.numpy(), expmap0=e_ref.numpy(),
+    _savez(os.path.join(GOLD, 'geometry_hyper_math.npz'), u=u.numpy(), center=cen.numpy(), expmap0=e_ref.numpy(),
              project=p_ref.numpy(), dist=d_ref.numpy(), mean=m_ref.numpy())
     # restated geoopt (UNPINNED) -- stored so the CUDA tests have fixed vectors; these are oracle outputs
     k = torch.tensor(-1.)
     e_g = ogm.expmap0(u, k=k)
     p_g = ogm.project(e_g, k=k)
-    np.savez(os.path.join(GOLD, 'geometry_geoopt_restated.npz'), u=u.numpy(), center=cen.numpy(), expmap0=e_g.numpy(),
+    _savez(os.path.join(GOLD, 'geometry_geoopt_restated.npz'), u=u.numpy(), center=cen.numpy(), expmap0=e_g.numpy(),
              project=p_g.numpy(), dist=ogm.dist(p_g, cen, k=k).numpy(), dist_cx=ogm.dist(cen, p_g, k=k).numpy(),
              dist0=ogm.dist0(p_g, k=k).numpy(), midpoint=ogm.weighted_midpoint(p_g, k=k).numpy())
 
@@ -174,9 +225,12 @@ def main() -> None:
     # pad_scores
     fr = np.array([0, 0, 0, .5, .4, 0, 0, 0, 0, 0, .2, .1, 0, 0, 0, 0, 0, 0, 0, 0.])
     assert np.array_equal(ref_eu.pad_scores(fr.copy(), np.zeros(20), 2), oagg.pad_scores(fr.copy(), np.zeros(20), 2))
-    np.savez(os.path.join(GOLD, 'aggregate_ref.npz'), scores=scores, trans=trans, meta=meta, frames=frames,
+    _savez(os.path.join(GOLD, 'aggregate_ref.npz'), scores=scores, trans=trans, meta=meta, frames=frames,
              clips=np.asarray(clips, dtype=np.int64), curves=np.concatenate(ref_curves),
              pad_in=fr, pad_out=ref_eu.pad_scores(fr.copy(), np.zeros(20), 2))
+    mahalanobis_fixture(ref_eu)
+    if only == 'mahalanobis':
+        return
     # ---- window construction + test-time transforms (utils/dataset_utils.py, utils/preprocessing.py, utils/dataset.py) ----
     from oracle import windows as owin
     import utils.dataset_utils as ref_du      # noqa: E402  (reference)
@@ -196,7 +250,7 @@ def main() -> None:
     ref_tr = np.stack([np.stack([t(np.array(w)) for w in segs], 0) for t in ref_du.ae_trans_list], 0)    # [5, N, 3, 12, 17]
     or_tr = np.stack([np.stack([owin.apply_pose_transform(w, m) for w in segs], 0) for m in owin.ae_trans_mats()], 0)
     assert np.array_equal(ref_tr, or_tr), 'oracle.windows apply_pose_transform differs from the reference'
-    np.savez(os.path.join(GOLD, 'windows_ref.npz'), traj=traj, starts=starts, mats=ref_mats, windows=segs[:, :2],
+    _savez(os.path.join(GOLD, 'windows_ref.npz'), traj=traj, starts=starts, mats=ref_mats, windows=segs[:, :2],
              transformed=ref_tr[:, :, :2].astype(np.float32))
     print('golden fixtures written to', GOLD)
     for fn in sorted(os.listdir(GOLD)):
@@ -204,4 +258,5 @@ def main() -> None:
 
 
 if __name__ == '__main__':
-    main()
+    # --only mahalanobis: (re)generate tests/golden/mahalanobis_ref.npz and stop (the other fixtures stay byte-identical)
+    main(sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else '')

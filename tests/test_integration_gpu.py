@@ -79,6 +79,53 @@ def test_train_eval_auc_parity(tmp_path, hyperbolic, static_center):
     assert set(per_t) == {0, 1}
 
 
+def test_mahalanobis_distance_task(tmp_path):
+    """distance: 'mahalanobis' on the Euclidean static-center encoder (models/euclidean_encoder_staticCenter.py:125-142,182-185,
+    268-270): inv_cov_matrix after setup / every epoch = inverse sample covariance of the training latents around the center,
+    the loss falls, and the eval scores are the reference's Mahalanobis distances (AUC to 4 decimals)"""
+    from sklearn.metrics import roc_auc_score
+    from coskad_b200 import tasks
+    from coskad_b200.data import get_dataset_and_loader
+    from coskad_b200.trainer import Trainer
+    from oracle import mahalanobis as omah
+    torch.manual_seed(0)
+    args, ae_args, *_ = _args(tmp_path, hyperbolic=False, static_center=True, distance='mahalanobis', ae_epochs=0)
+    train_ds, train_loader = get_dataset_and_loader(ae_args, 'train')
+    test_ds, test_loader = get_dataset_and_loader(ae_args, 'test')
+    args.gt_table = (test_ds.clips, test_ds.gts)
+    model = tasks.select_task(args)(args)
+    assert model.distance == 'mahalanobis' and 'model.inv_cov_matrix' in model.state_dict()
+    Trainer(max_epochs=0, verbose=False).fit(model, train_loader)              # setup('fit') only
+    sd = {k[len('model.'):]: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith('model.')}
+    with torch.no_grad():
+        z_tr = onet.stse_forward(train_ds.x, sd)
+    vi_ref = omah.inv_cov([z_tr[i:i + 256] for i in range(0, z_tr.shape[0], 256)], sd['c'])
+    vi = model.model.inv_cov_matrix.cpu()
+    assert float((vi - vi_ref).abs().max()) <= 5e-3 * float(vi_ref.abs().max()), (vi, vi_ref)
+    # training: three epochs, the Mahalanobis loss goes down and the matrix is refreshed from the epoch's latents
+    args.ae_epochs = 3
+    trainer = Trainer(max_epochs=3, verbose=False)
+    trainer.fit(model, train_loader, test_loader)
+    h = trainer.history
+    assert len(h) == 3 and all(np.isfinite(e['train_loss_mean']) for e in h) and h[-1]['loss'] < h[0]['loss'], h
+    assert not torch.equal(model.model.inv_cov_matrix.cpu(), vi)
+    # eval scores vs the oracle pipeline on the same weights / center / matrix
+    sd = {k[len('model.'):]: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith('model.')}
+    model.eval()
+    with torch.no_grad():
+        z_te = onet.stse_forward(test_ds.x, sd)
+        s_ref = omah.mahalanobis(z_te, sd['c'], sd['inv_cov_matrix'], reduce='none').view(-1)
+        s = model.window_scores(model.model(test_ds.x.cuda()))
+    assert float(((s.cpu() - s_ref).abs() / s_ref.abs()).max()) <= 1e-4
+    nt = args.dataset_num_transform
+    auc = model.post_processing(model.model(test_ds.x.cuda()), test_ds.trans, test_ds.meta, test_ds.frames, validation=False)
+    curves = oagg.aggregate_dataset(s_ref.numpy(), test_ds.trans.numpy(), test_ds.meta.numpy(), test_ds.frames.numpy(),
+                                    test_ds.clips, nt)
+    gt = np.concatenate([test_ds.gts[(s_, c_)] for s_, c_, _ in test_ds.clips])
+    pds = np.mean(np.stack([np.concatenate(curves[t]) for t in range(nt)], 0), 0)
+    assert round(auc, 4) == round(float(roc_auc_score(gt, pds)), 4)
+
+
 def test_center_init_matches_reference_semantics(tmp_path):
     """setup('fit'): c = weighted_midpoint(project(expmap0(z))) over ALL training windows (hyperbolic_encoder.py:101-123)"""
     from coskad_b200 import tasks

@@ -162,3 +162,61 @@ def test_frame_aggregation_random_datasets(seed):
     for t in range(3):
         for a, b in zip(out[t], ref[t]):
             assert np.array_equal(a, b)
+
+
+# ---- distance: 'mahalanobis' (utils/eval_utils.py:28-55, models/euclidean_encoder_staticCenter.py:40-46,133-142) -----------
+@pytest.mark.parametrize('D', [8, 16])
+def test_mahalanobis_matches_reference_fixture(golden_dir, D):
+    """tests/golden/mahalanobis_ref.npz holds outputs of the reference's own mahalanobis / windows_based_loss_mahalanobis /
+    batch_cov_mat_step (oracle/gen_golden.py)"""
+    from coskad_b200 import aggregate, gmath
+    g = np.load(os.path.join(golden_dir, 'mahalanobis_ref.npz'))
+    z, mu, VI = (torch.from_numpy(g[f'{k}{D}']).cuda() for k in ('z', 'mu', 'VI'))
+    zq = torch.from_numpy(g[f'zq{D}']).cuda()
+    ref = torch.from_numpy(g[f'dist{D}'])
+    got = gmath.mahalanobis_score(zq, mu, VI)
+    # the last row IS the center: the reference's two matmuls give exactly 0 there and so does the kernel
+    assert float(got[-1]) == 0.0 and float(ref[-1]) == 0.0
+    _close(got[:-1], ref[:-1], 1e-4, 0.0)                                   # pure relative, like the score gate
+    _close(gmath.mahalanobis(zq, mu, VI), ref.mean(), 1e-5, 0.0)
+    assert gmath.mahalanobis(zq, mu, VI, reduce='none').shape == (zq.shape[0], 1, 1)
+    # scatter matrix: shard-additive float64 sums of float32 products vs the reference's float32 matmul + sum
+    acc = gmath.cov_accumulator(D, z.device)
+    for i in range(0, z.shape[0], 256):
+        gmath.cov_partial(z[i:i + 256], mu, acc)
+    assert float(acc[D * D]) == z.shape[0]
+    scat = torch.from_numpy(g[f'scatter{D}']).double()
+    got_s = acc[:D * D].view(D, D).cpu()
+    assert float((got_s - scat).abs().max()) <= 2e-5 * float(scat.abs().max())
+    whole = gmath.cov_accumulator(D, z.device)
+    gmath.cov_partial(z, mu, whole)
+    assert float((whole - acc).abs().max()) <= 1e-9 * float(acc.abs().max())          # partial sums of shards add
+    # the host-side inverse of an SPD 8x8 / 16x16 matrix amplifies input rounding by its condition number
+    vi = gmath.inv_cov_finalize(acc, D).cpu()
+    assert float((vi - VI.cpu()).abs().max()) <= 2e-3 * float(VI.abs().max())
+    # compat surface: same float64 [w, n_frames] matrix as the reference's per-window loop
+    pose = aggregate.windows_based_loss_mahalanobis(mu, g[f'zq{D}'][:40], VI, g[f'frames{D}'], 60)
+    ref_pose = g[f'pose{D}']
+    assert pose.dtype == np.float64 and pose.shape == ref_pose.shape and np.array_equal(pose != 0, ref_pose != 0)
+    assert np.allclose(pose, ref_pose, rtol=1e-4, atol=0.0)
+
+
+def test_mahalanobis_backward_matches_oracle_autograd(golden_dir):
+    from coskad_b200 import gmath
+    from oracle import mahalanobis as omah
+    g = np.load(os.path.join(golden_dir, 'mahalanobis_ref.npz'))
+    z = torch.from_numpy(g['z16'][:300]).double().requires_grad_(True)
+    mu, VI = torch.from_numpy(g['mu16']).double(), torch.from_numpy(g['VI16']).double()
+    w = torch.linspace(0.5, 1.5, 300, dtype=torch.float64)
+    (omah.mahalanobis(z, mu, VI, reduce='none').view(-1) * w).sum().backward()
+    zc = torch.from_numpy(g['z16'][:300]).cuda().requires_grad_(True)
+    (gmath.mahalanobis_score(zc, mu.float().cuda(), VI.float().cuda()) * w.float().cuda()).sum().backward()
+    err = (zc.grad.cpu().double() - z.grad).abs()
+    assert float(err.max()) <= 1e-4 * float(z.grad.abs().max()), float(err.max())
+    # a non-symmetric VI: the gradient is (VI + VI^T) d / (2 dist), not VI d / dist
+    VIa = VI + 0.05 * torch.randn(16, 16, dtype=torch.float64, generator=torch.Generator().manual_seed(3)).triu(1)
+    z2 = torch.from_numpy(g['z16'][:64]).double().requires_grad_(True)
+    omah.mahalanobis(z2, mu, VIa).backward()
+    zc2 = torch.from_numpy(g['z16'][:64]).cuda().requires_grad_(True)
+    gmath.mahalanobis(zc2, mu.float().cuda(), VIa.float().cuda()).backward()
+    assert float((zc2.grad.cpu().double() - z2.grad).abs().max()) <= 1e-4 * float(z2.grad.abs().max())
