@@ -101,20 +101,27 @@ def ps_sample(mu: torch.Tensor, t: torch.Tensor, v: torch.Tensor) -> torch.Tenso
 
 
 class STSVAE(STSAE):
-    """models/sts/vae.py:13-169 with distribution 'ps' (the configured one, config/UBnormal/spherical_vae.yaml:45)"""
+    """models/sts/vae.py:13-169: distribution 'ps' (PowerSpherical, the configured one, config/UBnormal/spherical_vae.yaml:45)
+    or 'normal' (diagonal Gaussian: fc_var has latent_dim outputs, Z_mean is not normalised, vae.py:79-85,107-108,160-169)"""
 
     def __init__(self, input_dim, layer_channels, hidden_dimension, latent_dim, n_frames, n_joints, encoder_type='sts_gcn',
                  projector='linear', distance='euclidean', dropout=0.0, bias=True, device='cpu', *,
                  projector_hidden_layers=None, distribution='ps'):
         self.distribution = distribution.lower()
-        if self.distribution != 'ps':
-            raise NotImplementedError("only distribution 'ps' (PowerSpherical) is implemented -- the configured one")
+        if self.distribution not in ('ps', 'normal'):
+            raise ValueError(f'Distribution {self.distribution} not supported.')                      # vae.py:166
+        if self.distribution == 'normal' and 2 * latent_dim > 16:
+            raise NotImplementedError("distribution 'normal': the fused head holds 16 rows (fc_mean + fc_var = 2 * latent_dim), "
+                                      f'latent_dim {latent_dim} needs {2 * latent_dim}')
         super().__init__(input_dim, layer_channels, hidden_dimension, latent_dim, n_frames, n_joints, encoder_type,
                          projector, distance, dropout, bias, device, projector_hidden_layers=projector_hidden_layers)
-        self.mean_vector = None      # plain attribute for 'ps' upstream (spherical_vae.py:113), not a buffer
+        if self.distribution == 'ps':
+            self.mean_vector = None      # plain attribute for 'ps' upstream (spherical_vae.py:113), not a buffer
 
     def build_model(self) -> None:
         super().build_model()
+        if self.distribution == 'normal':            # a buffer for 'normal', a plain attribute for 'ps' (vae.py:56-58)
+            self.register_buffer('mean_vector', torch.zeros((1, self.latent_dim)))
         self.register_buffer('threshold_dist', torch.tensor(0, dtype=torch.float32))
 
     def _set_projector_type(self) -> None:
@@ -123,13 +130,13 @@ class STSVAE(STSAE):
         self.btlnk = nn.Identity()
         input_size = self.hidden_dimension * self.n_frames * self.n_joints
         self.fc_mean = nn.Linear(in_features=input_size, out_features=self.latent_dim)
-        self.fc_var = nn.Linear(in_features=input_size, out_features=1)
+        self.fc_var = nn.Linear(in_features=input_size, out_features=self.latent_dim if self.distribution == 'normal' else 1)
 
     def _head(self):
         w = torch.cat([self.fc_mean.weight, self.fc_var.weight], dim=0).detach().contiguous()
         b = torch.cat([self.fc_mean.bias, self.fc_var.bias], dim=0).detach().contiguous()
         self._head_keepalive = (w, b)
-        return w, b, self.latent_dim + 1
+        return w, b, w.shape[0]                       # 'ps': latent_dim + 1 rows, 'normal': 2 * latent_dim
 
     def _sync_encoder(self, ctx) -> None:
         src = [self.fc_mean.weight, self.fc_mean.bias, self.fc_var.weight, self.fc_var.bias]
@@ -148,23 +155,35 @@ class STSVAE(STSAE):
         if self.training:
             H = train.encoder_features(self, X, True)
             raw = train.linear_reduce(H, self.fc_mean.weight, self.fc_mean.bias)
-            Z_mean = raw / torch.norm(raw, dim=-1, keepdim=True)                                   # vae.py:81
+            Z_mean = raw / torch.norm(raw, dim=-1, keepdim=True) if self.distribution == 'ps' else raw   # vae.py:80-81
             Z_var = F.softplus(train.linear_reduce(H, self.fc_var.weight, self.fc_var.bias)) + 1   # vae.py:85
         else:
             raw9, _ = self.encode_score(X, _lib.SCORE_NONE)
-            Z_mean = gmath.l2_normalize(raw9[:, :self.latent_dim].contiguous())
+            Z_mean = raw9[:, :self.latent_dim].contiguous()
+            if self.distribution == 'ps':
+                Z_mean = gmath.l2_normalize(Z_mean)
             Z_var = F.softplus(raw9[:, self.latent_dim:]) + 1
         if return_shape:
             return Z_mean, Z_var, torch.Size([X.shape[0], self.hidden_dimension, self.n_frames, self.n_joints, 1])
         return Z_mean, Z_var
 
     def reparameterize(self, Z_mean, Z_var):
+        if self.distribution == 'normal':            # vae.py:107-109 (Z_var is used as the scale)
+            return (torch.distributions.normal.Normal(Z_mean, Z_var),
+                    torch.distributions.normal.Normal(torch.zeros_like(Z_mean), torch.ones_like(Z_var)))
         return PowerSphericalQ(loc=Z_mean, scale=torch.squeeze(Z_var, dim=-1)), HypersphericalUniformP(self.latent_dim - 1)
+
+    @staticmethod
+    def _rsample(q_Z, noise=None):
+        """one reparameterised sample; ``noise``: the standard-normal draw ('normal') or the (t, v) pair ('ps')"""
+        if isinstance(q_Z, torch.distributions.normal.Normal):
+            return q_Z.rsample() if noise is None else q_Z.loc + q_Z.scale * noise
+        return q_Z.rsample(noise=noise)
 
     def forward(self, X: torch.Tensor, noise=None):
         Z_mean, Z_var = self.encode(X)
         q_Z, p_Z = self.reparameterize(Z_mean, Z_var)
-        Z = q_Z.rsample(noise=noise)
+        Z = self._rsample(q_Z, noise)
         Xh = train.decode_forward(self, Z, self.training)
         return Z, Xh, (q_Z, p_Z, Z_var)
 
@@ -172,11 +191,13 @@ class STSVAE(STSAE):
     def cosine_scores(self, X: torch.Tensor, mean_vector: Optional[torch.Tensor] = None, sample: bool = False, noise=None):
         """eval score 1 - cos(mean_vector, Z); sample=False scores Z_mean with the fused kernel's cosine flavour"""
         mv = (self.mean_vector if mean_vector is None else mean_vector).view(-1)
-        if not sample:
+        if not sample and self.distribution == 'ps':
             _, s = self.encode_score(X, _lib.SCORE_COSINE, center=mv, want_latent=False)
             return s
+        if not sample:       # 'normal': the fused head holds 2 * latent_dim rows (mean | scale); score the mean rows
+            return gmath.cosine_score(self.encode(X)[0], mv.to(X.device))
         Z_mean, Z_var = self.encode(X)
-        Z = self.reparameterize(Z_mean, Z_var)[0].rsample(noise=noise)
+        Z = self._rsample(self.reparameterize(Z_mean, Z_var)[0], noise)
         return gmath.cosine_score(Z, mv.to(Z.device))
 
 
@@ -218,7 +239,10 @@ class LitSphericalVAE(LightningModule):
         if self._acc is None:
             self._acc = gmath.center_accumulator(self.model.latent_dim, data.device)
         gmath.center_partial(hidden_out.detach(), self._acc, _lib.SCORE_COSINE)      # replaces latent_cache (:88)
-        loss_kl = kl_divergence(q, p).mean()
+        if self.distribution == 'normal':            # spherical_vae.py:89-92
+            loss_kl = torch.distributions.kl.kl_divergence(q, p).sum(-1).mean()
+        else:
+            loss_kl = kl_divergence(q, p).mean()
         loss_rec = F.mse_loss(reconstructed_x, data)
         loss_reg = calc_reg_loss(self.model)
         loss_exp_dist = (1 / z_var).mean()
@@ -233,7 +257,11 @@ class LitSphericalVAE(LightningModule):
         if self._acc is None:
             return
         cdist.allreduce_center_acc(self._acc)
-        self.model.mean_vector = gmath.center_finalize(self._acc, self.model.latent_dim, _lib.SCORE_COSINE).view(1, -1)
+        mv = gmath.center_finalize(self._acc, self.model.latent_dim, _lib.SCORE_COSINE).view(1, -1)
+        if self.distribution == 'normal' and torch.is_tensor(self.model.mean_vector) and self.model.mean_vector.device == mv.device:
+            self.model.mean_vector.copy_(mv)          # a registered buffer for 'normal' (vae.py:57): stays in the state_dict
+        else:
+            self.model.mean_vector = mv
         if self.warmup_counter > 0:
             self.warmup_counter -= 1
         self._acc = None

@@ -17,6 +17,10 @@ What it restates (reference paths are relative to the upstream COSKAD tree):
 * ``oracle.power_spherical`` -- nicola-decao/power_spherical (unpinned, un-vendored ->
                             **parity unpinned**)
 * ``oracle.aggregate``   -- utils/eval_utils.py:57-106 + eval_COSKAD.py:140-253 in numpy
+* ``oracle.mahalanobis`` -- utils/eval_utils.py:28-55 + models/euclidean_encoder_staticCenter.py:40-46,
+                            133-142; pinned by tests/golden/mahalanobis_ref.npz (the reference's functions)
+The VAE network part of ``oracle.stsgcn`` (``stsvae_encode``) is pinned by the reference's own
+``models/sts/vae.py`` STSVAE (tests/golden/stsvae_ref.npz); only the PowerSpherical sampling stays unpinned.
 
 Pinning status: the network restatement is checked against the real reference modules
 (imported from /root/reference in the build container) by ``oracle/gen_golden.py``; the

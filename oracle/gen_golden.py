@@ -84,6 +84,45 @@ def mahalanobis_fixture(ref_eu) -> None:
     _savez(os.path.join(GOLD, 'mahalanobis_ref.npz'), **out)
 
 
+def vae_fixture() -> None:
+    """the REAL models/sts/vae.py STSVAE with ``power_spherical`` stubbed (un-vendored, only needed by reparameterize of 'ps'):
+    encode() of both distributions (fc_mean / normalisation / softplus + 1, vae.py:63-91) and, for 'normal', the whole
+    forward (Normal rsample, decode, vae.py:107-132) plus the KL term of models/spherical_vae.py:89-90"""
+    from oracle import stsgcn as onet
+    ps = _stub('power_spherical')
+    psd = _stub('power_spherical.distributions')
+    ps.__path__ = []
+    ps.distributions = psd
+    psd.PowerSpherical = psd.HypersphericalUniform = type('Unavailable', (), {})
+    import models.sts.vae as ref_vae          # noqa: E402  (reference)
+    x = onet.synth_windows(12, seed=999)
+    out = {'x': x.numpy()}
+    for dist in ('ps', 'normal'):
+        sd = onet.init_state_dict('stsvae', latent_dim=8, seed=2, distribution=dist)
+        ref = ref_vae.STSVAE(input_dim=2, layer_channels=[32, 16, 32], hidden_dimension=64, latent_dim=8, n_frames=12,
+                             n_joints=17, encoder_type='sts_gcn', projector='linear', distance='euclidean', dropout=0.0,
+                             # upstream defect: STSAE hands (device, bias) to STSE in swapped order (models/sts/ae.py:196), so
+                             # STSVAE.build_model calls torch.tensor(0, device=<the bias flag>) (vae.py:60) and cannot be
+                             # constructed with the defaults; a torch.device in the ``bias`` slot ends up as STSE.device and the
+                             # truthy 'cpu' string in the ``device`` slot as the Linear layers' bias flag -- the arithmetic is
+                             # the unmodified reference's
+                             bias=torch.device('cpu'), device='cpu', distribution=dist)
+        ref.load_state_dict(sd, strict=True)
+        ref.eval()
+        with torch.no_grad():
+            zm, zv = ref.encode(x)
+            zm_o, zv_o = onet.stsvae_encode(x, sd, distribution=dist)
+            assert torch.equal(zm, zm_o) and torch.equal(zv, zv_o), f'oracle stsvae_encode differs from the reference ({dist})'
+            out[f'z_mean_{dist}'], out[f'z_var_{dist}'] = zm.numpy(), zv.numpy()
+            if dist == 'normal':
+                torch.manual_seed(7)
+                Z, Xh, (q, p, zv2) = ref(x)
+                out['eps_normal'] = ((Z - zm) / zv).numpy()
+                out['z_normal'], out['xhat_normal'] = Z.numpy(), Xh.numpy()
+                out['kl_normal'] = torch.distributions.kl.kl_divergence(q, p).sum(-1).mean().numpy()
+    _savez(os.path.join(GOLD, 'stsvae_ref.npz'), **out)
+
+
 def main(only: str = '') -> None:
     global _ONLY
     _ONLY = only
@@ -229,7 +268,8 @@ def main(only: str = '') -> None:
              clips=np.asarray(clips, dtype=np.int64), curves=np.concatenate(ref_curves),
              pad_in=fr, pad_out=ref_eu.pad_scores(fr.copy(), np.zeros(20), 2))
     mahalanobis_fixture(ref_eu)
-    if only == 'mahalanobis':
+    vae_fixture()
+    if only in ('mahalanobis', 'stsvae'):
         return
     # ---- window construction + test-time transforms (utils/dataset_utils.py, utils/preprocessing.py, utils/dataset.py) ----
     from oracle import windows as owin

@@ -166,9 +166,10 @@ def _layer_params(sd: Dict[str, Tensor], pfx: str, ci: int, co: int, Tn: int, Vn
 
 def init_state_dict(kind: str = 'stse', input_dim: int = 2, layer_channels: Sequence[int] = (32, 16, 32),
                     hidden_dimension: int = 64, latent_dim: int = 16, n_frames: int = 12, n_joints: int = 17,
-                    seed: int = 0, randomize_bn: bool = True) -> Dict[str, Tensor]:
+                    seed: int = 0, randomize_bn: bool = True, distribution: str = 'ps') -> Dict[str, Tensor]:
     """Seeded random parameters with the reference's init distributions and key names
-    (kind: 'stse' | 'stsae' | 'stsvae').  Deterministic for a given torch build (CPU generator)."""
+    (kind: 'stse' | 'stsae' | 'stsvae'; distribution 'normal': fc_var has latent_dim rows and mean_vector is a buffer,
+    models/sts/vae.py:56-58,160-169).  Deterministic for a given torch build (CPU generator)."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, Tensor] = {'c': torch.zeros(latent_dim)}
     chans = [input_dim] + list(layer_channels) + [hidden_dimension]
@@ -182,9 +183,12 @@ def init_state_dict(kind: str = 'stse', input_dim: int = 2, layer_channels: Sequ
     if kind == 'stsvae':
         sd['fc_mean.weight'] = (torch.rand(latent_dim, F_, generator=g) * 2 - 1) * bound
         sd['fc_mean.bias'] = (torch.rand(latent_dim, generator=g) * 2 - 1) * bound
-        sd['fc_var.weight'] = (torch.rand(1, F_, generator=g) * 2 - 1) * bound
-        sd['fc_var.bias'] = (torch.rand(1, generator=g) * 2 - 1) * bound
+        vr = latent_dim if distribution == 'normal' else 1
+        sd['fc_var.weight'] = (torch.rand(vr, F_, generator=g) * 2 - 1) * bound
+        sd['fc_var.bias'] = (torch.rand(vr, generator=g) * 2 - 1) * bound
         sd['threshold_dist'] = torch.zeros(())
+        if distribution == 'normal':
+            sd['mean_vector'] = torch.zeros(1, latent_dim)
     if kind in ('stsae', 'stsvae'):
         b2 = 1.0 / math.sqrt(latent_dim)
         sd['rev_btlnk.weight'] = (torch.rand(F_, latent_dim, generator=g) * 2 - 1) * b2

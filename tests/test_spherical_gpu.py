@@ -122,3 +122,68 @@ def test_lit_spherical_vae_epoch(tmp_path):
     tr = Trainer(max_epochs=2, verbose=False).fit(model, train_loader, test_loader)
     assert model.model.mean_vector is not None and model.model.mean_vector.shape == (1, 8)
     assert all(np.isfinite(e['loss']) and 0 <= e['validation_auc'] <= 1 for e in tr.history)
+
+
+# ---- pinned by the REAL reference class: tests/golden/stsvae_ref.npz = outputs of models/sts/vae.py STSVAE (oracle/gen_golden.py
+#      vae_fixture; power_spherical is only needed by reparameterize of 'ps', so encode() of both distributions and the whole
+#      forward of 'normal' run on the unmodified reference)
+def _pair_dist(dist):
+    from coskad_b200 import spherical
+    sd = onet.init_state_dict('stsvae', latent_dim=8, seed=2, distribution=dist)
+    m = spherical.STSVAE(2, [32, 16, 32], 64, 8, 12, 17, distribution=dist)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.parametrize('dist', ['ps', 'normal'])
+def test_encode_matches_reference_class_fixture(golden_dir, dist):
+    import os
+    g = np.load(os.path.join(golden_dir, 'stsvae_ref.npz'))
+    m, sd = _pair_dist(dist)
+    assert sorted(m.state_dict().keys()) == sorted(sd.keys())            # 'normal': mean_vector is a buffer (vae.py:56-58)
+    zm, zv = m.encode(torch.from_numpy(g['x']).cuda())
+    _close(zm, torch.from_numpy(g[f'z_mean_{dist}']))
+    _close(zv, torch.from_numpy(g[f'z_var_{dist}']))
+    assert zv.shape == ((12, 8) if dist == 'normal' else (12, 1))
+
+
+def test_normal_distribution_forward_matches_reference_class(golden_dir):
+    """distribution 'normal' (vae.py:107-108,124-132): Z = Z_mean + Z_var * eps with the reference's own noise draw, the decoder
+    output, and KL(q || N(0, 1)).sum(-1).mean() of models/spherical_vae.py:89-90"""
+    import os
+    g = np.load(os.path.join(golden_dir, 'stsvae_ref.npz'))
+    m, _ = _pair_dist('normal')
+    x = torch.from_numpy(g['x']).cuda()
+    with torch.no_grad():
+        Z, Xh, (q, p, zv) = m(x, noise=torch.from_numpy(g['eps_normal']).cuda())
+    _close(Z, torch.from_numpy(g['z_normal']))
+    _close(Xh, torch.from_numpy(g['xhat_normal']), 1e-4, 1e-4)
+    kl = torch.distributions.kl.kl_divergence(q, p).sum(-1).mean()
+    assert abs(float(kl) - float(g['kl_normal'])) <= 1e-4 * abs(float(g['kl_normal']))
+    # deterministic eval score on the mean rows only (the fused head holds mean | scale)
+    mv = torch.from_numpy(g['z_mean_normal']).mean(0).cuda()
+    s = m.cosine_scores(x, mean_vector=mv, sample=False)
+    ref = 1 - torch.nn.functional.cosine_similarity(torch.from_numpy(g['z_mean_normal']), mv.cpu().view(1, -1))
+    # 1 - cos of nearly parallel vectors (~1e-3): one fp32 ulp of cos is 1e-4 of the score, so the tolerance here is absolute
+    assert float((s.cpu() - ref).abs().max()) <= 5e-7
+
+
+def test_lit_spherical_vae_normal_distribution_epoch(tmp_path):
+    from coskad_b200 import config as ccfg, tasks
+    from coskad_b200.data import get_dataset_and_loader
+    from coskad_b200.trainer import Trainer
+    torch.manual_seed(0)
+    ns = argparse.Namespace(dataset_choice='synthetic', exp_dir=str(tmp_path), dir_name='vaen', hyperbolic=False, static_center=True,
+                            use_decoder=False, use_vae=True, latent_dim=8, ae_epochs=2, opt_lr=1e-3, dataset_batch_size=256,
+                            dataset_num_transform=1, projector='linear', validation=True, seed=3, beta=1e-3, gamma=1e-2, phi=1.0,
+                            distribution='normal')
+    args, ae_args, *_ = ccfg.init_sub_args(ns)
+    _, train_loader = get_dataset_and_loader(ae_args, 'train')
+    test_ds, test_loader = get_dataset_and_loader(ae_args, 'test')
+    args.gt_table = (test_ds.clips, test_ds.gts)
+    model = tasks.select_task(args)(args)
+    assert model.model.distribution == 'normal' and model.model.fc_var.out_features == 8
+    tr = Trainer(max_epochs=2, verbose=False).fit(model, train_loader, test_loader)
+    assert 'model.mean_vector' in model.state_dict() and float(model.model.mean_vector.abs().sum()) > 0
+    assert all(np.isfinite(e['loss']) and 0 <= e['validation_auc'] <= 1 for e in tr.history)
+    assert tr.history[-1]['loss'] < tr.history[0]['loss'], tr.history
