@@ -281,3 +281,40 @@ def test_pin_geoopt_script_plumbing(tmp_path):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(tmp_path), root]))
     res = subprocess.run([sys.executable, script], capture_output=True, text=True, cwd=str(tmp_path), env=env)
     assert res.returncode == 0 and 'PINNED' in res.stdout and 'DIFF' not in res.stdout, res.stdout + res.stderr
+
+
+def test_mahalanobis_oracle_matches_reference_functions(golden_dir):
+    """tests/golden/mahalanobis_ref.npz: outputs of the reference's own mahalanobis / windows_based_loss_mahalanobis /
+    batch_cov_mat_step (utils/eval_utils.py:28-55, models/euclidean_encoder_staticCenter.py:40-46,133-142)"""
+    from oracle import mahalanobis as omah
+    g = _load(golden_dir, 'mahalanobis_ref.npz')
+    for D in (8, 16):
+        z, mu, VI = (torch.from_numpy(g[f'{k}{D}']) for k in ('z', 'mu', 'VI'))
+        batches = [z[i:i + 256] for i in range(0, z.shape[0], 256)]
+        assert torch.equal(sum(omah.batch_cov_mat_step(b, mu) for b in batches), torch.from_numpy(g[f'scatter{D}']))
+        assert torch.equal(omah.inv_cov(batches, mu), VI)
+        zq = torch.from_numpy(g[f'zq{D}'])
+        assert torch.equal(omah.mahalanobis(zq, mu, VI, reduce='none').reshape(-1), torch.from_numpy(g[f'dist{D}']))
+        pose = omah.windows_based_loss_mahalanobis(mu, g[f'zq{D}'][:40], VI, g[f'frames{D}'], 60)
+        assert np.array_equal(pose, g[f'pose{D}'])
+
+
+def test_stsvae_oracle_matches_reference_class(golden_dir):
+    """tests/golden/stsvae_ref.npz: outputs of the reference's own models/sts/vae.py STSVAE (encode of 'ps' and 'normal', the
+    whole 'normal' forward with the reference's noise draw)"""
+    g = _load(golden_dir, 'stsvae_ref.npz')
+    x = torch.from_numpy(g['x'])
+    for dist in ('ps', 'normal'):
+        sd = onet.init_state_dict('stsvae', latent_dim=8, seed=2, distribution=dist)
+        with torch.no_grad():
+            zm, zv = onet.stsvae_encode(x, sd, distribution=dist)
+        assert torch.allclose(zm, torch.from_numpy(g[f'z_mean_{dist}']), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(zv, torch.from_numpy(g[f'z_var_{dist}']), rtol=1e-5, atol=1e-6)
+    with torch.no_grad():
+        Z = zm + zv * torch.from_numpy(g['eps_normal'])
+        xh = onet.stsae_decode(Z, sd, x.shape)
+    assert torch.allclose(Z, torch.from_numpy(g['z_normal']), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(xh, torch.from_numpy(g['xhat_normal']), rtol=1e-4, atol=1e-5)
+    q = torch.distributions.Normal(zm, zv)
+    kl = torch.distributions.kl.kl_divergence(q, torch.distributions.Normal(torch.zeros_like(zm), torch.ones_like(zv))).sum(-1).mean()
+    assert abs(float(kl) - float(g['kl_normal'])) < 1e-5 * abs(float(g['kl_normal']))
