@@ -532,7 +532,7 @@ extern "C" int coskad_center_partial(coskad_ctx* ctx, int flavour, const float* 
   if (D <= 32) center_partial_kernel<1><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, part);
   else center_partial_kernel<4><<<g, kRowWarps * 32, 0, st>>>(flavour, zproj, B, D, part);
   CK_LAUNCH();
-  center_partial_final_kernel<<<1, 160, 0, st>>>(part, g, D, acc);
+  center_partial_final_kernel<<<1, dim3(32, 8), 0, st>>>(part, g, D, acc);
   CK_LAUNCH();
   return COSKAD_OK;
 }
@@ -889,7 +889,7 @@ extern "C" int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, con
   { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(nb) * 4 * CO); if (rc) return rc; }
   train_bn_prelu_bwd_reduce_kernel<<<dim3(CO, nb), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, B, CO, ctx->ws);
   CK_LAUNCH();
-  train_bn_prelu_bwd_reduce_final_kernel<<<1, kTrainThreads, 0, st>>>(ctx->ws, nb, CO, red);
+  train_bn_prelu_bwd_reduce_final_kernel<<<(3 * CO + 31) / 32 + 1, dim3(32, kPsRows), 0, st>>>(ctx->ws, nb, CO, red);
   CK_LAUNCH();
   if (dy1 && dy2) {        // NULL: the tensor-core backward (coskad_train_mix_bwd_tc) applies the BatchNorm / PReLU backward itself
     train_bn_prelu_bwd_apply_kernel<<<ew_grid(ctx, B * CO * 32), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2,

@@ -346,12 +346,35 @@ __global__ void center_partial_kernel(int flavour, const float* __restrict__ z, 
     else acc[D + (i - 32 * E)] = s;
   }
 }
+// second stage, fixed order: 32 x 8 threads, row y adds the partials y, y + 8, .. (batches of 8 loads in flight: one thread
+// per element walked up to 296 partials one L2 round trip at a time, 12 us), the rows meet in shared memory
 __global__ void center_partial_final_kernel(const double* __restrict__ part, int nblk, int D, double* acc) {
-  const int i = threadIdx.x;
-  if (i >= D + 2) return;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += part[static_cast<int64_t>(b) * (D + 2) + i];
-  acc[i] += s;
+  __shared__ double sh[8][33];
+  const int n = D + 2;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + threadIdx.x;
+    double s = 0.0;
+    if (i < n) {
+      int b = threadIdx.y;
+      for (; b + 7 * 8 < nblk; b += 8 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = part[static_cast<int64_t>(b + u * 8) * n + i];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
+      for (; b < nblk; b += 8) s += part[static_cast<int64_t>(b) * n + i];
+    }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < n) {
+      double t = 0.0;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
+      acc[i] += t;
+    }
+    __syncthreads();
+  }
 }
 
 // single warp

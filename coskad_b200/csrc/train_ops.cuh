@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "geometry.cuh"
 #include "latent_ops.cuh"
+#include "reduce.cuh"
 
 namespace coskad {
 
@@ -409,22 +410,29 @@ __global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout,
     part[(static_cast<int64_t>(blockIdx.y) * 4 + threadIdx.x) * CO + co] = static_cast<float>(t);
   }
 }
-// second stage of the reduction above, fixed order: red[0..3CO) += per-channel sums over the batch slices, red[3CO] += the
-// PReLU-slope sum over slices and channels (one warp, lane-strided then a fixed shuffle tree)
+// second stage of the reduction above, fixed order (partial_sum_block: 32 x kPsRows threads per 32 elements).  Blocks
+// 0 .. ceil(3CO/32)-1: red[i] += sum over the batch slices of part[y][q][co], i = q*CO + co < 3CO.  Last block: the PReLU-slope
+// sums, first per channel over the slices, then over the channels in ascending order -> red[3CO].
 __global__ void train_bn_prelu_bwd_reduce_final_kernel(const float* __restrict__ part, int nb, int CO, double* red) {
-  const int i = threadIdx.x;
-  if (i < 3 * CO) {
-    const int q = i / CO, co = i % CO;
-    double s = 0.0;
-    for (int y = 0; y < nb; ++y) s += static_cast<double>(part[(static_cast<int64_t>(y) * 4 + q) * CO + co]);
-    red[i] += s;
+  __shared__ double sh[kPsRows][33];
+  const int nmain = (3 * CO + 31) / 32;
+  if (static_cast<int>(blockIdx.x) < nmain) {
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    const double t = partial_sum_block(part, nb, 4 * CO, i, i < 3 * CO, sh);
+    if (threadIdx.y == 0 && i < 3 * CO) red[i] += t;
+    return;
   }
-  if (i >= blockDim.x - 32) {
-    const int lane = i & 31;
+  __shared__ double ch[64];
+  for (int c0 = 0; c0 < CO; c0 += 32) {
+    const int co = c0 + threadIdx.x;
+    const double t = partial_sum_block(part, nb, 4 * CO, 3 * CO + co, co < CO, sh);
+    if (threadIdx.y == 0 && co < CO) ch[co] = t;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
     double s = 0.0;
-    for (int j = lane; j < nb * CO; j += 32) s += static_cast<double>(part[(static_cast<int64_t>(j / CO) * 4 + 3) * CO + j % CO]);
-    s = warp_sum(s);
-    if (lane == 0) red[3 * CO] += s;
+    for (int co = 0; co < CO; ++co) s += ch[co];
+    red[3 * CO] += s;
   }
 }
 

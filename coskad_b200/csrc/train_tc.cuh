@@ -22,6 +22,7 @@
 //    (partial_sum_kernel): no floating-point atomics, two runs are bit-identical.
 #pragma once
 #include "common.cuh"
+#include "reduce.cuh"
 #include "tc.cuh"
 
 namespace coskad {
@@ -33,38 +34,6 @@ __host__ __device__ constexpr int tmem_alloc_cols(int need) {
 }
 // canonical K-major, no swizzle: element (n, k) of an [N][K] operand; LBO = (N/8)*128 B, SBO = 128 B (fold.cuh, tc_test.cuh)
 __device__ __forceinline__ int kmaj_idx(int n, int k, int N) { return ((k >> 2) * (N >> 3) + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3); }
-
-// out[i] += sum_j part[j*stride + i] in a FIXED order (double accumulator): the second stage of every cross-CTA reduction.
-// Few partials: one thread per element.  Many partials (hundreds of CTAs): a 32 x 8 block owns 32 consecutive elements,
-// row y sums the partials y, y + 8, .. (coalesced across x), the 8 rows meet in shared memory in a fixed order.
-template <typename TOut>
-__global__ void partial_sum_kernel(const float* __restrict__ part, int nparts, int64_t stride, int64_t n, TOut* out) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double s = 0.0;
-  for (int j = 0; j < nparts; ++j) s += static_cast<double>(part[static_cast<int64_t>(j) * stride + i]);
-  out[i] += static_cast<TOut>(s);
-}
-constexpr int kPsRows = 8;
-__device__ __forceinline__ double partial_sum_block(const float* __restrict__ part, int nparts, int64_t stride, int64_t i, bool ok,
-                                                    double (*sh)[33]) {
-  double s = 0.0;
-  if (ok) for (int j = threadIdx.y; j < nparts; j += kPsRows) s += static_cast<double>(part[static_cast<int64_t>(j) * stride + i]);
-  sh[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  double t = 0.0;
-  if (threadIdx.y == 0)
-#pragma unroll
-    for (int y = 0; y < kPsRows; ++y) t += sh[y][threadIdx.x];
-  return t;
-}
-template <typename TOut>
-__global__ void partial_sum_wide_kernel(const float* __restrict__ part, int nparts, int64_t stride, int64_t n, TOut* out) {
-  __shared__ double sh[kPsRows][33];
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
-  const double t = partial_sum_block(part, nparts, stride, i, i < n, sh);
-  if (threadIdx.y == 0 && i < n) out[i] += static_cast<TOut>(t);
-}
 
 // ---- forward: y1 = conv1x1(G; W1, b1), y2 = conv1x1(X; W2, b2) + per-CTA BatchNorm statistics ---------------------------
 // part [gridDim.x][4*CO] = sum y1, sum y1^2, sum y2, sum y2^2 per channel of the positions the CTA owned.

@@ -1,7 +1,10 @@
-"""usage: python tools/prof_summary.py gpurun_out/prof.ncu-rep profiles/name.md "title" """
-import csv, subprocess, sys, io, collections
+"""usage: python tools/prof_summary.py gpurun_out/prof.ncu-rep profiles/name.md "title"
+       python tools/prof_summary.py gpurun_out/name.raw.csv profiles/name.md "title"    (CSV pages exported on the GPU box by
+       tools/ncu_eval.sh / tools/ncu_csv.sh: name.raw.csv + name.source.csv; the .ncu-rep itself exceeds the gpurun_out/ cap)"""
+import csv, os, subprocess, sys, io, collections
 rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+from_csv = rep.endswith('.raw.csv')
+raw = open(rep).read() if from_csv else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 m = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
@@ -15,7 +18,7 @@ keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__b
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'smsp__sass_thread_inst_executed_op_ffma_pred_on.sum',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'sm__cycles_elapsed.max']
+        'sm__cycles_elapsed.max', 'lts__t_bytes.sum', 'lts__t_sectors_srcunit_tex_op_read.sum', 'l1tex__m_xbar2l1tex_read_bytes.sum']
 lines = [f'# {title}', '', f'source: `{rep}` (ncu --set full --clock-control none --import-source on), one launch', '',
          '| metric | value | unit |', '|---|---|---|']
 for k in keys:
@@ -27,13 +30,17 @@ st = [(h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_a
 for n, v in sorted(st, key=lambda kv: -kv[1])[:10]:
     lines.append(f'| {n} | {v:.3f} |')
 # per-barrier-segment breakdown from the SASS page
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+src_csv = rep[:-len('.raw.csv')] + '.source.csv'
+src = (open(src_csv).read() if os.path.exists(src_csv) else '') if from_csv else \
+    subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h2 = rows[1]; col = {h: i for i, h in enumerate(h2)}
+hrow = next((i for i, r in enumerate(rows[:5]) if 'Source' in r), 1)
+h2 = rows[hrow] if rows else []; col = {h: i for i, h in enumerate(h2)}
 segs = collections.defaultdict(collections.Counter); seg = 0
-for r in rows[2:]:
+for r in rows[hrow + 1:]:
     if len(r) < len(h2): continue
     s_ = r[col['Source']].strip()
+    if not s_: continue
     op = (s_.split()[1] if s_.startswith('@') else s_.split()[0]).split('.')[0]
     segs[seg]['samples'] += int(r[col['# Samples']] or 0)
     e = int(r[col['Instructions Executed']] or 0)
