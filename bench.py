@@ -691,14 +691,16 @@ def run_ours(args):
     ach_tf = FLOP_PER_WINDOW * W / (k_ms * 1e-3) / 1e12
     ach_gb = BYTES_PER_WINDOW * W / (k_ms * 1e-3) / 1e9
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    # CONSTANT, not measured in this run: ncu dram__bytes_read+write of one profiled launch
-    # (profiles/r01_v9_fused_eval_tc.md: 1726.73 + 10.98 MB for 1 048 576 windows), scaled to W
-    traffic_per_window = 1737.71e6 / 1048576
+    # CONSTANT, not measured in this run: ncu dram__bytes_read+write of one profiled launch of this kernel
+    # (profiles/r02_fused_eval_tc.md: 1726.40 + 10.27 MB for 1 048 576 windows; r01_v9: 1726.73 + 10.98 MB), scaled to W
+    traffic_per_window = 1736.67e6 / 1048576
+    l2_to_sm_per_window = 380.164e9 / 1048576      # l1tex__m_xbar2l1tex_read_bytes of the same capture
     roofline = {'bound': 'fp32_fma', 'achieved': ach_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s',
                 'frac': ach_tf / fp32_peak if fp32_peak else None,
                 'traffic': traffic_per_window * W,
                 'traffic_unit': 'bytes per launch; a CONSTANT from one ncu --set full capture (dram read+write of the profiled '
-                                'launch, profiles/), scaled to this launch -- not re-measured in this run',
+                                'launch, profiles/r02_fused_eval_tc.md), scaled to this launch -- not re-measured in this run',
+                'l2_to_sm_bytes_per_window': l2_to_sm_per_window,
                 'kernel': 'fused_eval_tc_kernel', 'launch_ms': k_ms,
                 'peak_source': 'measured on this GPU by coskad_measure_fp32_peak (register-resident FFMA loop)',
                 'peak_derived': fp32_peak_derived, 'frac_of_derived': ach_tf / fp32_peak_derived,
