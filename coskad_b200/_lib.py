@@ -62,6 +62,10 @@ SIGNATURES = {
     'coskad_train_mix_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64, C.c_int, C.c_int] + [c_float_p] * 3 + [C.c_void_p]),
     'coskad_train_bn_finalize': (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float] + [c_float_p] * 5
                                  + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'coskad_train_mix_fwd_bn': (C.c_int, [c_ctx_p] + [c_float_p] * 6 + [C.c_int64, C.c_int, C.c_int] + [c_float_p] * 2
+                                + [C.c_float, C.c_float] + [c_float_p] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'coskad_train_bn_prelu_bwd_grads': (C.c_int, [c_ctx_p] + [c_float_p] * 9 + [C.c_int64, C.c_int, C.c_void_p] + [c_float_p] * 5
+                                        + [C.c_void_p]),
     'coskad_train_bn_param_grads': (C.c_int, [c_ctx_p, C.c_void_p, C.c_int] + [c_float_p] * 5 + [C.c_void_p]),
     'coskad_train_bn_prelu_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 8 + [C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_train_bn_prelu_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 9 + [C.c_int64, C.c_int, C.c_void_p, c_float_p, c_float_p, C.c_void_p]),

@@ -815,10 +815,16 @@ static size_t tmem_pad_smem(K kernel, int per_sm) {
   const size_t target = (static_cast<size_t>(228) * 1024) / static_cast<size_t>(per_sm) - 1536;   // 1 KB per CTA is reserved
   return target > attr.sharedSizeBytes ? target - attr.sharedSizeBytes : 0;
 }
+struct BnFinalizeArgs {
+  float eps, momentum;
+  float *rm1, *rv1, *rm2, *rv2, *mi;
+  int64_t *nbt1, *nbt2;
+};
 // tcgen05 forward convolution: y1, y2 and the BatchNorm statistics (per-warp partials -> fixed-order second stage)
 template <int CIP, int CO, int COP>
 static int launch_tc_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1, const float* W2,
-                             const float* b2, int64_t B, int CI, float* y1, float* y2, double* stats, cudaStream_t st) {
+                             const float* b2, int64_t B, int CI, float* y1, float* y2, double* stats, cudaStream_t st,
+                             const BnFinalizeArgs* bn = nullptr) {
   const int64_t E = B * kP, ntiles = (E + kTcT - 1) / kTcT;
   int per_sm = 512 / tmem_alloc_cols(4 * CIP + 2 * COP);                // TMEM columns bound the resident CTAs
   if (per_sm > 4) per_sm = 4;
@@ -829,6 +835,13 @@ static int launch_tc_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, co
   // and the 128-byte row segments of neighbouring warps share cache lines (rows start at multiples of 816 B)
   tc_mix_fwd_kernel<CIP, CO, COP><<<g, kTcT, 0, st>>>(G, X, W1, b1, W2, b2, E, CI, y1, y2, ctx->ws);
   CK_LAUNCH();
+  if (bn != nullptr) {      // statistics second stage + BatchNorm finalize in one launch
+    train_bn_stats_finalize_kernel<<<(CO + 31) / 32, dim3(32, kPsRows), 0, st>>>(ctx->ws, g, static_cast<double>(E), CO, bn->eps,
+                                                                                bn->momentum, bn->rm1, bn->rv1, bn->rm2, bn->rv2,
+                                                                                bn->mi, bn->nbt1, bn->nbt2);
+    CK_LAUNCH();
+    return COSKAD_OK;
+  }
   return launch_partial_sum<double>(ctx, ctx->ws, g, 4 * CO, 4 * CO, stats, st);
 }
 
@@ -847,12 +860,49 @@ extern "C" int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float
   return launch_chan_gemm(ctx, true, G, X, W1, W2, 0, b1, b2, B, CI, CO, y1, y2, stats, st);
 }
 
+extern "C" int coskad_train_mix_fwd_bn(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1,
+                                       const float* W2, const float* b2, int64_t B, int CI, int CO, float* y1, float* y2,
+                                       float eps, float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi,
+                                       int64_t* nbt1, int64_t* nbt2, void* stream_) {
+  TRAIN_PRE();
+  if (!chan_ok(CI) || !chan_ok(CO)) return fail(ctx, COSKAD_ERR_ARG, "training kernels support channels {2,16,32,64}, got %d->%d", CI, CO);
+  if (ctx->train_impl != 1) return fail(ctx, COSKAD_ERR_STATE, "coskad_train_mix_fwd_bn is the tensor-core path (coskad_set_train_impl(ctx, 1))");
+  if (!mi) return fail(ctx, COSKAD_ERR_ARG, "coskad_train_mix_fwd_bn: mi is NULL");
+  if (B <= 0) return COSKAD_OK;
+  const BnFinalizeArgs bn{eps, momentum, rm1, rv1, rm2, rv2, mi, nbt1, nbt2};
+#define TC_FWD(ci, co, cip, cop) if (CI == ci && CO == co) return launch_tc_mix_fwd<cip, co, cop>(ctx, G, X, W1, b1, W2, b2, B, CI, y1, y2, nullptr, st, &bn)
+  TC_FWD(2, 32, 8, 32); TC_FWD(32, 16, 32, 16); TC_FWD(16, 32, 16, 32); TC_FWD(32, 64, 32, 64);      // encoder
+  TC_FWD(64, 32, 64, 32); TC_FWD(32, 2, 32, 16);                                                       // decoder
+#undef TC_FWD
+  return fail(ctx, COSKAD_ERR_ARG, "coskad_train_mix_fwd_bn: no tensor-core kernel for %d -> %d channels", CI, CO);
+}
+
 extern "C" int coskad_train_bn_finalize(coskad_ctx* ctx, const double* stats, int64_t n_per_channel, int CO, float eps,
                                         float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi,
                                         int64_t* nbt1, int64_t* nbt2, void* stream_) {
   TRAIN_PRE();
   train_bn_finalize_kernel<<<(CO + 63) / 64, 64, 0, st>>>(stats, static_cast<double>(n_per_channel), CO, eps, momentum, rm1,
                                                          rv1, rm2, rv2, mi, nbt1, nbt2);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
+extern "C" int coskad_train_bn_prelu_bwd_grads(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2,
+                                               const float* mi, const float* g1, const float* be1, const float* g2,
+                                               const float* be2, const float* slope, int64_t B, int CO, double* red,
+                                               float* dg1, float* dbe1, float* dg2, float* dbe2, float* dslope, void* stream_) {
+  TRAIN_PRE();
+  if (B <= 0) return COSKAD_OK;
+  if (!red) return fail(ctx, COSKAD_ERR_ARG, "coskad_train_bn_prelu_bwd_grads: red is NULL");
+  if (CO > 64) return fail(ctx, COSKAD_ERR_ARG, "bn_prelu_bwd supports c_out <= 64, got %d", CO);
+  int nb = static_cast<int>((B + 7) / 8);
+  const int cap = (ctx->sm_count * 8 + CO - 1) / CO;
+  if (nb > cap) nb = cap;
+  { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(nb) * 4 * CO); if (rc) return rc; }
+  train_bn_prelu_bwd_reduce_kernel<<<dim3(CO, nb), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, B, CO, ctx->ws);
+  CK_LAUNCH();
+  train_bn_prelu_bwd_reduce_final_kernel<true><<<(3 * CO + 31) / 32 + 1, dim3(32, kPsRows), 0, st>>>(ctx->ws, nb, CO, red, dg1, dbe1,
+                                                                                                 dg2, dbe2, dslope);
   CK_LAUNCH();
   return COSKAD_OK;
 }
@@ -889,7 +939,8 @@ extern "C" int coskad_train_bn_prelu_bwd(coskad_ctx* ctx, const float* dout, con
   { const int rc = ensure_ws(ctx, sizeof(float) * static_cast<size_t>(nb) * 4 * CO); if (rc) return rc; }
   train_bn_prelu_bwd_reduce_kernel<<<dim3(CO, nb), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, B, CO, ctx->ws);
   CK_LAUNCH();
-  train_bn_prelu_bwd_reduce_final_kernel<<<(3 * CO + 31) / 32 + 1, dim3(32, kPsRows), 0, st>>>(ctx->ws, nb, CO, red);
+  train_bn_prelu_bwd_reduce_final_kernel<false><<<(3 * CO + 31) / 32 + 1, dim3(32, kPsRows), 0, st>>>(ctx->ws, nb, CO, red, nullptr,
+                                                                                                  nullptr, nullptr, nullptr, nullptr);
   CK_LAUNCH();
   if (dy1 && dy2) {        // NULL: the tensor-core backward (coskad_train_mix_bwd_tc) applies the BatchNorm / PReLU backward itself
     train_bn_prelu_bwd_apply_kernel<<<ew_grid(ctx, B * CO * 32), kTrainThreads, 0, st>>>(dout, y1, y2, mi, g1, be1, g2, be2,

@@ -325,6 +325,39 @@ __global__ void train_bn_finalize_kernel(const double* __restrict__ stats, doubl
   }
 }
 
+// second stage of the BatchNorm statistics (per-CTA partials [nparts][4*CO] of tc_mix_fwd_kernel, fixed order) fused with
+// train_bn_finalize_kernel: one launch instead of partial_sum + finalize (+ the zero fill of the intermediate sums); the
+// arithmetic is the same, value for value.  Block x owns channels 32 x .. 32 x + 31.
+__global__ void train_bn_stats_finalize_kernel(const float* __restrict__ part, int nparts, double N, int CO, float eps,
+                                               float momentum, float* rm1, float* rv1, float* rm2, float* rv2,
+                                               float* __restrict__ mi, int64_t* nbt1, int64_t* nbt2) {
+  __shared__ double sh[kPsRows][33];
+  __shared__ double tot[4][32];
+  const int co = blockIdx.x * 32 + threadIdx.x;
+  for (int q = 0; q < 4; ++q) {
+    const double t = partial_sum_block(part, nparts, 4 * CO, q * CO + co, co < CO, sh);
+    if (threadIdx.y == 0) tot[q][threadIdx.x] = t;
+    __syncthreads();
+  }
+  if (threadIdx.y != 0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (nbt1) *nbt1 += 1;
+    if (nbt2) *nbt2 += 1;
+  }
+  if (co >= CO) return;
+  for (int br = 0; br < 2; ++br) {
+    const double mean = tot[2 * br][threadIdx.x] / N;
+    double var = tot[2 * br + 1][threadIdx.x] / N - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mi[(2 * br) * CO + co] = static_cast<float>(mean);
+    mi[(2 * br + 1) * CO + co] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    float* rm = br ? rm2 : rm1;
+    float* rv = br ? rv2 : rv1;
+    if (rm) rm[co] = (1.f - momentum) * rm[co] + momentum * static_cast<float>(mean);
+    if (rv) rv[co] = (1.f - momentum) * rv[co] + momentum * static_cast<float>(var * N / (N - 1.0));
+  }
+}
+
 // BN1(y1) + BN2(y2) with a fixed operation order (explicit rounding intrinsics: no re-contraction), so that the
 // forward and the two backward kernels see bit-identical pre-activations and hence the same PReLU branch.
 __device__ __forceinline__ float bn_pre(float y1, float y2, float m1, float i1, float m2, float i2, float g1, float be1,
@@ -413,13 +446,30 @@ __global__ void train_bn_prelu_bwd_reduce_kernel(const float* __restrict__ dout,
 // second stage of the reduction above, fixed order (partial_sum_block: 32 x kPsRows threads per 32 elements).  Blocks
 // 0 .. ceil(3CO/32)-1: red[i] += sum over the batch slices of part[y][q][co], i = q*CO + co < 3CO.  Last block: the PReLU-slope
 // sums, first per channel over the slices, then over the channels in ascending order -> red[3CO].
-__global__ void train_bn_prelu_bwd_reduce_final_kernel(const float* __restrict__ part, int nb, int CO, double* red) {
+// GRADS = false: red += the sums (the documented contract of coskad_train_bn_prelu_bwd: red is zeroed by the caller).
+// GRADS = true (coskad_train_bn_prelu_bwd_grads): red = the sums (no zero fill needed) and the parameter gradients are
+// accumulated in the same launch: d beta1 = d beta2 += red[0..CO), d gamma1 += red[CO..2CO), d gamma2 += red[2CO..3CO),
+// d slope += red[3CO] (what train_bn_param_grads_kernel does as a launch of its own).
+template <bool GRADS>
+__global__ void train_bn_prelu_bwd_reduce_final_kernel(const float* __restrict__ part, int nb, int CO, double* red, float* dg1,
+                                                       float* dbe1, float* dg2, float* dbe2, float* dslope) {
   __shared__ double sh[kPsRows][33];
   const int nmain = (3 * CO + 31) / 32;
   if (static_cast<int>(blockIdx.x) < nmain) {
     const int i = blockIdx.x * 32 + threadIdx.x;
     const double t = partial_sum_block(part, nb, 4 * CO, i, i < 3 * CO, sh);
-    if (threadIdx.y == 0 && i < 3 * CO) red[i] += t;
+    if (threadIdx.y == 0 && i < 3 * CO) {
+      if (GRADS) {
+        red[i] = t;
+        const float f = static_cast<float>(t);
+        const int q = i / CO, co = i - q * CO;
+        if (q == 0) { if (dbe1) dbe1[co] += f; if (dbe2) dbe2[co] += f; }
+        else if (q == 1) { if (dg1) dg1[co] += f; }
+        else if (dg2) dg2[co] += f;
+      } else {
+        red[i] += t;
+      }
+    }
     return;
   }
   __shared__ double ch[64];
@@ -432,7 +482,8 @@ __global__ void train_bn_prelu_bwd_reduce_final_kernel(const float* __restrict__
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     double s = 0.0;
     for (int co = 0; co < CO; ++co) s += ch[co];
-    red[3 * CO] += s;
+    if (GRADS) { red[3 * CO] = s; if (dslope) dslope[0] += static_cast<float>(s); }
+    else red[3 * CO] += s;
   }
 }
 

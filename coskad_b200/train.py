@@ -73,21 +73,30 @@ class _LayerFn(torch.autograd.Function):
                                               G.data_ptr(), st), 'coskad_train_contract_fwd')
         y1 = torch.empty((B, CO, X.shape[2], X.shape[3]), device=X.device, dtype=torch.float32)
         y2 = torch.empty_like(y1)
-        stats = torch.zeros(4 * CO, device=X.device, dtype=torch.float64)
-        c.check(lib.coskad_train_mix_fwd(c.h, G.data_ptr(), X.data_ptr(), W1.data_ptr(), _lib._ptr(b1), W2.data_ptr(),
-                                         _lib._ptr(b2), B, CI, CO, y1.data_ptr(), y2.data_ptr(), stats.data_ptr(), st),
-                'coskad_train_mix_fwd')
         bn1, bn2 = layer.tcn[1], layer.residual[1]
-        if training:
+        if training and getattr(c, 'train_impl', 1) == 1:
+            # tensor-core path: convolutions + statistics, then ONE launch for the statistics' second stage + BatchNorm finalize
             mi = torch.empty(4 * CO, device=X.device, dtype=torch.float32)
-            c.check(lib.coskad_train_bn_finalize(c.h, stats.data_ptr(), B * P, CO, float(bn1.eps), float(bn1.momentum),
-                                                 bn1.running_mean.data_ptr(), bn1.running_var.data_ptr(),
-                                                 bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), mi.data_ptr(),
-                                                 _nbt_ptr(bn1, X.device), _nbt_ptr(bn2, X.device), st),
-                    'coskad_train_bn_finalize')
-        else:   # eval: normalise with the running statistics (parameter prep, 4*CO numbers)
-            mi = torch.cat([bn1.running_mean, torch.rsqrt(bn1.running_var + bn1.eps),
-                            bn2.running_mean, torch.rsqrt(bn2.running_var + bn2.eps)]).to(torch.float32).contiguous()
+            c.check(lib.coskad_train_mix_fwd_bn(c.h, G.data_ptr(), X.data_ptr(), W1.data_ptr(), _lib._ptr(b1), W2.data_ptr(),
+                                                _lib._ptr(b2), B, CI, CO, y1.data_ptr(), y2.data_ptr(), float(bn1.eps),
+                                                float(bn1.momentum), bn1.running_mean.data_ptr(), bn1.running_var.data_ptr(),
+                                                bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), mi.data_ptr(),
+                                                _nbt_ptr(bn1, X.device), _nbt_ptr(bn2, X.device), st), 'coskad_train_mix_fwd_bn')
+        else:
+            stats = torch.zeros(4 * CO, device=X.device, dtype=torch.float64)
+            c.check(lib.coskad_train_mix_fwd(c.h, G.data_ptr(), X.data_ptr(), W1.data_ptr(), _lib._ptr(b1), W2.data_ptr(),
+                                             _lib._ptr(b2), B, CI, CO, y1.data_ptr(), y2.data_ptr(), stats.data_ptr(), st),
+                    'coskad_train_mix_fwd')
+            if training:
+                mi = torch.empty(4 * CO, device=X.device, dtype=torch.float32)
+                c.check(lib.coskad_train_bn_finalize(c.h, stats.data_ptr(), B * P, CO, float(bn1.eps), float(bn1.momentum),
+                                                     bn1.running_mean.data_ptr(), bn1.running_var.data_ptr(),
+                                                     bn2.running_mean.data_ptr(), bn2.running_var.data_ptr(), mi.data_ptr(),
+                                                     _nbt_ptr(bn1, X.device), _nbt_ptr(bn2, X.device), st),
+                        'coskad_train_bn_finalize')
+            else:   # eval: normalise with the running statistics (parameter prep, 4*CO numbers)
+                mi = torch.cat([bn1.running_mean, torch.rsqrt(bn1.running_var + bn1.eps),
+                                bn2.running_mean, torch.rsqrt(bn2.running_var + bn2.eps)]).to(torch.float32).contiguous()
         out = torch.empty_like(y1)
         c.check(lib.coskad_train_bn_prelu_fwd(c.h, y1.data_ptr(), y2.data_ptr(), mi.data_ptr(), g1.data_ptr(),
                                               be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(), B, CO,
@@ -117,11 +126,15 @@ class _LayerFn(torch.autograd.Function):
             dests[4] = dests[5] = None
         shapes = (W1.shape, W2.shape, (CO,), (CO,), A.shape, T.shape, (CO,), (CO,), (CO,), (CO,), (1,))
         need = [(i, int(torch.Size(sh).numel())) for i, sh in enumerate(shapes) if dests[i] is None]
-        offs = [(2 * (3 * CO + 1) + 3) // 4 * 4]
+        tc = getattr(c, 'train_impl', 1) == 1
+        nred = (2 * (3 * CO + 1) + 3) // 4 * 4
+        # tensor-core path: `red` is assigned by its kernel (coskad_train_bn_prelu_bwd_grads), so it needs no zero fill -- with every
+        # gradient going straight into the bucket views the layer's backward then starts without a memset at all
+        offs = [0 if tc else nred]
         for _, n in need:
             offs.append(offs[-1] + (n + 3) // 4 * 4)
-        zbuf = torch.zeros(offs[-1], device=X.device, dtype=torch.float32)
-        red = zbuf[:2 * (3 * CO + 1)].view(torch.float64)
+        zbuf = torch.zeros(offs[-1], device=X.device, dtype=torch.float32) if offs[-1] else None
+        red = (torch.empty(nred, device=X.device, dtype=torch.float32) if tc else zbuf[:nred]).view(torch.float64)[:3 * CO + 1]
         out = list(dests)
         for k, (i, n) in enumerate(need):
             out[i] = zbuf[offs[k]:offs[k] + n].view(shapes[i])
@@ -130,13 +143,19 @@ class _LayerFn(torch.autograd.Function):
         dy2 = torch.empty_like(y2)
         dG = torch.empty_like(X)
         dXres = torch.empty_like(X)
-        tc = getattr(c, 'train_impl', 1) == 1
-        c.check(lib.coskad_train_bn_prelu_bwd(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
-                                              g1.data_ptr(), be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(),
-                                              B, CO, red.data_ptr(), None if tc else dy1.data_ptr(),
-                                              None if tc else dy2.data_ptr(), st), 'coskad_train_bn_prelu_bwd')
-        c.check(lib.coskad_train_bn_param_grads(c.h, red.data_ptr(), CO, dg1.data_ptr(), dbe1.data_ptr(), dg2.data_ptr(),
-                                                dbe2.data_ptr(), dslope.data_ptr(), st), 'coskad_train_bn_param_grads')
+        if tc:      # reductions, then `red` + the BatchNorm / PReLU parameter gradients in one second-stage launch
+            c.check(lib.coskad_train_bn_prelu_bwd_grads(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
+                                                        g1.data_ptr(), be1.data_ptr(), g2.data_ptr(), be2.data_ptr(),
+                                                        slope.data_ptr(), B, CO, red.data_ptr(), dg1.data_ptr(), dbe1.data_ptr(),
+                                                        dg2.data_ptr(), dbe2.data_ptr(), dslope.data_ptr(), st),
+                    'coskad_train_bn_prelu_bwd_grads')
+        else:
+            c.check(lib.coskad_train_bn_prelu_bwd(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(),
+                                                  g1.data_ptr(), be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(),
+                                                  B, CO, red.data_ptr(), dy1.data_ptr(), dy2.data_ptr(), st),
+                    'coskad_train_bn_prelu_bwd')
+            c.check(lib.coskad_train_bn_param_grads(c.h, red.data_ptr(), CO, dg1.data_ptr(), dbe1.data_ptr(), dg2.data_ptr(),
+                                                    dbe2.data_ptr(), dslope.data_ptr(), st), 'coskad_train_bn_param_grads')
         if tc:      # BatchNorm / PReLU backward applied inside the tensor-core data-gradient kernel
             c.check(lib.coskad_train_mix_bwd_tc(c.h, dout.data_ptr(), y1.data_ptr(), y2.data_ptr(), mi.data_ptr(), g1.data_ptr(),
                                                 be1.data_ptr(), g2.data_ptr(), be2.data_ptr(), slope.data_ptr(), red.data_ptr(),

@@ -237,6 +237,19 @@ int coskad_train_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, const 
 int coskad_train_bn_finalize(coskad_ctx* ctx, const double* stats, int64_t n_per_channel, int CO, float eps,
                              float momentum, float* rm1, float* rv1, float* rm2, float* rv2, float* mi, int64_t* nbt1,
                              int64_t* nbt2, void* stream);
+/* coskad_train_mix_fwd + coskad_train_bn_finalize for the training forward on the tensor-core path: the statistics' second stage and
+ * the BatchNorm finalize are one launch and no intermediate `stats` buffer exists (the values are the same).
+ * replaces: nn.Conv2d 1x1 + nn.BatchNorm2d(train) statistics of both branches, models/graph_layers/stsgcn.py:56-62,74-79 */
+int coskad_train_mix_fwd_bn(coskad_ctx* ctx, const float* G, const float* X, const float* W1, const float* b1, const float* W2,
+                            const float* b2, int64_t B, int CI, int CO, float* y1, float* y2, float eps, float momentum,
+                            float* rm1, float* rv1, float* rm2, float* rv2, float* mi, int64_t* nbt1, int64_t* nbt2,
+                            void* stream);
+/* coskad_train_bn_prelu_bwd (dy1 = dy2 = NULL form) + coskad_train_bn_param_grads in two launches instead of three: `red`
+ * (double)[3*CO+1] is ASSIGNED (no zero fill needed), the parameter gradients are accumulated (each nullable). */
+int coskad_train_bn_prelu_bwd_grads(coskad_ctx* ctx, const float* dout, const float* y1, const float* y2, const float* mi,
+                                    const float* g1, const float* be1, const float* g2, const float* be2, const float* slope,
+                                    int64_t B, int CO, double* red, float* dg1, float* dbe1, float* dg2, float* dbe2,
+                                    float* dslope, void* stream);
 /* parameter gradients of the layer's two BatchNorms and its PReLU from `red` (coskad_train_bn_prelu_bwd), ACCUMULATED into
  * dg1 / dbe1 / dg2 / dbe2 [CO] and dslope [1] (each nullable): d beta1 = d beta2 = red[0..CO), d gamma1 = red[CO..2CO),
  * d gamma2 = red[2CO..3CO), d slope = red[3CO].  replaces: autograd of nn.BatchNorm2d / nn.PReLU parameters, stsgcn.py:62,79,82 */
