@@ -434,16 +434,27 @@ def leg_train(env: Env, steps: int, warm: int, fp32_peak: float):
 
     for i in range(warm):
         step(i)
+    # one untimed epoch end as well: its first call pays one-off costs (lazy CUDA module loads of the norm / logging ops, the NCCL
+    # communicator's first small all-reduce) that made the timed region vary by up to 27 ms from run to run
+    lit.training_epoch_end([])
     env.barrier()
     lit.on_train_epoch_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    trace = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)] if os.environ.get('COSKAD_BENCH_TRAIN_TRACE') else None
     e0.record()
     for i in range(steps):
+        if trace:
+            trace[i].record()
         step(warm + i)
+    if trace:
+        trace[steps].record()
     lit.training_epoch_end([])                               # center: all-reduce of D+2 doubles + finalisation
     e1.record()
     env.barrier()
     total = env.max_ms(e0.elapsed_time(e1))
+    if trace:            # debugging aid: per-step device times of the timed region
+        print('train_step trace (ms):', ' '.join(f'{trace[i].elapsed_time(trace[i + 1]):.3f}' for i in range(steps)),
+              '| epoch end', f'{trace[steps].elapsed_time(e1):.3f}', file=sys.stderr)
     loss = float(losses[-1])
     ach = 3 * FLOP_PER_WINDOW * TRAIN_BATCH * steps / (total * 1e-3) / 1e12
     del pool
