@@ -958,12 +958,30 @@ static int launch_tc_bwd_data(coskad_ctx* ctx, const float* dout, const float* y
   const int64_t E = B * kP, ntiles = (E + kTcT - 1) / kTcT;
   int per_sm = 512 / tmem_alloc_cols(4 * kBwdKC + 2 * NP);
   if (per_sm > 4) per_sm = 4;
+  // COSKAD_BWD_ASYNC=0 selects the register-load kernel (A/B measurement); default: cp.async staging one pass ahead.  The staging
+  // buffer (24 KB) may cost a resident CTA where the weight images are large (64 -> 64 channels: 3 instead of 4 per SM).
+  static const bool async = [] { const char* e = getenv("COSKAD_BWD_ASYNC"); return e == nullptr || atoi(e) != 0; }();
+  if (async) {
+    cudaFuncAttributes attr{};
+    CK(cudaFuncGetAttributes(&attr, tc_mix_bwd_data_kernel<CO, COK, NP, true>));
+    const size_t stage = sizeof(float) * kBwdStageFloats;
+    while (per_sm > 1 && (attr.sharedSizeBytes + stage + 1024) * per_sm > static_cast<size_t>(227) * 1024) --per_sm;
+    const size_t target = (static_cast<size_t>(228) * 1024) / static_cast<size_t>(per_sm) - 1536;
+    const size_t dyn = target > attr.sharedSizeBytes + stage ? target - attr.sharedSizeBytes : stage;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
+    const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
+    CK(cudaFuncSetAttribute(tc_mix_bwd_data_kernel<CO, COK, NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    tc_mix_bwd_data_kernel<CO, COK, NP, true><<<g, kTcT, dyn, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, E, CI, dy1,
+                                                                    dy2, dG, dXres);
+    CK_LAUNCH();
+    return COSKAD_OK;
+  }
   const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
   const int g = static_cast<int>(ntiles < cap ? ntiles : cap);
-  const size_t pad = tmem_pad_smem(tc_mix_bwd_data_kernel<CO, COK, NP>, per_sm);
-  CK(cudaFuncSetAttribute(tc_mix_bwd_data_kernel<CO, COK, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pad)));
-  tc_mix_bwd_data_kernel<CO, COK, NP><<<g, kTcT, pad, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, E, CI, dy1, dy2,
-                                                        dG, dXres);
+  const size_t pad = tmem_pad_smem(tc_mix_bwd_data_kernel<CO, COK, NP, false>, per_sm);
+  CK(cudaFuncSetAttribute(tc_mix_bwd_data_kernel<CO, COK, NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pad)));
+  tc_mix_bwd_data_kernel<CO, COK, NP, false><<<g, kTcT, pad, st>>>(dout, y1, y2, mi, g1, be1, g2, be2, slope, red, W1, W2, E, CI, dy1, dy2,
+                                                               dG, dXres);
   CK_LAUNCH();
   return COSKAD_OK;
 }

@@ -190,7 +190,13 @@ __global__ void __launch_bounds__(kTcT) tc_mix_fwd_kernel(const float* __restric
 // NP = max(16, c_in) output columns per branch; the K = COK = max(16, c_out) channels go through TMEM in chunks of KC = 16
 // (few TMEM columns per CTA: the resident CTAs, not a deeper pipeline inside one, hide the HBM latency).
 constexpr int kBwdKC = 16;
-template <int CO, int COK, int NP>
+// ASYNC: the (dout, y1, y2) values of a 16-channel pass are staged through a dynamic shared-memory buffer [3][16][128] with
+// 16-byte cp.async copies (12 per thread instead of 48 scalar loads; 4 consecutive positions never straddle a window:
+// 204 = 4 * 51) that are issued one pass AHEAD -- right after every thread has copied the current pass out of the buffer --
+// so the HBM latency of pass i + 1 overlaps the BatchNorm / PReLU arithmetic, the dy stores and the TMEM staging of pass i
+// without holding the values in registers (a register prefetch cost a resident CTA per SM and was slower).
+constexpr int kBwdStageFloats = 3 * kBwdKC * kTcT;                // 6144 floats = 24 KB
+template <int CO, int COK, int NP, bool ASYNC>
 __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
     const float* __restrict__ dout, const float* __restrict__ y1, const float* __restrict__ y2, const float* __restrict__ mi,
     const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ g2, const float* __restrict__ be2,
@@ -204,7 +210,26 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
   __shared__ float cst[13][COK];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar;
+  extern __shared__ __align__(16) float bwd_stage[];              // ASYNC: [3][16][128] (dout | y1 | y2 of one pass)
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t ntiles = (E + kTcT - 1) / kTcT;
+  // ASYNC: thread tid copies the position quad (tid % 32) of the rows (array, channel) = warp + 4 k, k = 0..11
+  auto issue_async = [&](int64_t t, int ch) {
+    if (t >= ntiles) return;
+    int64_t e = t * kTcT + 4 * (tid & 31);
+    if (e >= E) e = 0;                                            // ragged last tile: any valid quad, masked by `ok` later
+    const int64_t b = e / kP;
+    const int64_t base = (b * CO) * kP + (e - b * kP);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int row = warp + 4 * k, arr = row >> 4;
+      int co = ch * kBwdKC + (row & 15);
+      if (co >= CO) co = CO - 1;                                  // padded channels (c_out < 16): masked by `in` later
+      const float* src = (arr == 0 ? dout : arr == 1 ? y1 : y2) + base + static_cast<int64_t>(co) * kP;
+      cp_async16(bwd_stage + row * kTcT + 4 * (tid & 31), src);
+    }
+  };
+  if (ASYNC) { issue_async(blockIdx.x, 0); cp_async_commit(); }
   for (int i = tid; i < NP * COK; i += kTcT) {
     const int n = i / COK, k = i - n * COK;                       // n = ci, k = co
     const bool in = n < CI && k < CO;
@@ -233,12 +258,12 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
   if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
   tc::fence_proxy_async_smem();
   tc::fence_before_sync();
+  if (ASYNC) cp_async_wait_all();                                 // the first pass has landed when the barrier opens
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
   const uint32_t lane_base = tbase + (static_cast<uint32_t>(warp * 32) << 16);
   const float a = slope[0];
-  const int64_t ntiles = (E + kTcT - 1) / kTcT;
   uint32_t phase = 0;
   static_assert(KC == 16, "one 16-channel group per pass");
   // the (dout, y1, y2) values of a 16-channel pass: 48 unconditional loads in flight together (an out-of-range thread reads
@@ -269,9 +294,21 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       float dv[16], uv[16], vv[16];
-      issue(t, ch);
+      if (ASYNC) {
+        // this pass is in the staging buffer (waited for before the previous barrier): copy it out, and as soon as every
+        // thread has done so, put the next pass in flight
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { dv[j] = nd[j]; uv[j] = nu[j]; vv[j] = nv[j]; }
+        for (int j = 0; j < 16; ++j) {
+          dv[j] = bwd_stage[j * kTcT + tid]; uv[j] = bwd_stage[(16 + j) * kTcT + tid]; vv[j] = bwd_stage[(32 + j) * kTcT + tid];
+        }
+        __syncthreads();
+        if (ch + 1 < NCH) issue_async(t, ch + 1); else issue_async(t + gridDim.x, 0);
+        cp_async_commit();
+      } else {
+        issue(t, ch);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { dv[j] = nd[j]; uv[j] = nu[j]; vv[j] = nv[j]; }
+      }
       uint32_t h1[16], l1[16], h2[16], l2[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -302,6 +339,7 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
       tc::tmem_st16(lane_base + 3 * KC, l2);
       tc::wait_st();
       tc::fence_before_sync();
+      if (ASYNC) cp_async_wait_all();                             // the next pass (in flight since the top of this one)
       __syncthreads();
       if (tid == 0) {
         tc::fence_after_sync();
