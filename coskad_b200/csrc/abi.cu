@@ -1088,7 +1088,20 @@ extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_sma
   }
   else if (mode == 1) lin_expand_f_kernel<16><<<dim3((F + kTrainThreads - 1) / kTrainThreads, static_cast<unsigned>((B + kExpRows - 1) / kExpRows)), kTrainThreads, 0, st>>>(a_small, W, sd, sf, bias, B, F, D, out);
   else if (mode == 2) {
-    const int nb = B >= 512 ? 4 : 1;                  // row slices: >= 16 rows per warp
+    // row slices: >= 16 rows per warp, and as many blocks as fill whole waves of the 2 resident blocks per SM (102 feature blocks
+    // x 4 slices = 408 blocks were 1.38 waves on 296 slots: the second wave ran at 38 % occupancy)
+    int nb = B >= 512 ? 4 : 1;
+    if (B >= 1024) {
+      static const int env_nb = [] { const char* e = getenv("COSKAD_WGRAD_SLICES"); return e ? atoi(e) : 0; }();
+      const int fb = (F + kWgF - 1) / kWgF, slots = 2 * ctx->sm_count;
+      double best = 0.0;
+      for (int c = 2; c <= 8 && B / c >= 128; ++c) {
+        const int blocks = fb * c, waves = (blocks + slots - 1) / slots;
+        const double eff = static_cast<double>(blocks) / (static_cast<double>(waves) * slots);
+        if (eff > best + 1e-9) { best = eff; nb = c; }
+      }
+      if (env_nb > 0) nb = env_nb;
+    }
     const size_t n = static_cast<size_t>(D) * F;
     { const int rc = ensure_ws(ctx, sizeof(float) * n * nb); if (rc) return rc; }
     lin_wgrad_kernel<16><<<dim3((F + kWgF - 1) / kWgF, nb), kTrainThreads, 0, st>>>(a_small, A_wide, sd, sf, B, F, D, ctx->ws);

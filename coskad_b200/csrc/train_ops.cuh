@@ -834,7 +834,8 @@ __global__ void __launch_bounds__(kGThreads) chan_gemm_kernel(const float* __res
 // writes its partial sums to its slice of `out` ([slices][B][D]); partial_sum_kernel adds the slices in a fixed order.  A lane takes 4 consecutive features: 16-byte loads
 // of the activations (4 in flight per lane) and of the staged weights; F % 4 == 0 (host-checked).
 constexpr int kLinRows = 4;            // rows per warp
-constexpr int kLinFC = 512;            // features per staged chunk
+constexpr int kLinFC = 512;            // features per staged chunk (544 = a third of a 1 632-feature slice was measured slower:
+                                       // 4.25 lane strides per chunk leave most lanes idle in the fifth)
 constexpr int kLinSlices = 8;
 template <int DMAX>
 __global__ void lin_reduce_f_kernel(const float* __restrict__ A, const float* __restrict__ W, int64_t sd, int64_t sf,
