@@ -92,10 +92,90 @@ constexpr int kCWarps = kCThreads / 32;
 // blocks per SM, the C = 16 stages: lane = (row % 16, output half)): with two resident blocks the load -> compute -> store
 // phases of one overlap the other's and the FP32 stages see 24 instead of 12 warps per SM.
 constexpr int kCRowsSmall = kNW * 16;            // 48
-__host__ __device__ constexpr int contract_smem_bytes(int nr) { return (2 * nr * kCS + kTwFloats + kAwFloats) * 4; }
+// plane stride (floats): 205 (odd: the 32 lanes = rows of the C = 32 stages hit 32 banks) for the 96-row kernels; 206 for the 48-row
+// kernels: the 16 lanes = channels of the C = 16 stages are 14 c mod 32 apart -- 16 distinct banks, the two output halves
+// broadcast -- and an EVEN stride makes every row 8-byte aligned, so rows move with 8-byte cp.async / LDS.64 / STG.64: half the
+// load / store instructions of these MIO-bound phases (ncu: mio_throttle is their top stall)
+__host__ __device__ constexpr int contract_stride(int nr) { return nr == 3 * 16 ? 206 : kCS; }
+__host__ __device__ constexpr int contract_smem_bytes(int nr) { return (2 * nr * contract_stride(nr) + kTwFloats + kAwFloats) * 4; }
 constexpr int kCSmemBytes = contract_smem_bytes(kCRows);
 static_assert(kCSmemBytes <= 227 * 1024, "contraction kernels: shared memory plan exceeds 227 KB");
 static_assert(2 * (contract_smem_bytes(kCRowsSmall) + 1024) <= 227 * 1024, "two 48-row blocks per SM");
+// the C = 16 contraction stages of fused_eval.cuh (lane = (channel, output half), 3 row groups per lane, FFMA2) with the plane
+// stride as a template parameter; src == dst is allowed
+template <int NWARPS, int CS>
+__device__ __forceinline__ void temporal_stage_c16_cs(const float* src, float* dst, const float* Tw, int warp, int lane) {
+  const int c = lane & 15, q0 = (lane >> 4) * 6;
+  for (int v = warp; v < kV; v += NWARPS) {
+    unsigned long long acc[kNW][3];
+#pragma unroll
+    for (int n = 0; n < kNW; ++n)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc[n][q] = 0ull;
+    const float* s_ = src + c * CS + v;
+    const float* w = Tw + v * (kT * kT) + q0;
+#pragma unroll 4
+    for (int t = 0; t < kT; ++t) {
+      unsigned long long x[kNW];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) x[n] = dup2(s_[n * 16 * CS + t * kV]);
+      const unsigned long long w01 = *reinterpret_cast<const unsigned long long*>(w + t * kT);
+      const unsigned long long w23 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 2);
+      const unsigned long long w45 = *reinterpret_cast<const unsigned long long*>(w + t * kT + 4);
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) {
+        ffma2(acc[n][0], x[n], w01); ffma2(acc[n][1], x[n], w23); ffma2(acc[n][2], x[n], w45);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      float* d = dst + (n * 16 + c) * CS + v;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { d[(q0 + 2 * q) * kV] = lo2(acc[n][q]); d[(q0 + 2 * q + 1) * kV] = hi2(acc[n][q]); }
+    }
+  }
+}
+template <int NWARPS, int CS>
+__device__ __forceinline__ void spatial_stage_c16_cs(float* buf, const float* Aw, int warp, int lane) {
+  const int c = lane & 15, h = lane >> 4;
+  for (int t = warp; t < kT; t += NWARPS) {
+    unsigned long long acc[kNW][4];
+    float acc8[kNW];
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[n][j] = 0ull;
+      acc8[n] = 0.f;
+    }
+    const float* s_ = buf + c * CS + t * kV;
+    const float* a = Aw + t * (kV * kAW) + 8 * h;
+#pragma unroll 1
+    for (int v = 0; v < kV; ++v) {
+      float g[kNW];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) g[n] = s_[n * 16 * CS + v];
+      const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(a + v * kAW);
+      const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(a + v * kAW + 4);
+      const float w8 = a[v * kAW + 8];
+#pragma unroll
+      for (int n = 0; n < kNW; ++n) {
+        const unsigned long long g2 = dup2(g[n]);
+        ffma2(acc[n][0], g2, w0.x); ffma2(acc[n][1], g2, w0.y);
+        ffma2(acc[n][2], g2, w1.x); ffma2(acc[n][3], g2, w1.y);
+        acc8[n] = fmaf(g[n], w8, acc8[n]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < kNW; ++n) {
+      float* d = buf + (n * 16 + c) * CS + t * kV;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { d[8 * h + 2 * j] = lo2(acc[n][j]); d[8 * h + 2 * j + 1] = hi2(acc[n][j]); }
+      if (h == 1) d[16] = acc8[n];
+    }
+  }
+}
 template <int NR> struct ContractStages;
 template <> struct ContractStages<kCRows> {
   static __device__ __forceinline__ void temporal(const float* src, float* dst, const float* Tw, int warp, int lane) {
@@ -107,10 +187,10 @@ template <> struct ContractStages<kCRows> {
 };
 template <> struct ContractStages<kCRowsSmall> {
   static __device__ __forceinline__ void temporal(const float* src, float* dst, const float* Tw, int warp, int lane) {
-    temporal_stage_c16<kCThreads / 32>(src, dst, Tw, warp, lane);
+    temporal_stage_c16_cs<kCThreads / 32, contract_stride(kCRowsSmall)>(src, dst, Tw, warp, lane);
   }
   static __device__ __forceinline__ void spatial(float* buf, const float* Aw, int warp, int lane) {
-    spatial_stage_c16<EpiIdentity, kCThreads / 32>(buf, Aw, EpiIdentity{}, warp, lane);
+    spatial_stage_c16_cs<kCThreads / 32, contract_stride(kCRowsSmall)>(buf, Aw, warp, lane);
   }
 };
 constexpr int kContractPart = kT * kV * kV + kV * kT * kT;     // floats of one block's [dA | dT] partial
@@ -118,16 +198,56 @@ constexpr int kContractPart = kT * kV * kV + kV * kT * kT;     // floats of one 
 // Row-block copies, one warp per row (rows warp, warp + 12, ..), lanes = positions p = lane + 32 k: one pointer per row and
 // a few instructions per element (a flat element index cost ~20 integer instructions per 4-byte copy).
 constexpr int kRowIters = (kP + 31) / 32;                         // 7
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned s_ = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s_), "l"(gmem) : "memory");
+}
 template <int NR>
 __device__ __forceinline__ void contract_load_rows(float* dst, const float* __restrict__ src, int64_t r0, int nr, int tid) {
+  constexpr int CS = contract_stride(NR);
   const int warp = tid >> 5, lane = tid & 31;
   for (int row = warp; row < NR; row += kCWarps) {
     const float* s = src + (r0 + (row < nr ? row : nr - 1)) * kP;   // ragged last block: replicate the last row, never stored
-    float* d = dst + row * kCS;
+    float* d = dst + row * CS;
+    if constexpr (CS % 2 == 0) {                                    // 8-byte copies: rows are 8-byte aligned on both sides
 #pragma unroll
-    for (int k = 0; k < kRowIters; ++k) {
-      const int p = lane + 32 * k;
-      if (p < kP) cp_async4(d + p, s + p);
+      for (int k = 0; k < (kP / 2 + 31) / 32; ++k) {
+        const int p = 2 * (lane + 32 * k);
+        if (p < kP) cp_async8(d + p, s + p);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kRowIters; ++k) {
+        const int p = lane + 32 * k;
+        if (p < kP) cp_async4(d + p, s + p);
+      }
+    }
+  }
+}
+// L2 prefetch of rows [r0, r0 + nr) of a [R][204] array (one 128-byte line per request): issued one block ahead, so that the
+// later cp.async / LDG of these rows find them in L2 (the kernels have no shared memory or registers left for a deeper pipeline)
+__device__ __forceinline__ void contract_prefetch_rows(const float* __restrict__ src, int64_t r0, int nr, int tid) {
+  const char* base = reinterpret_cast<const char*>(src + r0 * kP);
+  const int nlines = (nr * kP * 4 + 127) / 128;
+  for (int i = tid; i < nlines; i += kCThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<int64_t>(i) * 128));
+}
+// the T / A operator tables -> shared memory with all loads of a thread in flight together (as a load -> store loop the
+// prologue exposed one L2 / HBM round trip per element: 12-17 % of the kernels' time, ncu source page)
+template <class F>
+__device__ __forceinline__ void contract_fill_table(float* dst, int n, int tid, F value_ptr) {
+  constexpr int kBatch = 6;
+  for (int i0 = tid; i0 < n; i0 += kCThreads * kBatch) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * kCThreads;
+      const float* p = value_ptr(i < n ? i : n - 1);
+      v[u] = p ? __ldg(p) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * kCThreads;
+      if (i < n) dst[i] = v[u];
     }
   }
 }
@@ -135,9 +255,42 @@ __device__ __forceinline__ void contract_load_rows(float* dst, const float* __re
 template <int NR>
 __device__ __forceinline__ void contract_store_rows(float* __restrict__ dst, const float* planes, const float* __restrict__ add,
                                                     int64_t r0, int nr, int tid) {
+  constexpr int CS = contract_stride(NR);
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int kRB = 4;
   static_assert(NR % (kCWarps * kRB) == 0, "row-block store plan");
+  if constexpr (CS % 2 == 0) {                                      // 8-byte path: LDS.64 + (LDG.64) + STG.64, 4 iterations per row
+    constexpr int kIt = (kP / 2 + 31) / 32;
+    for (int rb = warp; rb < NR; rb += kCWarps * kRB) {
+      float2 a[kRB][kIt];
+#pragma unroll
+      for (int j = 0; j < kRB; ++j) {
+        const int row = rb + j * kCWarps;
+#pragma unroll
+        for (int k = 0; k < kIt; ++k) {
+          const int p = 2 * (lane + 32 * k);
+          a[j][k] = (add != nullptr && row < nr && p < kP) ? __ldg(reinterpret_cast<const float2*>(add + (r0 + row) * kP + p)) : make_float2(0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kRB; ++j) {
+        const int row = rb + j * kCWarps;
+        if (row < nr) {
+          float* d = dst + (r0 + row) * kP;
+          const float* s = planes + row * CS;
+#pragma unroll
+          for (int k = 0; k < kIt; ++k) {
+            const int p = 2 * (lane + 32 * k);
+            if (p < kP) {
+              const float2 v = *reinterpret_cast<const float2*>(s + p);
+              *reinterpret_cast<float2*>(d + p) = make_float2(v.x + a[j][k].x, v.y + a[j][k].y);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int rb = warp; rb < NR; rb += kCWarps * kRB) {
     float a[kRB][kRowIters];
 #pragma unroll
@@ -154,7 +307,7 @@ __device__ __forceinline__ void contract_store_rows(float* __restrict__ dst, con
       const int row = rb + j * kCWarps;
       if (row < nr) {
         float* d = dst + (r0 + row) * kP;
-        const float* s = planes + row * kCS;
+        const float* s = planes + row * CS;
 #pragma unroll
         for (int k = 0; k < kRowIters; ++k) {
           const int p = lane + 32 * k;
@@ -171,19 +324,20 @@ __global__ void __launch_bounds__(kCThreads, NR == kCRows ? 1 : 2) train_contrac
                                                                          const float* __restrict__ T, int64_t R,
                                                                          float* __restrict__ G1, float* __restrict__ G) {
   extern __shared__ __align__(128) float csm[];
+  constexpr int CS = contract_stride(NR);
   float* Xs = csm;
-  float* Gs = Xs + NR * kCS;
-  float* Ts = Gs + NR * kCS;
+  float* Gs = Xs + NR * CS;
+  float* Ts = Gs + NR * CS;
   float* As = Ts + kTwFloats;                      // rows padded 17 -> kAW
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < kTwFloats; i += kCThreads) Ts[i] = T[i];
-  for (int i = tid; i < kAwFloats; i += kCThreads) { const int w = i % kAW, tv = i / kAW; As[i] = (w < kV) ? A[tv * kV + w] : 0.f; }
   const int64_t nblk = (R + NR - 1) / NR;
-  if (static_cast<int64_t>(blockIdx.x) < nblk) {
+  if (static_cast<int64_t>(blockIdx.x) < nblk) {                  // the first block's rows fly while the tables are filled
     const int64_t r0 = static_cast<int64_t>(blockIdx.x) * NR;
     contract_load_rows<NR>(Xs, X, r0, static_cast<int>(R - r0 < NR ? R - r0 : NR), tid);
   }
   cp_async_commit();
+  contract_fill_table(Ts, kTwFloats, tid, [&](int i) { return T + i; });
+  contract_fill_table(As, kAwFloats, tid, [&](int i) -> const float* { const int w = i % kAW, tv = i / kAW; return (w < kV) ? A + tv * kV + w : nullptr; });
   for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     const int64_t r0 = blk * NR;
     const int nr = static_cast<int>(R - r0 < NR ? R - r0 : NR);
@@ -212,16 +366,17 @@ __global__ void __launch_bounds__(kCThreads, NR == kCRows ? 1 : 2) train_contrac
     const float* __restrict__ dG, const float* __restrict__ dXres, const float* __restrict__ X, const float* __restrict__ G1,
     const float* __restrict__ A, const float* __restrict__ T, int64_t R, float* __restrict__ dX, float* __restrict__ part) {
   extern __shared__ __align__(128) float csm[];
+  constexpr int CS = contract_stride(NR);
   float* P0 = csm;                                 // dG -> dG1 (in place)
-  float* P1 = P0 + NR * kCS;                   // G1, then X, then dX
-  float* Tt = P1 + NR * kCS;                   // Tt[v][q][t] = T[v][t][q]
+  float* P1 = P0 + NR * CS;                        // G1, then X, then dX
+  float* Tt = P1 + NR * CS;                        // Tt[v][q][t] = T[v][t][q]
   float* At = Tt + kTwFloats;                      // At[t][w][v] = A[t][v][w], rows padded 17 -> kAW
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < kTwFloats; i += kCThreads) { const int v = i / (kT * kT), q = (i / kT) % kT, t = i % kT; Tt[i] = T[v * (kT * kT) + t * kT + q]; }
-  for (int i = tid; i < kAwFloats; i += kCThreads) {
+  contract_fill_table(Tt, kTwFloats, tid, [&](int i) { const int v = i / (kT * kT), q = (i / kT) % kT, t = i % kT; return T + v * (kT * kT) + t * kT + q; });
+  contract_fill_table(At, kAwFloats, tid, [&](int i) -> const float* {
     const int v = i % kAW, tw = i / kAW, t = tw / kV, w = tw % kV;
-    At[i] = (v < kV) ? A[(t * kV + v) * kV + w] : 0.f;
-  }
+    return (v < kV) ? A + (t * kV + v) * kV + w : nullptr;
+  });
   // dA tiles: thread < 300 owns (t, 4 v, 4 w); dT tiles: thread < 306 owns (v, 4 t, 2 q)
   const bool hasA = tid < kT * 25, hasT = tid < kV * 18;
   const int at = tid / 25, avg = (tid % 25) / 5, awg = tid % 5;
@@ -249,13 +404,24 @@ __global__ void __launch_bounds__(kCThreads, NR == kCRows ? 1 : 2) train_contrac
     contract_load_rows<NR>(P0, dG, r0, nr, tid);
     contract_load_rows<NR>(P1, G1, r0, nr, tid);
     cp_async_commit();
+    {   // this block's late operands (X, dXres) and the next block's early ones (dG, G1): into L2 now, used 1-4 stages later
+      contract_prefetch_rows(X, r0, nr, tid);
+      if (dXres != nullptr) contract_prefetch_rows(dXres, r0, nr, tid);
+      const int64_t nb = blk + gridDim.x;
+      if (nb < nblk) {
+        const int64_t n0 = nb * NR;
+        const int nn = static_cast<int>(R - n0 < NR ? R - n0 : NR);
+        contract_prefetch_rows(dG, n0, nn, tid);
+        contract_prefetch_rows(G1, n0, nn, tid);
+      }
+    }
     cp_async_wait_all();
     __syncthreads();
     if (hasA) {
       for (int r = 0; r < nr; ++r) {
         float g[4], d[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { g[i] = P1[r * kCS + aiv[i]]; d[i] = P0[r * kCS + aiw[i]]; }
+        for (int i = 0; i < 4; ++i) { g[i] = P1[r * CS + aiv[i]]; d[i] = P0[r * CS + aiw[i]]; }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -272,8 +438,8 @@ __global__ void __launch_bounds__(kCThreads, NR == kCRows ? 1 : 2) train_contrac
       for (int r = 0; r < nr; ++r) {
         float x[4], d[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = P1[r * kCS + tit[i]];
-        d[0] = P0[r * kCS + tiq[0]]; d[1] = P0[r * kCS + tiq[1]];
+        for (int i = 0; i < 4; ++i) x[i] = P1[r * CS + tit[i]];
+        d[0] = P0[r * CS + tiq[0]]; d[1] = P0[r * CS + tiq[1]];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { accT[i][0] = fmaf(x[i], d[0], accT[i][0]); accT[i][1] = fmaf(x[i], d[1], accT[i][1]); }
       }
