@@ -35,6 +35,34 @@ __host__ __device__ constexpr int tmem_alloc_cols(int need) {
 // canonical K-major, no swizzle: element (n, k) of an [N][K] operand; LBO = (N/8)*128 B, SBO = 128 B (fold.cuh, tc_test.cuh)
 __device__ __forceinline__ int kmaj_idx(int n, int k, int N) { return ((k >> 2) * (N >> 3) + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3); }
 
+// hi / lo K-major images of a (zero-padded) weight matrix pair, built with all global loads of a thread in flight together: as a
+// load -> split -> store loop the prologue exposed one L2 round trip per element (8-10 % of the kernels, ncu source page)
+template <int NROWS, int KDIM, class F>
+__device__ __forceinline__ void build_weight_images(float (*wimg)[NROWS * KDIM], int tid, F elem) {
+  constexpr int kBatch = 8;
+  for (int i0 = tid; i0 < NROWS * KDIM; i0 += kTcT * kBatch) {
+    float a[kBatch], b[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * kTcT;
+      const int ii = i < NROWS * KDIM ? i : NROWS * KDIM - 1;
+      elem(ii / KDIM, ii % KDIM, a[u], b[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * kTcT;
+      if (i < NROWS * KDIM) {
+        const int n = i / KDIM, k = i - n * KDIM;
+        uint32_t h, l;
+        tc::split_tf32(a[u], h, l);
+        wimg[0][kmaj_idx(n, k, NROWS)] = __uint_as_float(h); wimg[1][kmaj_idx(n, k, NROWS)] = __uint_as_float(l);
+        tc::split_tf32(b[u], h, l);
+        wimg[2][kmaj_idx(n, k, NROWS)] = __uint_as_float(h); wimg[3][kmaj_idx(n, k, NROWS)] = __uint_as_float(l);
+      }
+    }
+  }
+}
+
 // ---- forward: y1 = conv1x1(G; W1, b1), y2 = conv1x1(X; W2, b2) + per-CTA BatchNorm statistics ---------------------------
 // part [gridDim.x][4*CO] = sum y1, sum y1^2, sum y2, sum y2^2 per channel of the positions the CTA owned.
 // CIP = c_in padded to a multiple of 8 (K step of kind::tf32), COP = c_out padded to a multiple of 16 (N of an M = 128 MMA).
@@ -53,15 +81,11 @@ __global__ void __launch_bounds__(kTcT) tc_mix_fwd_kernel(const float* __restric
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < COP * CIP; i += kTcT) {
-    const int n = i / CIP, k = i - n * CIP;
+  build_weight_images<COP, CIP>(wimg, tid, [&](int n, int k, float& a, float& b) {
     const bool in = n < CO && k < CI;
-    uint32_t h, l;
-    tc::split_tf32(in ? W1[n * CI + k] : 0.f, h, l);
-    wimg[0][kmaj_idx(n, k, COP)] = __uint_as_float(h); wimg[1][kmaj_idx(n, k, COP)] = __uint_as_float(l);
-    tc::split_tf32(in ? W2[n * CI + k] : 0.f, h, l);
-    wimg[2][kmaj_idx(n, k, COP)] = __uint_as_float(h); wimg[3][kmaj_idx(n, k, COP)] = __uint_as_float(l);
-  }
+    a = in ? __ldg(W1 + n * CI + k) : 0.f;
+    b = in ? __ldg(W2 + n * CI + k) : 0.f;
+  });
   for (int i = tid; i < 2 * COP; i += kTcT) {
     const int br = i / COP, co = i % COP;
     const float* bp = br ? b2 : b1;
@@ -207,7 +231,7 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
   constexpr int kColD = 4 * KC;                                   // A: dy1_hi, dy1_lo, dy2_hi, dy2_lo; D: dG | dXres
   constexpr int kAlloc = tmem_alloc_cols(4 * KC + 2 * NP);
   __shared__ __align__(128) float wimg[4][NP * COK];              // (W1^T) hi, lo, (W2^T) hi, lo: [N = ci][K = co]
-  __shared__ float cst[13][COK];
+  __shared__ __align__(16) float cst[COK][16];                    // 13 per-channel constants, one 64-byte row per channel: 4 LDS.128
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar;
   extern __shared__ __align__(16) float bwd_stage[];              // ASYNC: [3][16][128] (dout | y1 | y2 of one pass)
@@ -230,29 +254,26 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
     }
   };
   if (ASYNC) { issue_async(blockIdx.x, 0); cp_async_commit(); }
-  for (int i = tid; i < NP * COK; i += kTcT) {
-    const int n = i / COK, k = i - n * COK;                       // n = ci, k = co
+  build_weight_images<NP, COK>(wimg, tid, [&](int n, int k, float& a_, float& b_) {       // n = ci, k = co
     const bool in = n < CI && k < CO;
-    uint32_t h, l;
-    tc::split_tf32(in ? W1[k * CI + n] : 0.f, h, l);
-    wimg[0][kmaj_idx(n, k, NP)] = __uint_as_float(h); wimg[1][kmaj_idx(n, k, NP)] = __uint_as_float(l);
-    tc::split_tf32(in ? W2[k * CI + n] : 0.f, h, l);
-    wimg[2][kmaj_idx(n, k, NP)] = __uint_as_float(h); wimg[3][kmaj_idx(n, k, NP)] = __uint_as_float(l);
-  }
+    a_ = in ? __ldg(W1 + k * CI + n) : 0.f;
+    b_ = in ? __ldg(W2 + k * CI + n) : 0.f;
+  });
   const double Nd = static_cast<double>(E);
   for (int co = tid; co < COK; co += kTcT) {
     if (co >= CO) {
 #pragma unroll
-      for (int q = 0; q < 13; ++q) cst[q][co] = 0.f;
+      for (int q = 0; q < 16; ++q) cst[co][q] = 0.f;
       continue;
     }
     const float i1 = mi[CO + co], i2 = mi[3 * CO + co], ga1 = g1[co], ga2 = g2[co];
-    cst[0][co] = mi[co]; cst[1][co] = i1; cst[2][co] = mi[2 * CO + co]; cst[3][co] = i2;
-    cst[4][co] = ga1; cst[5][co] = be1[co]; cst[6][co] = ga2; cst[7][co] = be2[co];
-    cst[8][co] = static_cast<float>(red[co] / Nd);
-    cst[9][co] = static_cast<float>(red[CO + co] / Nd);
-    cst[10][co] = static_cast<float>(red[2 * CO + co] / Nd);
-    cst[11][co] = ga1 * i1; cst[12][co] = ga2 * i2;
+    cst[co][0] = mi[co]; cst[co][1] = i1; cst[co][2] = mi[2 * CO + co]; cst[co][3] = i2;
+    cst[co][4] = ga1; cst[co][5] = be1[co]; cst[co][6] = ga2; cst[co][7] = be2[co];
+    cst[co][8] = static_cast<float>(red[co] / Nd);
+    cst[co][9] = static_cast<float>(red[CO + co] / Nd);
+    cst[co][10] = static_cast<float>(red[2 * CO + co] / Nd);
+    cst[co][11] = ga1 * i1; cst[co][12] = ga2 * i2;
+    cst[co][13] = cst[co][14] = cst[co][15] = 0.f;
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, kAlloc);
   if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
@@ -314,12 +335,13 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_data_kernel(
       for (int j = 0; j < 16; ++j) {
         const int co = ch * KC + j;
         float hh1, hh2;
-        const float pre = bn_pre(uv[j], vv[j], cst[0][co], cst[1][co], cst[2][co], cst[3][co], cst[4][co], cst[5][co],
-                                 cst[6][co], cst[7][co], hh1, hh2);
+        const float4 k0 = *reinterpret_cast<const float4*>(&cst[co][0]), k1 = *reinterpret_cast<const float4*>(&cst[co][4]);
+        const float4 k2 = *reinterpret_cast<const float4*>(&cst[co][8]), k3 = *reinterpret_cast<const float4*>(&cst[co][12]);
+        const float pre = bn_pre(uv[j], vv[j], k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, hh1, hh2);
         const float ds = pre > 0.f ? dv[j] : a * dv[j];
         const bool in = ok && co < CO;
-        const float r1 = in ? cst[11][co] * (ds - cst[8][co] - hh1 * cst[9][co]) : 0.f;
-        const float r2 = in ? cst[12][co] * (ds - cst[8][co] - hh2 * cst[10][co]) : 0.f;
+        const float r1 = in ? k2.w * (ds - k2.x - hh1 * k2.y) : 0.f;
+        const float r2 = in ? k3.x * (ds - k2.x - hh2 * k2.z) : 0.f;
         if (in) {
           const int64_t o = ybase + static_cast<int64_t>(co) * kP;
           dy1[o] = r1;
