@@ -460,10 +460,36 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
   // the 16-byte loads of a tile: unconditional, all in flight together while the previous tile's MMAs run; an item past the
   // end of the batch (E % 4 == 0: entirely in or out) or past the row list reads a valid address and is zeroed when consumed
   float4 vn[kItemsMax];
+  // item u of thread tid is the 16-byte chunk kc = tid % kCh of row r = tid / kCh + u * kRS.  When the class boundaries
+  // (c_out, 2 c_out, 2 c_out + c_in) are multiples of kRS -- every layer but the 2-channel input layer -- the class of an item
+  // (dy1 | dy2 | G | X), its channel and its image offset depend on u alone: resolved at compile time, and the tile position
+  // (window, offset) is computed once per tile instead of once per item.  (As generic per-item integer arithmetic this loop was
+  // 64 % of the kernel's time: 49 M of its 54 M warp instructions, ncu source page.)
+  constexpr int kRS = kTcT / kCh;                                  // rows between a thread's consecutive items
+  static_assert(kTcT % kCh == 0 && kRS % 8 == 0, "row step of the item mapping");
+  constexpr bool kAligned = (CO % kRS == 0) && (CI8 % kRS == 0);
+  const bool fast = kAligned && CI == CI8;
+  const int kcT = tid % kCh, rbT = tid / kCh;
+  const int oT = (rbT >> 3) * kSbo + kcT * kWgLbo + (rbT & 7) * 4;
   auto issue = [&](int64_t t) {
     const int64_t e0 = t * KT;
     const int64_t b0 = e0 / kP;
     const int p0 = static_cast<int>(e0 - b0 * kP);
+    if (fast) {
+      int p = p0 + 4 * kcT;
+      int64_t b = b0;
+      if (p >= kP) { p -= kP; b += 1; }
+      if (e0 + 4 * kcT >= E) { b = 0; p = 0; }
+      const int64_t off_co = (b * CO + rbT) * kP + p, off_ci = (b * CI8 + rbT) * kP + p;
+#pragma unroll
+      for (int u = 0; u < kItemsMax; ++u) {
+        constexpr int kUA = CO / kRS, kUB = CI8 / kRS;              // items per class
+        const int m = u < kUA ? u : u < 2 * kUA ? u - kUA : u < 2 * kUA + kUB ? u - 2 * kUA : u - 2 * kUA - kUB;
+        const float* src = u < kUA ? dy1 + off_co : u < 2 * kUA ? dy2 + off_co : u < 2 * kUA + kUB ? G + off_ci : X + off_ci;
+        if (u < 2 * kUA + 2 * kUB) vn[u] = tc::ldg_stay4(src + static_cast<int64_t>(m * kRS) * kP);
+      }
+      return;
+    }
 #pragma unroll
     for (int u = 0; u < kItemsMax; ++u) {
       int it = tid + u * kTcT;
@@ -490,6 +516,25 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
       phase ^= 1;
       tc::fence_after_sync();
     }
+    if (fast) {
+      const bool oob = e0 + 4 * kcT >= E;
+#pragma unroll
+      for (int u = 0; u < kItemsMax; ++u) {
+        constexpr int kUA = CO / kRS, kUB = CI8 / kRS;
+        if (u < 2 * kUA + 2 * kUB) {
+          const int m = u < kUA ? u : u < 2 * kUA ? u - kUA : u < 2 * kUA + kUB ? u - 2 * kUA : u - 2 * kUA - kUB;
+          float* hi_img = u < kUA ? Aimg : u < 2 * kUA ? Aimg + 2 * kAimg : u < 2 * kUA + kUB ? Bimg : Bimg + 2 * kBimg;
+          const int img = u < 2 * kUA ? kAimg : kBimg;
+          const int o = oT + m * (kRS / 8) * kSbo;
+          const float4 v = oob ? make_float4(0.f, 0.f, 0.f, 0.f) : vn[u];
+          uint32_t h[4], l[4];
+          tc::split_tf32(v.x, h[0], l[0]); tc::split_tf32(v.y, h[1], l[1]);
+          tc::split_tf32(v.z, h[2], l[2]); tc::split_tf32(v.w, h[3], l[3]);
+          *reinterpret_cast<uint4*>(hi_img + o) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(hi_img + img + o) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+    } else
 #pragma unroll
     for (int u = 0; u < kItemsMax; ++u) {
       const int it = tid + u * kTcT;
