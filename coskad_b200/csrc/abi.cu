@@ -836,7 +836,7 @@ static int launch_tc_mix_fwd(coskad_ctx* ctx, const float* G, const float* X, co
   tc_mix_fwd_kernel<CIP, CO, COP><<<g, kTcT, 0, st>>>(G, X, W1, b1, W2, b2, E, CI, y1, y2, ctx->ws);
   CK_LAUNCH();
   if (bn != nullptr) {      // statistics second stage + BatchNorm finalize in one launch
-    train_bn_stats_finalize_kernel<<<(CO + 31) / 32, dim3(32, kPsRows), 0, st>>>(ctx->ws, g, static_cast<double>(E), CO, bn->eps,
+    train_bn_stats_finalize_kernel<<<(CO + 7) / 8, dim3(32, kBsfRows), 0, st>>>(ctx->ws, g, static_cast<double>(E), CO, bn->eps,
                                                                                 bn->momentum, bn->rm1, bn->rv1, bn->rm2, bn->rv2,
                                                                                 bn->mi, bn->nbt1, bn->nbt2);
     CK_LAUNCH();

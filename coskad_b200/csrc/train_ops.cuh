@@ -493,35 +493,54 @@ __global__ void train_bn_finalize_kernel(const double* __restrict__ stats, doubl
 
 // second stage of the BatchNorm statistics (per-CTA partials [nparts][4*CO] of tc_mix_fwd_kernel, fixed order) fused with
 // train_bn_finalize_kernel: one launch instead of partial_sum + finalize (+ the zero fill of the intermediate sums); the
-// arithmetic is the same, value for value.  Block x owns channels 32 x .. 32 x + 31.
-__global__ void train_bn_stats_finalize_kernel(const float* __restrict__ part, int nparts, double N, int CO, float eps,
-                                               float momentum, float* rm1, float* rv1, float* rm2, float* rv2,
-                                               float* __restrict__ mi, int64_t* nbt1, int64_t* nbt2) {
-  __shared__ double sh[kPsRows][33];
-  __shared__ double tot[4][32];
-  const int co = blockIdx.x * 32 + threadIdx.x;
-  for (int q = 0; q < 4; ++q) {
-    const double t = partial_sum_block(part, nparts, 4 * CO, q * CO + co, co < CO, sh);
-    if (threadIdx.y == 0) tot[q][threadIdx.x] = t;
-    __syncthreads();
+// arithmetic is the same as the finalize kernel's.  Block x owns 8 channels: lane = quantity q * 8 + channel (q = sum y1, sum y1^2,
+// sum y2, sum y2^2), 32 rows of threads share the partials (row y adds partials y, y + 32, .. in ascending order, 8 loads in flight),
+// the rows meet in shared memory in a fixed order, and the quantities of a channel meet through shuffles.  (A first version with
+// 32 channels per block walked the four quantities one after the other on 1-2 blocks: 13.7 us per launch.)
+constexpr int kBsfRows = 32;
+__global__ void __launch_bounds__(32 * kBsfRows) train_bn_stats_finalize_kernel(
+    const float* __restrict__ part, int nparts, double N, int CO, float eps, float momentum, float* rm1, float* rv1, float* rm2,
+    float* rv2, float* __restrict__ mi, int64_t* nbt1, int64_t* nbt2) {
+  __shared__ double sh[kBsfRows][33];
+  const int lane = threadIdx.x, y = threadIdx.y;
+  const int q = lane >> 3, co = blockIdx.x * 8 + (lane & 7);
+  const bool ok = co < CO;
+  const int64_t i = static_cast<int64_t>(q) * CO + co, stride = 4 * CO;
+  double s = 0.0;
+  if (ok) {
+    int j = y;
+    for (; j + 7 * kBsfRows < nparts; j += 8 * kBsfRows) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[static_cast<int64_t>(j + u * kBsfRows) * stride + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += static_cast<double>(v[u]);
+    }
+    for (; j < nparts; j += kBsfRows) s += static_cast<double>(part[static_cast<int64_t>(j) * stride + i]);
   }
-  if (threadIdx.y != 0) return;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  sh[y][lane] = s;
+  __syncthreads();
+  if (y != 0) return;
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < kBsfRows; ++r) t += sh[r][lane];
+  // lane (q, c): q even holds a sum, q odd the matching sum of squares, 8 lanes further
+  const double sq = __shfl_down_sync(0xffffffffu, t, 8);
+  if (blockIdx.x == 0 && lane == 0) {
     if (nbt1) *nbt1 += 1;
     if (nbt2) *nbt2 += 1;
   }
-  if (co >= CO) return;
-  for (int br = 0; br < 2; ++br) {
-    const double mean = tot[2 * br][threadIdx.x] / N;
-    double var = tot[2 * br + 1][threadIdx.x] / N - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mi[(2 * br) * CO + co] = static_cast<float>(mean);
-    mi[(2 * br + 1) * CO + co] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    float* rm = br ? rm2 : rm1;
-    float* rv = br ? rv2 : rv1;
-    if (rm) rm[co] = (1.f - momentum) * rm[co] + momentum * static_cast<float>(mean);
-    if (rv) rv[co] = (1.f - momentum) * rv[co] + momentum * static_cast<float>(var * N / (N - 1.0));
-  }
+  if (!ok || (q & 1)) return;
+  const int br = q >> 1;
+  const double mean = t / N;
+  double var = sq / N - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mi[(2 * br) * CO + co] = static_cast<float>(mean);
+  mi[(2 * br + 1) * CO + co] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  float* rm = br ? rm2 : rm1;
+  float* rv = br ? rv2 : rv1;
+  if (rm) rm[co] = (1.f - momentum) * rm[co] + momentum * static_cast<float>(mean);
+  if (rv) rv[co] = (1.f - momentum) * rv[co] + momentum * static_cast<float>(var * N / (N - 1.0));
 }
 
 // BN1(y1) + BN2(y2) with a fixed operation order (explicit rounding intrinsics: no re-contraction), so that the
