@@ -67,11 +67,6 @@ __device__ __forceinline__ unsigned long long dup2(float x) {
 __device__ __forceinline__ float lo2(unsigned long long v) { return __uint_as_float(static_cast<uint32_t>(v & 0xffffffffull)); }
 __device__ __forceinline__ float hi2(unsigned long long v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
 
-// PReLU as multiply + min/max (2 instructions instead of multiply + compare + select): max(v, a v) for a <= 1, min(v, a v)
-// for a > 1 is v for v >= 0 and a v otherwise; the slope test is loop-invariant (FMNMX takes the min/max choice as a predicate)
-__device__ __forceinline__ float prelu(float v, float a) {
-  const float av = a * v;
-  return a <= 1.f ? fmaxf(v, av) : fminf(v, av);
-}
+__device__ __forceinline__ float prelu(float v, float a) { return v >= 0.f ? v : a * v; }
 
 }  // namespace coskad
