@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
   const bool fast = kAligned && CI == CI8;
   const int kcT = tid % kCh, rbT = tid / kCh;
   const int oT = (rbT >> 3) * kSbo + kcT * kWgLbo + (rbT & 7) * 4;
-  auto issue = [&](int64_t t) {
+  auto issue = [&](int64_t t, bool PF = false) {
     const int64_t e0 = t * KT;
     const int64_t b0 = e0 / kP;
     const int p0 = static_cast<int>(e0 - b0 * kP);
@@ -486,7 +486,10 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
         constexpr int kUA = CO / kRS, kUB = CI8 / kRS;              // items per class
         const int m = u < kUA ? u : u < 2 * kUA ? u - kUA : u < 2 * kUA + kUB ? u - 2 * kUA : u - 2 * kUA - kUB;
         const float* src = u < kUA ? dy1 + off_co : u < 2 * kUA ? dy2 + off_co : u < 2 * kUA + kUB ? G + off_ci : X + off_ci;
-        if (u < 2 * kUA + 2 * kUB) vn[u] = tc::ldg_stay4(src + static_cast<int64_t>(m * kRS) * kP);
+        if (u < 2 * kUA + 2 * kUB) {
+          if (PF) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + static_cast<int64_t>(m * kRS) * kP));
+          else vn[u] = tc::ldg_stay4(src + static_cast<int64_t>(m * kRS) * kP);
+        }
       }
       return;
     }
@@ -511,6 +514,10 @@ __global__ void __launch_bounds__(kTcT) tc_mix_bwd_weight_kernel(const float* __
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t e0 = t * KT;
     issue(t);                                                       // overlaps the previous tile's MMAs (waited for below)
+    // the tile after the next one: into L2 now (the loads of a tile only have the previous tile's MMA time to land: since the
+    // integer overhead is gone this kernel waits on them -- long scoreboard is its top stall -- and neither registers nor shared
+    // memory are left for a second tile in flight)
+    if (fast && t + 2 * static_cast<int64_t>(gridDim.x) < ntiles) issue(t + 2 * static_cast<int64_t>(gridDim.x), true);
     if (!first) {                                                   // the previous tile's MMAs still read the images
       tc::mbar_wait(&bar, phase);
       phase ^= 1;
