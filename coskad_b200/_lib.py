@@ -66,6 +66,8 @@ SIGNATURES = {
                                 + [C.c_float, C.c_float] + [c_float_p] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     'coskad_train_bn_prelu_bwd_grads': (C.c_int, [c_ctx_p] + [c_float_p] * 9 + [C.c_int64, C.c_int, C.c_void_p] + [c_float_p] * 5
                                         + [C.c_void_p]),
+    'coskad_adam_step': (C.c_int, [c_ctx_p] + [c_float_p] * 4 + [C.c_int64, c_float_p, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                   c_float_p, C.c_void_p]),
     'coskad_train_bn_param_grads': (C.c_int, [c_ctx_p, C.c_void_p, C.c_int] + [c_float_p] * 5 + [C.c_void_p]),
     'coskad_train_bn_prelu_fwd': (C.c_int, [c_ctx_p] + [c_float_p] * 8 + [C.c_int64, C.c_int, c_float_p, C.c_void_p]),
     'coskad_train_bn_prelu_bwd': (C.c_int, [c_ctx_p] + [c_float_p] * 9 + [C.c_int64, C.c_int, C.c_void_p, c_float_p, c_float_p, C.c_void_p]),

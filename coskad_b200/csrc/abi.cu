@@ -1112,6 +1112,23 @@ extern "C" int coskad_train_linear(coskad_ctx* ctx, int mode, const float* a_sma
   return COSKAD_OK;
 }
 
+extern "C" int coskad_adam_step(coskad_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, const float* lr,
+                                float beta1, float beta2, float eps, int64_t* step, float* scratch, void* stream_) {
+  TRAIN_PRE();
+  if (n <= 0) return COSKAD_OK;
+  if (!p || !g || !m || !v || !lr || !step || !scratch) return fail(ctx, COSKAD_ERR_ARG, "coskad_adam_step: NULL pointer");
+  if (n % 4) return fail(ctx, COSKAD_ERR_ARG, "coskad_adam_step: n must be a multiple of 4 (pad the flat buffers), got %lld", (long long)n);
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(ctx, COSKAD_ERR_ARG, "coskad_adam_step: buffers must be 16-byte aligned");
+  adam_tick_kernel<<<1, 1, 0, st>>>(step, scratch, beta1, beta2);
+  CK_LAUNCH();
+  const int64_t n4 = n / 4;
+  const int blocks = static_cast<int>((n4 + 255) / 256 < 2 * ctx->sm_count ? (n4 + 255) / 256 : 2 * ctx->sm_count);
+  adam_flat_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n4, lr, scratch, beta1, beta2, eps);
+  CK_LAUNCH();
+  return COSKAD_OK;
+}
+
 extern "C" int coskad_train_col_sum(coskad_ctx* ctx, const float* a, int64_t B, int N, float* out, void* stream_) {
   TRAIN_PRE();
   if (B <= 0 || N <= 0) return COSKAD_OK;

@@ -1205,4 +1205,38 @@ __global__ void col_sum_kernel(const float* __restrict__ a, int64_t B, int N, fl
   }
 }
 
+// ---- Adam over ONE flat parameter buffer (dist.FlatGradBucket gradients, optim.FlatAdam) -------------------------------------
+// torch.optim.Adam(params, lr, betas, eps) with its defaults (no weight decay, no amsgrad) -- models/hyperbolic_encoder.py:199 --
+// in the arithmetic of torch's fused / capturable kernel: m = lerp(m, g, 1 - b1); v = b2 v + (1 - b2) g^2;
+// p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  torch's multi-tensor kernel takes two 22 us launches for the
+// encoder's 62 small tensors (240 k parameters); one pass over the flat buffers is a few microseconds.
+// tick: t += 1, sc[0] = 1 / (1 - b1^t), sc[1] = 1 / sqrt(1 - b2^t)  (one thread; ordered before the update by the stream)
+__global__ void adam_tick_kernel(int64_t* step, float* sc, float beta1, float beta2) {
+  const int64_t t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(t));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(t));
+  sc[0] = static_cast<float>(1.0 / bc1);
+  sc[1] = static_cast<float>(1.0 / sqrt(bc2));
+}
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 int64_t n4, const float* __restrict__ lr, const float* __restrict__ sc, float beta1, float beta2,
+                                 float eps) {
+  const float step_size = lr[0] * sc[0], inv_bc2s = sc[1];
+  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = fmaf(w1, ga[k] - ma[k], ma[k]);
+      va[k] = fmaf(w2 * ga[k], ga[k], beta2 * va[k]);
+      const float denom = fmaf(sqrtf(va[k]), inv_bc2s, eps);
+      pa[k] = pa[k] - step_size * (ma[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
 }  // namespace coskad

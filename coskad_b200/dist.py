@@ -55,7 +55,8 @@ class FlatGradBucket:
         if not self.params:
             return self
         if self.flat is None or self.flat.device != self.params[0].device:
-            self.flat = torch.zeros(self.numel, device=self.params[0].device, dtype=torch.float32)
+            # padded to a multiple of 4 floats: the flat Adam kernel (optim.FlatAdam) walks the buffers as float4
+            self.flat = torch.zeros((self.numel + 3) // 4 * 4, device=self.params[0].device, dtype=torch.float32)
             self.views, off = [], 0
             for p in self.params:
                 self.views.append(self.flat[off:off + p.numel()].view_as(p))

@@ -115,10 +115,24 @@ class TrainStep:
     def __init__(self, model: 'LightningModule', opt: torch.optim.Optimizer, bucket: 'cdist.FlatGradBucket',
                  device: torch.device) -> None:
         self.model, self.opt, self.bucket, self.device = model, opt, bucket, device
+        self.flat_adam = None                      # optim.FlatAdam, created at the first step (the bucket must be attached)
+        self._flat_tried = False
         self.graph_a: Optional[torch.cuda.CUDAGraph] = None
         self.graph_b: Optional[torch.cuda.CUDAGraph] = None
         self.static: Optional[List[torch.Tensor]] = None
         self.loss: Optional[torch.Tensor] = None
+
+    def _opt_step(self) -> None:
+        """the optimizer: one flat Adam kernel when ``opt`` is a plain Adam over the attached bucket (optim.FlatAdam), else opt.step()"""
+        if not self._flat_tried and self.device.type == 'cuda' and not torch.cuda.is_current_stream_capturing():
+            self._flat_tried = True
+            if not os.environ.get('COSKAD_NO_FLAT_ADAM'):
+                from .optim import FlatAdam
+                self.flat_adam = FlatAdam.wrap(self.opt, self.bucket)
+        if self.flat_adam is not None:
+            self.flat_adam.step()
+        else:
+            self.opt.step()
 
     def eager(self, batch, batch_idx: int) -> torch.Tensor:
         # a function of its own: no reference to the autograd graph (the loss) survives the step, so a later capture
@@ -127,7 +141,7 @@ class TrainStep:
         loss = self.model.training_step(batch, batch_idx)
         loss.backward()
         self.bucket.allreduce_()
-        self.opt.step()
+        self._opt_step()
         return loss.detach()
 
     @property
@@ -146,12 +160,12 @@ class TrainStep:
             loss = self.model.training_step(self.static, batch_idx)
             loss.backward()
             if not split:
-                self.opt.step()
+                self._opt_step()
         self.loss = loss.detach()                  # no reference to the autograd graph is kept
         if split:
             self.graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
-                self.opt.step()
+                self._opt_step()
 
     def matches(self, batch) -> bool:
         return self.static is not None and _same_layout(batch, self.static)

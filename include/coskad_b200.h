@@ -277,6 +277,12 @@ int coskad_train_mix_bwd_tc(coskad_ctx* ctx, const float* dout, const float* y1,
                             const double* red, const float* G, const float* X, const float* W1, const float* W2, int64_t B,
                             int CI, int CO, float* dy1, float* dy2, float* dG, float* dXres, float* dW1, float* db1,
                             float* dW2, float* db2, void* stream);
+/* One Adam step over flat buffers p, g, m, v [n] (n % 4 == 0, 16-byte aligned): step += 1 (int64 device scalar), then
+ * m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2; p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps); lr is a
+ * device scalar (schedulers update it in place; graph-replay safe), scratch is 2 device floats.
+ * replaces: torch.optim.Adam(self.parameters(), lr=opt_lr) . step(), models/hyperbolic_encoder.py:199 (defaults: no weight decay) */
+int coskad_adam_step(coskad_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1,
+                     float beta2, float eps, int64_t* step, float* scratch, void* stream);
 /* 1 (default): coskad_train_mix_fwd runs on the tensor cores; 0: the FP32 CUDA-core kernels (A/B measurement).  Every
  * cross-CTA reduction of the training path (BatchNorm statistics, weight / bias / graph-operator gradients, linear heads)
  * is a fixed-order two-stage sum through a ctx-owned workspace: two runs on the same inputs are bit-identical.  The

@@ -6,6 +6,7 @@
     COSKAD_TB_NOAR=1 / COSKAD_TB_FOREACH=1                       A/B switches: skip the all-reduce / for-each instead of fused Adam
     COSKAD_TRAIN_IMPL=0                                          A/B: the FP32 CUDA-core convolution kernels instead of tcgen05
     COSKAD_TB_NODIRECT=1                                         A/B: gradients handed to autograd instead of accumulated into the bucket views
+    COSKAD_NO_FLAT_ADAM=1                                        A/B: torch's fused multi-tensor Adam instead of the flat Adam kernel
 """
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -37,6 +38,12 @@ c = torch.zeros(16, device=dev); c[0] = 0.1
 acc = gmath.center_accumulator(16, dev)
 DIRECT = not os.environ.get('COSKAD_TB_NODIRECT')         # A/B: COSKAD_TB_NODIRECT=1 = gradients through autograd's AccumulateGrad
 
+flat_adam = None
+if DIRECT and not os.environ.get('COSKAD_NO_FLAT_ADAM'):   # what trainer.TrainStep does: one flat Adam kernel instead of torch's multi-tensor step
+    from coskad_b200.optim import FlatAdam
+    bucket.attach()
+    flat_adam = FlatAdam.wrap(opt, bucket)
+
 def step():
     hidden = m(x)
     reg = calc_reg_loss(m)
@@ -48,7 +55,8 @@ def step():
     loss.backward()
     if not os.environ.get('COSKAD_TB_NOAR'):
         bucket.allreduce_()                               # flat NCCL all-reduce of the gradients (no-op on one GPU)
-    opt.step()
+    if flat_adam is not None: flat_adam.step()
+    else: opt.step()
     return loss
 
 if GRAPH:
