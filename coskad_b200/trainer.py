@@ -130,6 +130,11 @@ class TrainStep:
                 from .optim import FlatAdam
                 self.flat_adam = FlatAdam.wrap(self.opt, self.bucket)
         if self.flat_adam is not None:
+            if not torch.cuda.is_current_stream_capturing() and not self.flat_adam.intact():
+                # e.g. module.to() / zero_grad(set_to_none=True) after the first step: the flat buffers no longer alias the
+                # parameters -- updating them would silently train nothing
+                raise RuntimeError('the parameters / gradients are no longer views of the flat buffers optim.FlatAdam updates; '
+                                   'set COSKAD_NO_FLAT_ADAM=1 to keep torch.optim.Adam.step()')
             self.flat_adam.step()
         else:
             self.opt.step()

@@ -42,3 +42,19 @@ def test_batch_layout_guard():
     assert _flat_tensors(a) and _same_layout(a, [torch.empty_like(t) for t in a])
     assert not _same_layout([a[0][:5], a[1][:5]], a)                # ragged last batch -> eager step
     assert not _flat_tensors([a, a]) and not _flat_tensors([])     # nested batches (dataset_double_item) stay eager
+
+
+def test_flat_adam_is_only_used_for_a_plain_cuda_adam_over_an_attached_bucket():
+    """optim.FlatAdam.wrap declines (-> the caller keeps opt.step()) for CPU parameters, other optimizers, weight decay and
+    unattached buckets: nothing of it runs without a GPU"""
+    import torch
+    from coskad_b200 import dist as cdist
+    from coskad_b200.optim import FlatAdam
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
+    bucket = cdist.FlatGradBucket(ps)
+    assert FlatAdam.wrap(torch.optim.Adam(ps, lr=1e-3), bucket) is None            # bucket not attached
+    bucket.attach()
+    assert bucket.flat.numel() % 4 == 0 and bucket.flat.numel() >= 17               # padded for the float4 kernel
+    assert FlatAdam.wrap(torch.optim.Adam(ps, lr=1e-3), bucket) is None            # CPU parameters
+    assert FlatAdam.wrap(torch.optim.SGD(ps, lr=1e-3), bucket) is None
+    assert FlatAdam.wrap(None, bucket) is None
