@@ -58,3 +58,31 @@ def test_flat_adam_is_only_used_for_a_plain_cuda_adam_over_an_attached_bucket():
     assert FlatAdam.wrap(torch.optim.Adam(ps, lr=1e-3), bucket) is None            # CPU parameters
     assert FlatAdam.wrap(torch.optim.SGD(ps, lr=1e-3), bucket) is None
     assert FlatAdam.wrap(None, bucket) is None
+
+
+def test_regulariser_accumulates_into_marked_grad_views_like_autograd():
+    """losses._L2Reg: with parameters marked by FlatGradBucket.attach() the regulariser's gradient goes into the bucket views with
+    one multi-tensor add (and autograd gets None); unmarked parameters take the ordinary path.  Same numbers either way."""
+    import torch
+    from coskad_b200 import dist as cdist
+    from coskad_b200.losses import calc_reg_loss
+
+    def make():
+        torch.manual_seed(3)
+        m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 2))
+        return m
+
+    a, b = make(), make()
+    (calc_reg_loss(a) * 0.37).backward()
+    bucket = cdist.FlatGradBucket(b.parameters()).attach()
+    bucket.zero_()
+    assert all(getattr(p, 'coskad_direct_grad', False) for p in b.parameters())
+    (calc_reg_loss(b) * 0.37).backward()
+    for (n, p), q in zip(a.named_parameters(), b.parameters()):
+        if 'bias' in n:
+            assert p.grad is None and float(q.grad.abs().sum()) == 0.0          # biases are not regularised (model_utils.py:92)
+        else:
+            assert torch.equal(p.grad, q.grad), n
+        assert q.grad.data_ptr() >= bucket.flat.data_ptr()                      # still a view of the bucket
+    bucket.detach()
+    assert all(p.grad is None and not p.coskad_direct_grad for p in b.parameters())
